@@ -1,0 +1,207 @@
+"""ctypes wrapper around the CPU oracle (oracle/lfit_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+CPU legs of bench.py -- never by lfit_python_b200/.  PARITY UNPINNED: the
+reference's arithmetic (`lfit`, `trm.roche`; /root/reference/CVModel.py:13,15)
+is not vendored, so this oracle is the repo's own restatement.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liblfit_oracle.so")
+
+NPAR = 18
+FLAG_INCL, SKIP_WD, SKIP_DISC, SKIP_BS, SKIP_DONOR = 1, 2, 4, 8, 16
+SOLVER_ROBUST, SOLVER_NEWTON = 0, 1
+PRIOR_TYPES = {"gauss": 0, "gaussPos": 1, "uniform": 2, "log_uniform": 3, "mod_jeff": 4}
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("n_wd_rings", C.c_int), ("n_disc_r", C.c_int), ("n_disc_th", C.c_int), ("n_bs", C.c_int),
+        ("n_donor_th", C.c_int), ("n_quad", C.c_int), ("donor_ulimb", C.c_double),
+        ("donor_gdexp", C.c_double), ("solver", C.c_int),
+    ]
+
+
+class Layout(C.Structure):
+    _fields_ = [
+        ("ndim", C.c_int), ("n_ecl", C.c_int), ("npars", C.c_int),
+        ("gather", C.POINTER(C.c_int)), ("consts", C.POINTER(C.c_double)),
+        ("n_prior", C.c_int), ("prior_src", C.POINTER(C.c_int)), ("prior_type", C.POINTER(C.c_int)),
+        ("prior_p1", C.POINTER(C.c_double)), ("prior_p2", C.POINTER(C.c_double)),
+        ("prior_norm", C.POINTER(C.c_double)), ("prior_isvar", C.POINTER(C.c_int)),
+        ("lc_off", C.POINTER(C.c_longlong)), ("lc_phase", C.POINTER(C.c_double)),
+        ("lc_width", C.POINTER(C.c_double)), ("lc_y", C.POINTER(C.c_double)),
+        ("lc_ye", C.POINTER(C.c_double)),
+    ]
+
+
+def build(force=False):
+    """Compile the oracle with the Makefile next to this file."""
+    if force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+        for f in ("lfit_oracle.c", "lfit_oracle.h", "roche_core.h")
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        _lib.lfo_default_config.argtypes = [C.POINTER(Config)]
+        _lib.lfo_roche_xl1.argtypes = [C.c_double, dp]
+        _lib.lfo_roche_findphi.argtypes = [C.c_double, C.c_double, dp]
+        _lib.lfo_roche_findi.argtypes = [C.c_double, C.c_double, dp]
+        _lib.lfo_roche_bspot.argtypes = [C.c_double, C.c_double, dp]
+        _lib.lfo_roche_ingress_egress.argtypes = [C.c_double, C.c_double, dp, C.c_double, C.c_double,
+                                                  C.c_int, dp, dp]
+        _lib.lfo_calc_flux.argtypes = [C.POINTER(Config), dp, C.c_int, C.c_int, C.c_int, dp, dp,
+                                       dp, dp, dp, dp, dp]
+        _lib.lfo_chisq.argtypes = [C.POINTER(Config), dp, C.c_int, C.c_int, dp, dp, dp, dp]
+        _lib.lfo_chisq.restype = C.c_double
+        _lib.lfo_prior_ln_prob.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+        _lib.lfo_prior_ln_prob.restype = C.c_double
+        _lib.lfo_log_prob.argtypes = [C.POINTER(Config), C.POINTER(Layout), C.c_int, C.c_longlong, dp,
+                                      dp, dp, C.c_int]
+        _lib.lfo_max_threads.restype = C.c_int
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def config(**kw):
+    cfg = Config()
+    lib().lfo_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise KeyError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+class RocheError(Exception):
+    pass
+
+
+def xl1(q):
+    out = C.c_double()
+    if lib().lfo_roche_xl1(q, C.byref(out)):
+        raise RocheError("xl1: q must be > 0")
+    return out.value
+
+
+def findphi(q, incl_deg):
+    out = C.c_double()
+    if lib().lfo_roche_findphi(q, incl_deg, C.byref(out)):
+        raise RocheError("findphi failed")
+    return out.value
+
+
+def findi(q, dphi):
+    out = C.c_double()
+    if lib().lfo_roche_findi(q, dphi, C.byref(out)):
+        raise RocheError("findi: no inclination gives that eclipse width")
+    return out.value
+
+
+def bspot(q, rad):
+    out = (C.c_double * 4)()
+    if lib().lfo_roche_bspot(q, rad, out):
+        raise RocheError("bspot: stream does not reach that radius")
+    return tuple(out)
+
+
+def ingress_egress(q, incl_deg, p0, xi=0.0, eta=0.0, solver=SOLVER_NEWTON):
+    a, b = C.c_double(), C.c_double()
+    p = (C.c_double * 3)(*p0)
+    r = lib().lfo_roche_ingress_egress(q, incl_deg, p, xi, eta, solver, C.byref(a), C.byref(b))
+    if r < 0:
+        raise RocheError("bad q")
+    return (a.value, b.value) if r else None
+
+
+def calc_flux(pars, phase, width=None, cfg=None, flags=0, components=False):
+    """lfit.CV(pars).calcFlux(pars, phase, width) on the CPU oracle."""
+    cfg = cfg or config()
+    pars = np.ascontiguousarray(pars, dtype=np.float64)
+    phase = np.ascontiguousarray(phase, dtype=np.float64)
+    n = phase.shape[0]
+    if width is None:
+        width = np.zeros(n)
+    width = np.ascontiguousarray(np.broadcast_to(np.asarray(width, dtype=np.float64), (n,)))
+    tot = np.empty(n)
+    comps = [np.empty(n) for _ in range(4)] if components else [None] * 4
+    st = lib().lfo_calc_flux(C.byref(cfg), _dp(pars), pars.shape[0], flags, n, _dp(phase), _dp(width),
+                             _dp(tot), *[_dp(c) for c in comps])
+    if components:
+        return st, tot, comps
+    return st, tot
+
+
+def chisq(pars, phase, width, y, ye, cfg=None):
+    cfg = cfg or config()
+    pars = np.ascontiguousarray(pars, dtype=np.float64)
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (phase, width, y, ye)]
+    return lib().lfo_chisq(C.byref(cfg), _dp(pars), pars.shape[0], arrs[0].shape[0], *[_dp(a) for a in arrs])
+
+
+def prior_ln_prob(ptype, p1, p2, norm, val):
+    return lib().lfo_prior_ln_prob(PRIOR_TYPES[ptype] if isinstance(ptype, str) else ptype, p1, p2, norm, val)
+
+
+class FlatLayout:
+    """Owns the numpy arrays behind an lfo_layout (same fields as the C-ABI's set_* calls)."""
+
+    def __init__(self, ndim, npars, gather, consts, prior_src, prior_type, prior_p1, prior_p2,
+                 prior_norm, prior_isvar, lc_off, lc_phase, lc_width, lc_y, lc_ye):
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self.gather = i32(gather).reshape(-1, NPAR)
+        self.consts = f64(consts) if len(consts) else np.zeros(1)
+        self.prior_src, self.prior_type, self.prior_isvar = i32(prior_src), i32(prior_type), i32(prior_isvar)
+        self.prior_p1, self.prior_p2, self.prior_norm = f64(prior_p1), f64(prior_p2), f64(prior_norm)
+        self.lc_off = np.ascontiguousarray(lc_off, dtype=np.int64)
+        self.lc_phase, self.lc_width, self.lc_y, self.lc_ye = f64(lc_phase), f64(lc_width), f64(lc_y), f64(lc_ye)
+        self.ndim, self.npars, self.n_ecl = int(ndim), int(npars), self.gather.shape[0]
+        L = Layout()
+        L.ndim, L.n_ecl, L.npars = self.ndim, self.n_ecl, self.npars
+        L.gather, L.consts = _ip(self.gather), _dp(self.consts)
+        L.n_prior = self.prior_src.shape[0]
+        L.prior_src, L.prior_type, L.prior_isvar = _ip(self.prior_src), _ip(self.prior_type), _ip(self.prior_isvar)
+        L.prior_p1, L.prior_p2, L.prior_norm = _dp(self.prior_p1), _dp(self.prior_p2), _dp(self.prior_norm)
+        L.lc_off = self.lc_off.ctypes.data_as(C.POINTER(C.c_longlong))
+        L.lc_phase, L.lc_width, L.lc_y, L.lc_ye = _dp(self.lc_phase), _dp(self.lc_width), _dp(self.lc_y), _dp(self.lc_ye)
+        self.c = L
+
+
+def log_prob(layout, theta, what=2, cfg=None, nthreads=0, return_chisq=False):
+    cfg = cfg or config()
+    theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+    n = theta.shape[0]
+    assert theta.shape[1] == layout.ndim
+    out = np.empty(n)
+    chis = np.empty((n, layout.n_ecl)) if return_chisq else None
+    lib().lfo_log_prob(C.byref(cfg), C.byref(layout.c), what, n, _dp(theta), _dp(out), _dp(chis), nthreads)
+    return (out, chis) if return_chisq else out
+
+
+def max_threads():
+    return lib().lfo_max_threads()
