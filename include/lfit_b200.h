@@ -1,0 +1,125 @@
+/*
+ * include/lfit_b200.h -- C ABI of the B200 (sm_100a) LFIT CV eclipse-model engine.
+ *
+ * This is the drop-in boundary for the one hot path of wildjames/lfit_python:
+ * evaluating lfit.CV(pars).calcFlux(pars, phase, width) and its chi-squared /
+ * log-probability for every emcee walker.  Plain pointers and sizes only; no
+ * torch types.  Every entry point names the reference interface it replaces
+ * (file:line under /root/reference).  The reference binds this path through
+ * Cython (`import lfit`, CVModel.py:13) and a CPython extension (`from trm
+ * import roche`, CVModel.py:15); the ctypes stub that replaces both is
+ * lfit_python_b200/_cabi.py and is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - all functions return 0 on success, a negative LFB_E* code on failure;
+ *    lfb_last_error() gives the message.  An INVALID MODEL IS DATA, not an
+ *    error: -inf log-probability / +inf chi-squared / NaN flux, as the reference
+ *    produces at CVModel.py:139-144,163-171 and model.py:489-493.
+ *  - there is no CPU fallback: every call needs a CUDA device.
+ *  - pointers marked "host or device" are classified with
+ *    cudaPointerGetAttributes; host buffers are staged through pinned memory.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream).
+ *  - a handle is not thread-safe; use one per GPU / rank.
+ */
+#ifndef LFIT_B200_H
+#define LFIT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFB_NPAR 18 /* CV parameter slots, order of ComplexEclipse.cv_parnames (CVModel.py:383-390) */
+
+enum {
+    LFB_OK = 0,
+    LFB_EINVAL = -1,   /* bad argument (shape, count, NULL) */
+    LFB_ECUDA = -2,    /* CUDA runtime error */
+    LFB_ESTATE = -3,   /* call order: layout / lightcurves not set */
+    LFB_ENOMEM = -4
+};
+
+/* lfb_calc_flux flags */
+enum {
+    LFB_FLAG_INCL = 1,      /* slot 5 (dphi) holds the inclination in degrees: the lfit.Py* component API (testCV.py:44-49) */
+    LFB_FLAG_SKIP_WD = 2,
+    LFB_FLAG_SKIP_DISC = 4,
+    LFB_FLAG_SKIP_BS = 8,
+    LFB_FLAG_SKIP_DONOR = 16
+};
+
+/* prior codes = Prior.type (model.py:70) */
+enum { LFB_PRIOR_GAUSS = 0, LFB_PRIOR_GAUSSPOS, LFB_PRIOR_UNIFORM, LFB_PRIOR_LOGUNIFORM, LFB_PRIOR_MODJEFF };
+
+/* lfb_log_prob `what` = the three wrappers of mcmcfit.py:30-48 */
+enum { LFB_LN_PRIOR = 0, LFB_LN_LIKE = 1, LFB_LN_PROB = 2 };
+
+/* lfb_roche `which` = trm.roche calls on the path (CVModel.py:222,288,460,561) */
+enum { LFB_ROCHE_XL1 = 0, LFB_ROCHE_FINDPHI = 1, LFB_ROCHE_FINDI = 2, LFB_ROCHE_BSPOT = 3 };
+
+/* Surface-grid density (the element counts the lfit component constructors take,
+ * testCV.py:31,43).  Zero / NULL selects the defaults in brackets. */
+typedef struct {
+    int n_wd_rings;      /* [10]  white dwarf: 4*n^2 sky tiles */
+    int n_disc_r;        /* [25]  disc rings  */
+    int n_disc_th;       /* [40]  disc sectors (even): 25*40 = 1000 = testCV.py:31 */
+    int n_bs;            /* [200] bright-spot strip elements */
+    int n_donor_th;      /* [18]  donor rings -> 412 tiles (testCV.py:43 asks for 400) */
+    int n_quad;          /* [3]   exposure quadrature points (odd; Simpson) */
+    double donor_ulimb;  /* [0.8] */
+    double donor_gdexp;  /* [0.32] */
+} lfb_config;
+
+typedef struct lfb_handle lfb_handle;
+
+/* lfit.CV.__init__ (CVModel.py:128): allocate an engine on CUDA device `device`. */
+int lfb_create(int device, const lfb_config *cfg, lfb_handle **out);
+void lfb_destroy(lfb_handle *h);
+const char *lfb_last_error(const lfb_handle *h); /* h may be NULL: last create() error */
+int lfb_get_config(const lfb_handle *h, lfb_config *out);
+
+/* The flattened tree: replaces the per-walker traversal of
+ * Node.__set_parameter_vector__ (model.py:586-603) + SimpleEclipse.cv_parlist
+ * (CVModel.py:335-354).  gather[e*18+k] >= 0: column of theta; < 0: consts[-g-1].
+ * npars is 14 (SimpleEclipse) or 18 (ComplexEclipse). */
+int lfb_set_layout(lfb_handle *h, int ndim, int n_ecl, int npars, const int *gather, int n_consts,
+                   const double *consts);
+
+/* Every Param of the tree with its Prior (model.py:40-141, Node.ln_prior model.py:426-474). */
+int lfb_set_priors(lfb_handle *h, int n_prior, const int *src, const int *type, const double *p1,
+                   const double *p2, const double *norm, const int *isvar);
+
+/* Lightcurve.x/.w/.y/.ye of every leaf (CVModel.py:20-83), concatenated; copied once to HBM. */
+int lfb_set_lightcurves(lfb_handle *h, int n_ecl, const long long *off, const double *phase,
+                        const double *width, const double *y, const double *ye);
+
+/* mcmcfit.ln_prior / ln_like / ln_prob (mcmcfit.py:30-48) for n walkers at once.
+ * theta: row-major f64[n][ndim], host or device.  out: f64[n], host or device.
+ * chisq_out (optional): f64[n][n_ecl] per-leaf SimpleEclipse.chisq (CVModel.py:157-178). */
+int lfb_log_prob(lfb_handle *h, int what, long long n, const double *theta, double *out,
+                 double *chisq_out, void *stream);
+
+/* lfit.CV.calcFlux(pars, phase, width) (CVModel.py:138,154; plot_lc_model.py:134) for n_sets
+ * parameter sets sharing one phase grid.  pars: f64[n_sets][npars] (host or device), phase/width:
+ * f64[n_ph] host.  out_total: f64[n_sets][n_ph]; out_comp (optional): f64[4][n_sets][n_ph] in
+ * the order ywd, yd, ys, yrs (the scaled contributions, plot_lc_model.py:135-138). */
+int lfb_calc_flux(lfb_handle *h, long long n_sets, const double *pars, int npars, int flags, int n_ph,
+                  const double *phase, const double *width, double *out_total, double *out_comp,
+                  void *stream);
+
+/* trm.roche.{xl1(q), findphi(q,i), findi(q,dphi), bspot(q,rad)} batched on the device.
+ * a: first argument (q), b: second argument (ignored for xl1); out: f64[n][4]
+ * (xl1 / dphi / incl_deg in out[.][0]; bspot -> x, y, vx, vy); ok[n]: 1 = value, 0 = the
+ * reference would raise (CVModel.py:223,309). */
+int lfb_roche(lfb_handle *h, int which, long long n, const double *a, const double *b, double *out,
+              int *ok);
+
+/* counters for bench.py: kernels launched by this handle since creation */
+long long lfb_launch_count(const lfb_handle *h);
+/* device time (ms) of the last lfb_log_prob's lightcurve kernel, measured with CUDA events on
+ * the stream it ran on; valid after the stream is synchronised.  <0 if none. */
+float lfb_last_kernel_ms(lfb_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,219 @@
+"""ctypes binding of include/lfit_b200.h -- the only way Python reaches the CUDA engine.
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is
+present every entry point raises.  The reference binds the same path through
+Cython (`import lfit`, /root/reference/CVModel.py:13) and the `trm.roche`
+C extension (CVModel.py:15).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+NPAR = 18
+LN_PRIOR, LN_LIKE, LN_PROB = 0, 1, 2
+FLAG_INCL, FLAG_SKIP_WD, FLAG_SKIP_DISC, FLAG_SKIP_BS, FLAG_SKIP_DONOR = 1, 2, 4, 8, 16
+ROCHE_XL1, ROCHE_FINDPHI, ROCHE_FINDI, ROCHE_BSPOT = 0, 1, 2, 3
+PRIOR_CODES = {"gauss": 0, "gaussPos": 1, "uniform": 2, "log_uniform": 3, "mod_jeff": 4}
+
+EXPORTS = (
+    "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_get_config", "lfb_set_layout",
+    "lfb_set_priors", "lfb_set_lightcurves", "lfb_log_prob", "lfb_calc_flux", "lfb_roche",
+    "lfb_launch_count", "lfb_last_kernel_ms",
+)
+
+
+class EngineError(RuntimeError):
+    """The CUDA engine reported an error (or cannot run at all)."""
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("n_wd_rings", C.c_int), ("n_disc_r", C.c_int), ("n_disc_th", C.c_int), ("n_bs", C.c_int),
+        ("n_donor_th", C.c_int), ("n_quad", C.c_int), ("donor_ulimb", C.c_double), ("donor_gdexp", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load():
+    """dlopen the in-tree library, declaring every prototype of include/lfit_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise EngineError(
+            "CUDA library %s is not built (run `python -m lfit_python_b200._build`); "
+            "there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    lib.lfb_create.argtypes = [C.c_int, C.POINTER(Config), C.POINTER(vp)]
+    lib.lfb_destroy.argtypes = [vp]
+    lib.lfb_destroy.restype = None
+    lib.lfb_last_error.argtypes = [vp]
+    lib.lfb_last_error.restype = C.c_char_p
+    lib.lfb_get_config.argtypes = [vp, C.POINTER(Config)]
+    lib.lfb_set_layout.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, C.c_int, dp]
+    lib.lfb_set_priors.argtypes = [vp, C.c_int, ip, ip, dp, dp, dp, ip]
+    lib.lfb_set_lightcurves.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong), dp, dp, dp, dp]
+    lib.lfb_log_prob.argtypes = [vp, C.c_int, C.c_longlong, vp, vp, vp, vp]
+    lib.lfb_calc_flux.argtypes = [vp, C.c_longlong, vp, C.c_int, C.c_int, C.c_int, dp, dp, vp, vp, vp]
+    lib.lfb_roche.argtypes = [vp, C.c_int, C.c_longlong, dp, dp, dp, ip]
+    lib.lfb_launch_count.argtypes = [vp]
+    lib.lfb_launch_count.restype = C.c_longlong
+    lib.lfb_last_kernel_ms.argtypes = [vp]
+    lib.lfb_last_kernel_ms.restype = C.c_float
+    _lib = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class Engine:
+    """One lfb_handle: an engine bound to one CUDA device."""
+
+    def __init__(self, device=0, **grid):
+        self._lib = load()
+        cfg = Config()
+        for k, v in grid.items():
+            if not hasattr(cfg, k):
+                raise TypeError("unknown grid option %r" % k)
+            setattr(cfg, k, v)
+        h = C.c_void_p()
+        rc = self._lib.lfb_create(int(device), C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise EngineError("lfb_create failed (%d): %s" % (rc, self._lib.lfb_last_error(None).decode()))
+        self._h = h
+        self.device = int(device)
+        self.ndim = self.n_ecl = self.npars = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lfb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError("%s failed (%d): %s" % (what, rc, self._lib.lfb_last_error(self._h).decode()))
+
+    @property
+    def config(self):
+        cfg = Config()
+        self._check(self._lib.lfb_get_config(self._h, C.byref(cfg)), "lfb_get_config")
+        return {k: getattr(cfg, k) for k, _ in Config._fields_}
+
+    @property
+    def launch_count(self):
+        return int(self._lib.lfb_launch_count(self._h))
+
+    def last_kernel_ms(self):
+        return float(self._lib.lfb_last_kernel_ms(self._h))
+
+    # -- flattened tree -----------------------------------------------------------------
+    def set_layout(self, ndim, npars, gather, consts):
+        gather = _i32(gather).reshape(-1, NPAR)
+        consts = _f64(consts).ravel()
+        self._check(self._lib.lfb_set_layout(self._h, int(ndim), gather.shape[0], int(npars), _ip(gather),
+                                             consts.shape[0], _dp(consts) if consts.size else None),
+                    "lfb_set_layout")
+        self.ndim, self.n_ecl, self.npars = int(ndim), gather.shape[0], int(npars)
+
+    def set_priors(self, src, ptype, p1, p2, norm, isvar):
+        src, ptype, isvar = _i32(src), _i32(ptype), _i32(isvar)
+        p1, p2, norm = _f64(p1), _f64(p2), _f64(norm)
+        self._check(self._lib.lfb_set_priors(self._h, src.shape[0], _ip(src), _ip(ptype), _dp(p1), _dp(p2),
+                                             _dp(norm), _ip(isvar)), "lfb_set_priors")
+
+    def set_lightcurves(self, off, phase, width, y, ye):
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        phase, width, y, ye = _f64(phase), _f64(width), _f64(y), _f64(ye)
+        self._check(self._lib.lfb_set_lightcurves(self._h, off.shape[0] - 1,
+                                                  off.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                                  _dp(phase), _dp(width), _dp(y), _dp(ye)), "lfb_set_lightcurves")
+
+    # -- hot path -----------------------------------------------------------------------
+    def log_prob(self, theta, what=LN_PROB, return_chisq=False):
+        """theta: (n, ndim) host array -> ln-values (n,) [and chisq (n, n_ecl)]."""
+        theta = _f64(theta)
+        if theta.ndim != 2 or theta.shape[1] != self.ndim:
+            raise ValueError("Wrong vector length - Expected {}, got {}".format(self.ndim, theta.shape[-1]))
+        n = theta.shape[0]
+        out = np.empty(n)
+        chis = np.empty((n, self.n_ecl)) if return_chisq else None
+        self._check(self._lib.lfb_log_prob(self._h, int(what), n, theta.ctypes.data, out.ctypes.data,
+                                           chis.ctypes.data if return_chisq else None, None), "lfb_log_prob")
+        return (out, chis) if return_chisq else out
+
+    def log_prob_device(self, theta_ptr, n, out_ptr, what=LN_PROB, chisq_ptr=None, stream=None):
+        """Raw-pointer variant (device or host pointers, e.g. torch tensors' data_ptr())."""
+        self._check(self._lib.lfb_log_prob(self._h, int(what), int(n), theta_ptr, out_ptr, chisq_ptr, stream),
+                    "lfb_log_prob")
+
+    def calc_flux(self, pars, phase, width=None, flags=0, components=False):
+        pars = _f64(pars)
+        single = pars.ndim == 1
+        pars = np.atleast_2d(pars)
+        if pars.shape[1] not in (14, 18):
+            raise ValueError("CV takes 14 (simple BS) or 18 (complex BS) parameters, got %d" % pars.shape[1])
+        phase = _f64(phase).ravel()
+        n_ph = phase.shape[0]
+        if width is None:
+            width = np.zeros(n_ph)
+        width = _f64(np.broadcast_to(np.asarray(width, dtype=np.float64), (n_ph,)))
+        n = pars.shape[0]
+        tot = np.empty((n, n_ph))
+        comp = np.empty((4, n, n_ph)) if components else None
+        self._check(self._lib.lfb_calc_flux(self._h, n, pars.ctypes.data, pars.shape[1], int(flags), n_ph, _dp(phase),
+                                            _dp(width), tot.ctypes.data, comp.ctypes.data if components else None,
+                                            None), "lfb_calc_flux")
+        if single:
+            tot = tot[0]
+            comp = comp[:, 0] if components else None
+        return (tot, comp) if components else tot
+
+    def roche(self, which, a, b=None):
+        a = _f64(np.atleast_1d(a))
+        b = _f64(np.broadcast_to(np.atleast_1d(0.0 if b is None else b), a.shape))
+        out = np.empty((a.shape[0], 4))
+        ok = np.empty(a.shape[0], dtype=np.int32)
+        self._check(self._lib.lfb_roche(self._h, int(which), a.shape[0], _dp(a), _dp(b), _dp(out), _ip(ok)),
+                    "lfb_roche")
+        return out, ok.astype(bool)
+
+
+_default_engines = {}
+
+
+def default_engine(device=0):
+    """Process-wide engine with the default surface grid (created on first use)."""
+    if device not in _default_engines:
+        _default_engines[device] = Engine(device)
+    return _default_engines[device]

@@ -1,0 +1,1031 @@
+// lfit_kernels.cu -- sm_100a kernels + C ABI (include/lfit_b200.h) for the LFIT CV
+// eclipse model: lfit.CV.calcFlux / chi-squared / log-probability for every walker.
+//
+// Reference interfaces replaced (file:line under /root/reference):
+//   lfit.CV(pars).calcFlux(pars, phase, width)         CVModel.py:128,138
+//   SimpleEclipse.chisq / ln_like                       CVModel.py:157-191
+//   LCModel.ln_prior / SimpleEclipse.ln_prior           CVModel.py:440-491,193-324
+//   Node.ln_prior / Node.ln_prob, Prior.ln_prob         model.py:426-498,83-113
+//   mcmcfit.ln_prior / ln_like / ln_prob                mcmcfit.py:30-48
+//   trm.roche.xl1 / findphi / findi / bspot             CVModel.py:222,288,460,561
+//
+// Kernel pipeline of one lfb_log_prob call (all FP64, no tensor cores: the work is
+// root finding and masked sums, not a contraction):
+//   walker_kernel  one thread per walker: L1, Phi_c, inclination from (q, dphi), the
+//                  Param priors and the scalar validity rules
+//   stream_kernel  one thread per (walker, eclipse): ballistic stream -> bright-spot
+//                  impact point, azimuth validity rule
+//   lightcurve_kernel  one CTA per (walker, eclipse): (1) ingress/egress phases of every
+//                  white-dwarf / disc / bright-spot element from the Roche LOS solve and
+//                  the donor's surface tiles, kept in shared memory; (2) visible flux per
+//                  exposure sample; (3) weighted component sum; (4) chi-squared reduction
+//   finish_kernel  one thread per walker: ln_prior - chi^2/2 with the -inf rules
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lfit_b200.h"
+#include "roche_device.cuh"
+
+namespace {
+
+using namespace lfb;
+
+enum { P_WDFLUX = 0, P_DFLUX, P_SFLUX, P_RSFLUX, P_Q, P_DPHI, P_RDISC, P_ULIMB, P_RWD, P_SCALE, P_AZ,
+       P_FIS, P_DEXP, P_PHI0, P_EXP1, P_EXP2, P_TILT, P_YAW };
+
+constexpr int kThreads = 256;
+constexpr int kMaxDonorRings = 128;
+constexpr int kMaxQuad = 15;
+
+struct DevLayout {
+    int ndim, n_ecl, npars, n_prior;
+    const int* gather;
+    const double* consts;
+    const int *psrc, *ptype, *pisvar;
+    const double *pp1, *pp2, *pnorm;
+};
+
+struct DevLC {
+    const long long* off;
+    const double *phase, *width, *y, *ye;
+};
+
+struct GridCfg {
+    int n_wd_rings, n_wd, n_disc_r, n_disc_th, n_disc, n_bs, n_donor_th, n_donor_q, n_quad;
+    double donor_ulimb, donor_gdexp;
+    const int* donor_ring_off;  // [n_donor_th + 1] offsets of each ring's quarter tiles
+    double quad_off[kMaxQuad], quad_w[kMaxQuad];
+};
+
+struct WalkerScal {
+    Roche R;
+    double si, ci;
+    double lnprior;
+    int status;  // 0: a model exists; else the parameters admit none
+};
+
+struct JobScal {
+    double xs, ys;
+    int status;
+};
+
+__device__ __forceinline__ double fetch(const DevLayout& L, const double* th, int src)
+{
+    return src >= 0 ? th[src] : L.consts[-src - 1];
+}
+
+// ---------------------------------------------------------------- walker_kernel
+__global__ void walker_kernel(DevLayout L, int what, int flags, long long n, const double* __restrict__ theta,
+                              WalkerScal* __restrict__ ws)
+{
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    const double* th = theta + w * L.ndim;
+    WalkerScal W;
+    W.status = 0;
+    W.lnprior = 0.0;
+    W.si = 1.0;
+    W.ci = 0.0;
+    double q = fetch(L, th, L.gather[P_Q]), dphi = fetch(L, th, L.gather[P_DPHI]);
+    double maxphi = 0.0;
+    if (!isfinite(q) || !isfinite(dphi) || !roche_init(q, W.R)) {
+        W.status = 1;
+        W.R.mu = W.R.omu = W.R.xl1 = W.R.rs = W.R.phic = W.R.rin = 0.0;
+    } else if (flags & LFB_FLAG_INCL) {
+        if (!(dphi > 0.0) || !(dphi <= 90.0)) W.status = 1;
+        else sincos_(dphi * kDeg, &W.si, &W.ci);
+    } else {
+        maxphi = findphi90(W.R);
+        if (!findi(W.R, dphi, maxphi, W.si)) W.status = 1;
+        else W.ci = sqrt(1.0 - W.si * W.si);
+    }
+    if (what != LFB_LN_LIKE) {
+        double lnp = 0.0;
+        // LCModel.ln_prior (CVModel.py:440-491): roche failure or dphi beyond the edge-on width
+        if (!isfinite(q) || !(q > 0.0) || !(q < 1e6)) lnp = -INFINITY;
+        else if (!(dphi <= maxphi - 1e-6)) lnp = -INFINITY;
+        // Node.ln_prior (model.py:426-474): any invalid Param -> -inf, variable ones add up
+        for (int k = 0; k < L.n_prior && lnp > -INFINITY; ++k) {
+            double lp = prior_ln_prob(L.ptype[k], L.pp1[k], L.pp2[k], L.pnorm[k], fetch(L, th, L.psrc[k]));
+            if (!isfinite(lp)) lnp = -INFINITY;
+            else if (L.pisvar[k]) lnp += lp;
+        }
+        // SimpleEclipse.ln_prior (CVModel.py:217-276): disc radius and spot scale windows
+        for (int e = 0; e < L.n_ecl && lnp > -INFINITY; ++e) {
+            const int* g = L.gather + e * LFB_NPAR;
+            double rdisc = fetch(L, th, g[P_RDISC]), rwd = fetch(L, th, g[P_RWD]), scale = fetch(L, th, g[P_SCALE]);
+            if (!(rdisc * W.R.xl1 <= 0.46)) lnp = -INFINITY;
+            if (!(scale <= rwd * 3.0) || !(scale >= rwd / 3.0)) lnp = -INFINITY;
+        }
+        W.lnprior = lnp;
+    }
+    ws[w] = W;
+}
+
+// ---------------------------------------------------------------- stream_kernel
+__global__ void stream_kernel(DevLayout L, int what, int flags, long long njobs, const double* __restrict__ theta,
+                              WalkerScal* ws, JobScal* __restrict__ js)
+{
+    long long job = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (job >= njobs) return;
+    long long w = job / L.n_ecl;
+    int e = (int)(job - w * L.n_ecl);
+    JobScal J;
+    J.xs = J.ys = 0.0;
+    J.status = 0;
+    const WalkerScal W = ws[w];
+    bool prior_dead = what != LFB_LN_LIKE && !(W.lnprior > -INFINITY);
+    if (W.status != 0 || (flags & LFB_FLAG_SKIP_BS) || prior_dead) {
+        J.status = W.status != 0;
+        js[job] = J;
+        return;
+    }
+    const double* th = theta + w * L.ndim;
+    const int* g = L.gather + e * LFB_NPAR;
+    double rdisc_a = fetch(L, th, g[P_RDISC]) * W.R.xl1;
+    double imp[4];
+    if (!isfinite(rdisc_a) || !bspot(W.R, rdisc_a, imp)) {
+        J.status = 2;  // the stream misses the disc (roche.bspot raises, CVModel.py:309-316)
+        if (what != LFB_LN_LIKE) ws[w].lnprior = -INFINITY;
+    } else {
+        J.xs = imp[0];
+        J.ys = imp[1];
+        if (what != LFB_LN_LIKE) {
+            // azimuth window about the disc tangent at the impact point (CVModel.py:282-307)
+            double az = fetch(L, th, g[P_AZ]);
+            double alpha = atan2(imp[1], imp[0]) / kDeg;
+            if (alpha < 0.0) alpha = 90.0 - alpha;
+            double tangent = alpha + 90.0;
+            double minaz = fmax(0.0, tangent - 80.0), maxaz = fmin(178.0, tangent + 80.0);
+            if (!(az >= minaz) || !(az <= maxaz)) ws[w].lnprior = -INFINITY;
+        }
+    }
+    js[job] = J;
+}
+
+// ---------------------------------------------------------------- lightcurve_kernel
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the CTA, result in every thread.  Fixed tree: deterministic.
+__device__ __forceinline__ double block_sum(double v, double* red)
+{
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) t += red[i];
+    return t;
+}
+
+struct LCArgs {
+    DevLayout L;
+    DevLC lc;
+    GridCfg G;
+    int what, flags, mode;  // mode 0: chi-squared, 1: flux curves
+    long long njobs;
+    const double* theta;
+    const WalkerScal* ws;
+    const JobScal* js;
+    double* chisq;     // [njobs]
+    double* flux_tot;  // mode 1: [njobs][n_ph]
+    double* flux_comp; // mode 1 (optional): [4][njobs][n_ph]
+};
+
+__global__ void __launch_bounds__(kThreads) lightcurve_kernel(const __grid_constant__ LCArgs A)
+{
+    extern __shared__ double sm[];
+    const GridCfg& G = A.G;
+    const int NT = G.n_wd + G.n_disc + G.n_bs;
+    double* t_in = sm;
+    double* t_out = t_in + NT;
+    double* t_w = t_out + NT;
+    double* dq_nx = t_w + NT;
+    double* dq_ny = dq_nx + G.n_donor_q;
+    double* dq_nz = dq_ny + G.n_donor_q;
+    double* dq_w = dq_nz + G.n_donor_q;
+    double* ringw = dq_w + G.n_donor_q;  // [n_disc_r]
+    __shared__ double s_par[LFB_NPAR];
+    __shared__ double red[kThreads / 32];
+    const int tid = threadIdx.x;
+    const bool do_wd = !(A.flags & LFB_FLAG_SKIP_WD), do_disc = !(A.flags & LFB_FLAG_SKIP_DISC);
+    const bool do_bs = !(A.flags & LFB_FLAG_SKIP_BS), do_don = !(A.flags & LFB_FLAG_SKIP_DONOR);
+
+    for (long long job = blockIdx.x; job < A.njobs; job += gridDim.x) {
+        const long long w = job / A.L.n_ecl;
+        const int e = (int)(job - w * A.L.n_ecl);
+        const long long lc0 = A.mode ? 0 : A.lc.off[e];
+        const int n_ph = (int)(A.lc.off[A.mode ? 1 : e + 1] - lc0);
+        __syncthreads();
+        if (tid < LFB_NPAR) {
+            double v = 0.0;
+            if (tid < A.L.npars) v = fetch(A.L, A.theta + w * A.L.ndim, A.L.gather[e * LFB_NPAR + tid]);
+            else if (tid == P_EXP1) v = 2.0;
+            else if (tid == P_EXP2) v = 1.0;
+            else if (tid == P_TILT) v = 90.0;
+            s_par[tid] = v;
+        }
+        __syncthreads();
+        const WalkerScal W = A.ws[w];
+        const JobScal J = A.js[job];
+        const Roche R = W.R;
+        const double si = W.si, ci = W.ci;
+        bool finite_all = true;
+#pragma unroll
+        for (int k = 0; k < LFB_NPAR; ++k) finite_all = finite_all && isfinite(s_par[k]);
+        const double rwd_a = s_par[P_RWD] * R.xl1, rdisc_a = s_par[P_RDISC] * R.xl1;
+        bool valid = finite_all && W.status == 0 && J.status == 0;
+        if ((do_wd || do_disc) && !(s_par[P_RWD] > 0.0)) valid = false;
+        if (do_disc && !(rdisc_a > rwd_a)) valid = false;
+        if (do_bs && (!(s_par[P_SCALE] > 0.0) || !(s_par[P_EXP1] > 0.0) || !(s_par[P_EXP2] > 0.0))) valid = false;
+        const bool skipped = A.what == LFB_LN_PROB && !(W.lnprior > -INFINITY);
+        if (!valid || skipped) {
+            if (A.mode == 0) {
+                if (tid == 0) A.chisq[job] = skipped ? NAN : INFINITY;
+            } else {
+                for (int j = tid; j < n_ph; j += kThreads) {
+                    A.flux_tot[job * n_ph + j] = NAN;
+                    if (A.flux_comp)
+                        for (int cidx = 0; cidx < 4; ++cidx) A.flux_comp[((long long)cidx * A.njobs + job) * n_ph + j] = NAN;
+                }
+            }
+            continue;
+        }
+
+        // ---- stage 1: element grids and their ingress/egress phases ----
+        const int n_wd_half = do_wd ? G.n_wd / 2 : 0;
+        const int n_disc_half = do_disc ? G.n_disc / 2 : 0;
+        const int n_bs = do_bs ? G.n_bs : 0;
+        const int n_dq = do_don ? G.n_donor_q : 0;
+        if (do_disc)
+            for (int m = tid; m < G.n_disc_r; m += kThreads) {
+                double r = rwd_a + (m + 0.5) * (rdisc_a - rwd_a) / G.n_disc_r;
+                ringw[m] = pow(r, 1.0 - s_par[P_DEXP]);
+            }
+        if (!do_wd) for (int t = tid; t < G.n_wd; t += kThreads) { t_in[t] = kBig; t_out[t] = -kBig; t_w[t] = 0.0; }
+        if (!do_disc) for (int t = tid; t < G.n_disc; t += kThreads) { t_in[G.n_wd + t] = kBig; t_out[G.n_wd + t] = -kBig; t_w[G.n_wd + t] = 0.0; }
+        if (!do_bs) for (int t = tid; t < G.n_bs; t += kThreads) { int i = G.n_wd + G.n_disc + t; t_in[i] = kBig; t_out[i] = -kBig; t_w[i] = 0.0; }
+        __syncthreads();
+        // bright-spot strip constants
+        double bs_smax = 1.0, bs_smaxp = 1.0, bs_shi = 1.0, bs_tx = 1.0, bs_ty = 0.0;
+        if (do_bs) {
+            bs_smax = pow(s_par[P_EXP1] / s_par[P_EXP2], 1.0 / s_par[P_EXP2]);
+            bs_smaxp = pow(bs_smax, s_par[P_EXP2]);
+            bs_shi = fmin(20.0 + bs_smax, pow(bs_smaxp + 30.0, 1.0 / s_par[P_EXP2]));
+            sincos_(s_par[P_AZ] * kDeg, &bs_ty, &bs_tx);
+        }
+        const int n_tasks = n_wd_half + n_disc_half + n_bs + n_dq;
+        for (int task = tid; task < n_tasks; task += kThreads) {
+            if (task < n_wd_half + n_disc_half + n_bs) {
+                Point T = {0.0, 0.0, 0.0, 0.0, 0.0};
+                int i0, i1;
+                double wt;
+                if (task < n_wd_half) {
+                    // white dwarf: ring k of the sky disc, tiles with cos(alpha) > 0; mirror in xi
+                    int h = task;
+                    int k = (int)sqrt(0.5 * (double)h);
+                    while (2 * k * k > h) --k;
+                    while (2 * (k + 1) * (k + 1) <= h) ++k;
+                    int r = h - 2 * k * k, q1 = 2 * k + 1, nk = 4 * q1;
+                    int j = r < q1 ? r : r + 2 * q1;
+                    double inv = 1.0 / G.n_wd_rings;
+                    double ra = k * inv, rb = (k + 1) * inv;
+                    double rho = sqrt(0.5 * (ra * ra + rb * rb));
+                    double ua = 1.0 - ra * ra, ub = 1.0 - rb * rb;
+                    double mubar = (2.0 / 3.0) * (ua * sqrt(ua) - ub * sqrt(ub)) / (rb * rb - ra * ra);
+                    wt = (1.0 - s_par[P_ULIMB]) + s_par[P_ULIMB] * mubar;
+                    double sa, ca;
+                    sincos_((j + 0.5) * kTwoPi / nk, &sa, &ca);
+                    T.xi = rwd_a * rho * ca;
+                    T.eta = rwd_a * rho * sa;
+                    i0 = 4 * k * k + j;
+                    i1 = 4 * k * k + (nk / 2 - 1 - j + nk) % nk;
+                } else if (task < n_wd_half + n_disc_half) {
+                    // disc: ring m, sector j on the y > 0 side; mirror in y
+                    int h = task - n_wd_half, hth = G.n_disc_th / 2;
+                    int m = h / hth, j = h - m * hth;
+                    double r = rwd_a + (m + 0.5) * (rdisc_a - rwd_a) / G.n_disc_r;
+                    double sa, ca;
+                    sincos_((j + 0.5) * kTwoPi / G.n_disc_th, &sa, &ca);
+                    T.x = r * ca;
+                    T.y = r * sa;
+                    wt = ringw[m];
+                    i0 = G.n_wd + m * G.n_disc_th + j;
+                    i1 = G.n_wd + m * G.n_disc_th + (G.n_disc_th - 1 - j);
+                } else {
+                    // bright spot: strip through the stream impact point along azimuth az
+                    int k = task - n_wd_half - n_disc_half;
+                    double s = bs_shi * k / (G.n_bs - 1);
+                    wt = k == 0 ? 0.0 : pow(s / bs_smax, s_par[P_EXP1]) * exp(bs_smaxp - pow(s, s_par[P_EXP2]));
+                    double len = (s - bs_smax) * s_par[P_SCALE] * R.xl1;
+                    T.x = J.xs + len * bs_tx;
+                    T.y = J.ys + len * bs_ty;
+                    i0 = i1 = G.n_wd + G.n_disc + k;
+                }
+                double pin, pout;
+                if (!ingress_egress(R, si, ci, T, &pin, &pout)) { pin = kBig; pout = -kBig; }
+                t_in[i0] = pin;
+                t_out[i0] = pout;
+                t_w[i0] = wt;
+                if (i1 != i0) {
+                    t_in[i1] = pout > pin ? -pout : kBig;
+                    t_out[i1] = pout > pin ? -pin : -kBig;
+                    t_w[i1] = wt;
+                }
+            } else {
+                // donor: quarter of the tiles on the critical surface (y > 0, z > 0)
+                int h = task - (n_wd_half + n_disc_half + n_bs);
+                int k = 0;
+                while (G.donor_ring_off[k + 1] <= h) ++k;
+                int j = h - G.donor_ring_off[k], mk = G.donor_ring_off[k + 1] - G.donor_ring_off[k];
+                double sth, cth, sph, cph;
+                double dth = kPi / G.n_donor_th, dph = kTwoPi / (4 * mk);
+                sincos_((k + 0.5) * dth, &sth, &cth);
+                sincos_((j + 0.5) * dph, &sph, &cph);
+                double dx = -cth, dy = sth * cph, dz = sth * sph, g[3];
+                double r = donor_radius(R, dx, dy, dz, g);
+                double gm = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+                double nx = g[0] / gm, ny = g[1] / gm, nz = g[2] / gm;
+                double area = r * r * sth * dth * dph / (nx * dx + ny * dy + nz * dz);
+                dq_nx[h] = nx;
+                dq_ny[h] = ny;
+                dq_nz[h] = nz;
+                dq_w[h] = area * pow(gm, G.donor_gdexp);
+            }
+        }
+        __syncthreads();
+
+        // component totals ("flux at maximum light", README.md:24-28)
+        double p_wd = 0.0, p_d = 0.0, p_s = 0.0, p_rs = 0.0;
+        for (int t = tid; t < G.n_wd; t += kThreads) p_wd += t_w[t];
+        for (int t = tid; t < G.n_disc; t += kThreads) p_d += t_w[G.n_wd + t];
+        for (int t = tid; t < G.n_bs; t += kThreads) p_s += t_w[G.n_wd + G.n_disc + t];
+        const double ud = G.donor_ulimb;
+        for (int t = tid; t < n_dq; t += kThreads) {
+            // donor at quadrature (phase 0.25): c = 0, s = 1
+            double b = si * dq_ny[t], d = ci * dq_nz[t], wv = dq_w[t], m;
+            m = -b + d; if (m > 0.0) p_rs += wv * m * (1.0 - ud + ud * m);
+            m = b + d;  if (m > 0.0) p_rs += wv * m * (1.0 - ud + ud * m);
+            m = -b - d; if (m > 0.0) p_rs += wv * m * (1.0 - ud + ud * m);
+            m = b - d;  if (m > 0.0) p_rs += wv * m * (1.0 - ud + ud * m);
+        }
+        const double tot_wd = block_sum(p_wd, red), tot_d = block_sum(p_d, red), tot_s = block_sum(p_s, red),
+                     tot_rs = block_sum(p_rs, red);
+        // beamed part of the spot: polar angle tilt from +z, azimuth az - 90 + yaw
+        double beam_a = 0.0, beam_b = 0.0, beam_d = 0.0, beam_norm = 1.0;
+        const double fis = s_par[P_FIS];
+        if (do_bs) {
+            double st, ct, sp, cp;
+            sincos_(s_par[P_TILT] * kDeg, &st, &ct);
+            sincos_((s_par[P_AZ] - 90.0 + s_par[P_YAW]) * kDeg, &sp, &cp);
+            beam_a = si * st * cp;
+            beam_b = -si * st * sp;
+            beam_d = ci * ct;
+            double cmax = si * st + ci * ct;
+            beam_norm = fis + (1.0 - fis) * (cmax > 0.0 ? cmax : 0.0);
+        }
+        const double i_wd = do_wd ? 1.0 / tot_wd : 0.0, i_d = do_disc ? 1.0 / tot_d : 0.0;
+        const double i_s = (do_bs && beam_norm > 0.0 && tot_s > 0.0) ? 1.0 / (beam_norm * tot_s) : 0.0;
+        const double i_rs = do_don ? 1.0 / tot_rs : 0.0;
+
+        // ---- stages 2-4: visible flux per exposure sample, component mix, chi-squared ----
+        const int K = G.n_quad;
+        const double phi0 = s_par[P_PHI0];
+        const double* t_in_d = t_in + G.n_wd;
+        const double* t_in_s = t_in_d + G.n_disc;
+        double chi = 0.0;
+        for (int j = tid; j < n_ph; j += kThreads) {
+            const double phj = A.lc.phase[lc0 + j], wj = A.lc.width[lc0 + j];
+            double ywd = 0.0, yd = 0.0, ys = 0.0, yrs = 0.0;
+            for (int k = 0; k < K; ++k) {
+                double ph = phj + G.quad_off[k] * wj - phi0;
+                ph -= rint(ph);
+                double s, c;
+                sincos_(kTwoPi * ph, &s, &c);
+                double v_wd = 0.0, v_d = 0.0, v_s = 0.0, v_rs = 0.0;
+                for (int t = 0; t < G.n_wd; ++t)
+                    if (!(ph > t_in[t] && ph < t_out[t])) v_wd += t_w[t];
+                for (int t = 0; t < G.n_disc; ++t)
+                    if (!(ph > t_in_d[t] && ph < (t_out + G.n_wd)[t])) v_d += (t_w + G.n_wd)[t];
+                for (int t = 0; t < G.n_bs; ++t)
+                    if (!(ph > t_in_s[t] && ph < (t_out + G.n_wd + G.n_disc)[t])) v_s += (t_w + G.n_wd + G.n_disc)[t];
+                for (int t = 0; t < n_dq; ++t) {
+                    double a = si * dq_nx[t] * c, b = si * dq_ny[t] * s, d = ci * dq_nz[t], wv = dq_w[t], m;
+                    m = a - b + d; if (m > 0.0) v_rs += wv * m * (1.0 - ud + ud * m);
+                    m = a + b + d; if (m > 0.0) v_rs += wv * m * (1.0 - ud + ud * m);
+                    m = a - b - d; if (m > 0.0) v_rs += wv * m * (1.0 - ud + ud * m);
+                    m = a + b - d; if (m > 0.0) v_rs += wv * m * (1.0 - ud + ud * m);
+                }
+                double bm = beam_a * c + beam_b * s + beam_d;
+                double beam = fis + (1.0 - fis) * (bm > 0.0 ? bm : 0.0);
+                const double qw = G.quad_w[k];
+                ywd += qw * v_wd * i_wd;
+                yd += qw * v_d * i_d;
+                ys += qw * beam * v_s * i_s;
+                yrs += qw * v_rs * i_rs;
+            }
+            const double fwd = s_par[P_WDFLUX] * ywd, fd = s_par[P_DFLUX] * yd, fs = s_par[P_SFLUX] * ys,
+                         frs = s_par[P_RSFLUX] * yrs;
+            const double f = fwd + fd + fs + frs;
+            if (A.mode == 0) {
+                double r = (A.lc.y[lc0 + j] - f) / A.lc.ye[lc0 + j];
+                chi += r * r;
+            } else {
+                A.flux_tot[job * n_ph + j] = f;
+                if (A.flux_comp) {
+                    A.flux_comp[((long long)0 * A.njobs + job) * n_ph + j] = fwd;
+                    A.flux_comp[((long long)1 * A.njobs + job) * n_ph + j] = fd;
+                    A.flux_comp[((long long)2 * A.njobs + job) * n_ph + j] = fs;
+                    A.flux_comp[((long long)3 * A.njobs + job) * n_ph + j] = frs;
+                }
+            }
+        }
+        if (A.mode == 0) {
+            chi = block_sum(chi, red);
+            if (tid == 0) A.chisq[job] = isnan(chi) ? INFINITY : chi;  // NaN model -> +inf (CVModel.py:163-171)
+        }
+    }
+}
+
+// ---------------------------------------------------------------- finish_kernel
+__global__ void finish_kernel(int what, int n_ecl, long long n, const WalkerScal* __restrict__ ws,
+                              const double* __restrict__ chisq, double* __restrict__ out)
+{
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    double lnp = ws[w].lnprior;
+    double v;
+    if (what == LFB_LN_PRIOR) {
+        v = lnp;
+    } else {
+        double like = 0.0;
+        if (what == LFB_LN_LIKE || lnp > -INFINITY)
+            for (int e = 0; e < n_ecl; ++e) like += -0.5 * chisq[w * n_ecl + e];
+        v = what == LFB_LN_LIKE ? like : (lnp > -INFINITY ? lnp + like : -INFINITY);
+    }
+    if (isnan(v)) v = -INFINITY;  // never NaN towards the sampler (model.py:489-493)
+    out[w] = v;
+}
+
+// ---------------------------------------------------------------- roche_kernel
+__global__ void roche_kernel(int which, long long n, const double* __restrict__ a, const double* __restrict__ b,
+                             double* __restrict__ out, int* __restrict__ ok)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double o[4] = {0.0, 0.0, 0.0, 0.0};
+    int good = 0;
+    Roche R;
+    if (roche_init(a[i], R)) {
+        if (which == LFB_ROCHE_XL1) {
+            o[0] = R.xl1;
+            good = 1;
+        } else if (which == LFB_ROCHE_FINDPHI) {
+            double inc = b[i];
+            if (inc == 90.0) {
+                o[0] = findphi90(R);
+                good = 1;
+            } else if (inc > 0.0 && inc < 90.0) {
+                Point T = {0.0, 0.0, 0.0, 0.0, 0.0};
+                double si, ci, pin, pout;
+                sincos_(inc * kDeg, &si, &ci);
+                if (ingress_egress(R, si, ci, T, &pin, &pout)) {
+                    o[0] = pout - pin;
+                    good = 1;
+                }
+            }
+        } else if (which == LFB_ROCHE_FINDI) {
+            double sini;
+            if (findi(R, b[i], findphi90(R), sini)) {
+                o[0] = asin(sini) / kDeg;
+                good = 1;
+            }
+        } else if (which == LFB_ROCHE_BSPOT) {
+            good = bspot(R, b[i], o) ? 1 : 0;
+        }
+    }
+    for (int k = 0; k < 4; ++k) out[i * 4 + k] = good ? o[k] : NAN;
+    ok[i] = good;
+}
+
+}  // namespace
+
+// ================================================================= host side / C ABI
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned_host = false;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        release();
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    void release()
+    {
+        if (p) { if (pinned_host) cudaFreeHost(p); else cudaFree(p); }
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() { return (T*)p; }
+};
+
+struct lfb_handle {
+    int device = 0;
+    lfb_config cfg{};
+    GridCfg grid{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    std::string err;
+    long long launches = 0;
+    int sm_count = 148;
+    size_t smem_bytes = 0;
+    // layout
+    bool have_layout = false, have_lc = false;
+    int ndim = 0, n_ecl = 0, npars = 0, n_prior = 0;
+    DevBuf gather, consts, psrc, ptype, pisvar, pp1, pp2, pnorm, donor_off;
+    DevBuf lc_off, lc_phase, lc_width, lc_y, lc_ye;
+    // calc_flux scratch layout
+    DevBuf cf_gather, cf_off, cf_phase, cf_width, cf_pars, cf_tot, cf_comp;
+    // work
+    DevBuf theta, out, chisq, ws, js;
+    DevBuf h_in, h_out, h_chisq;
+    lfb_handle() { h_in.pinned_host = h_out.pinned_host = h_chisq.pinned_host = true; }
+};
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return LFB_ECUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+static int fail(lfb_handle* h, int code, const std::string& msg)
+{
+    h->err = msg;
+    return code;
+}
+
+static bool is_device_ptr(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int upload(lfb_handle* h, DevBuf& b, const void* src, size_t bytes)
+{
+    CK(b.reserve(bytes ? bytes : 8));
+    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyDefault, h->stream));
+    return LFB_OK;
+}
+
+static int donor_ring_count(int nth, int k)
+{
+    double th = (k + 0.5) * lfb::kPi / nth;
+    return (int)fmax(1.0, floor(0.5 * nth * sin(th) + 0.5));
+}
+
+extern "C" {
+
+int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
+{
+    if (!out) return LFB_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                         " (this engine has no CPU fallback)";
+        cudaGetLastError();
+        return LFB_ECUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "device index out of range";
+        return LFB_EINVAL;
+    }
+    lfb_config c{};
+    if (cfg_in) c = *cfg_in;
+    if (c.n_wd_rings <= 0) c.n_wd_rings = 10;
+    if (c.n_disc_r <= 0) c.n_disc_r = 25;
+    if (c.n_disc_th <= 0) c.n_disc_th = 40;
+    if (c.n_bs <= 0) c.n_bs = 200;
+    if (c.n_donor_th <= 0) c.n_donor_th = 18;
+    if (c.n_quad <= 0) c.n_quad = 3;
+    if (!(c.donor_ulimb != 0.0)) c.donor_ulimb = 0.8;
+    if (!(c.donor_gdexp != 0.0)) c.donor_gdexp = 0.32;
+    if ((c.n_disc_th & 1) || !(c.n_quad & 1) || c.n_quad > kMaxQuad || c.n_donor_th > kMaxDonorRings ||
+        c.n_bs < 2 || c.n_wd_rings > 256 || c.n_disc_r > 4096) {
+        g_create_error = "bad grid configuration (n_disc_th even, n_quad odd <= 15, n_donor_th <= 128, n_bs >= 2)";
+        return LFB_EINVAL;
+    }
+    lfb_handle* h = new lfb_handle();
+    h->device = device;
+    h->cfg = c;
+    auto bail = [&](const char* what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        delete h;
+        return LFB_ECUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    GridCfg& G = h->grid;
+    G.n_wd_rings = c.n_wd_rings;
+    G.n_wd = 4 * c.n_wd_rings * c.n_wd_rings;
+    G.n_disc_r = c.n_disc_r;
+    G.n_disc_th = c.n_disc_th;
+    G.n_disc = c.n_disc_r * c.n_disc_th;
+    G.n_bs = c.n_bs;
+    G.n_donor_th = c.n_donor_th;
+    G.n_quad = c.n_quad;
+    G.donor_ulimb = c.donor_ulimb;
+    G.donor_gdexp = c.donor_gdexp;
+    std::vector<int> off(c.n_donor_th + 1, 0);
+    for (int k = 0; k < c.n_donor_th; ++k) off[k + 1] = off[k] + donor_ring_count(c.n_donor_th, k);
+    G.n_donor_q = off[c.n_donor_th];
+    if (h->donor_off.reserve(off.size() * sizeof(int)) != cudaSuccess ||
+        cudaMemcpy(h->donor_off.p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail("donor ring table", cudaGetLastError());
+    G.donor_ring_off = h->donor_off.as<int>();
+    // composite Simpson nodes on [-1, 1] (exposure = phase +- width, CVModel.py:64)
+    if (c.n_quad == 1) {
+        G.quad_off[0] = 0.0;
+        G.quad_w[0] = 1.0;
+    } else {
+        int nint = c.n_quad - 1;
+        for (int k = 0; k < c.n_quad; ++k) {
+            G.quad_off[k] = -1.0 + 2.0 * k / nint;
+            double cw = (k == 0 || k == nint) ? 1.0 : ((k & 1) ? 4.0 : 2.0);
+            G.quad_w[k] = cw / (3.0 * nint);
+        }
+    }
+    size_t nt = (size_t)G.n_wd + G.n_disc + G.n_bs;
+    h->smem_bytes = sizeof(double) * (3 * nt + 4 * (size_t)G.n_donor_q + G.n_disc_r);
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (h->smem_bytes > (size_t)max_smem - 1024) {
+        g_create_error = "surface grid too dense for shared memory";
+        delete h;
+        return LFB_EINVAL;
+    }
+    if ((e = cudaFuncSetAttribute(lightcurve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)) !=
+        cudaSuccess)
+        return bail("cudaFuncSetAttribute", e);
+    *out = h;
+    return LFB_OK;
+}
+
+void lfb_destroy(lfb_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->gather, &h->consts, &h->psrc, &h->ptype, &h->pisvar, &h->pp1, &h->pp2, &h->pnorm,
+                      &h->donor_off, &h->lc_off, &h->lc_phase, &h->lc_width, &h->lc_y, &h->lc_ye, &h->cf_gather,
+                      &h->cf_off, &h->cf_phase, &h->cf_width, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta,
+                      &h->out, &h->chisq, &h->ws, &h->js, &h->h_in, &h->h_out, &h->h_chisq};
+    for (DevBuf* b : bufs) b->release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* lfb_last_error(const lfb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lfb_get_config(const lfb_handle* h, lfb_config* out)
+{
+    if (!h || !out) return LFB_EINVAL;
+    *out = h->cfg;
+    return LFB_OK;
+}
+
+long long lfb_launch_count(const lfb_handle* h) { return h ? h->launches : 0; }
+
+float lfb_last_kernel_ms(lfb_handle* h)
+{
+    if (!h || !h->ev_valid) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) {
+        cudaGetLastError();
+        return -1.0f;
+    }
+    return ms;
+}
+
+int lfb_set_layout(lfb_handle* h, int ndim, int n_ecl, int npars, const int* gather, int n_consts,
+                   const double* consts)
+{
+    if (!h) return LFB_EINVAL;
+    if (ndim < 0 || n_ecl < 1 || (npars != 14 && npars != 18) || !gather || n_consts < 0 || (n_consts && !consts))
+        return fail(h, LFB_EINVAL, "set_layout: need n_ecl >= 1, npars in {14, 18}, gather");
+    for (int e = 0; e < n_ecl; ++e)
+        for (int k = 0; k < npars; ++k) {
+            int g = gather[e * LFB_NPAR + k];
+            if (g >= ndim || (g < 0 && -g - 1 >= n_consts)) return fail(h, LFB_EINVAL, "set_layout: gather index out of range");
+        }
+    // q, dphi and rwd live on the root of the tree (LCModel.node_par_names, CVModel.py:434)
+    for (int e = 1; e < n_ecl; ++e)
+        if (gather[e * LFB_NPAR + P_Q] != gather[P_Q] || gather[e * LFB_NPAR + P_DPHI] != gather[P_DPHI])
+            return fail(h, LFB_EINVAL, "set_layout: q and dphi must be shared by every eclipse");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = upload(h, h->gather, gather, sizeof(int) * (size_t)n_ecl * LFB_NPAR))) return rc;
+    if ((rc = upload(h, h->consts, consts, sizeof(double) * (size_t)n_consts))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->ndim = ndim;
+    h->n_ecl = n_ecl;
+    h->npars = npars;
+    h->have_layout = true;
+    h->have_lc = false;
+    h->n_prior = 0;
+    return LFB_OK;
+}
+
+int lfb_set_priors(lfb_handle* h, int n_prior, const int* src, const int* type, const double* p1, const double* p2,
+                   const double* norm, const int* isvar)
+{
+    if (!h) return LFB_EINVAL;
+    if (!h->have_layout) return fail(h, LFB_ESTATE, "set_priors: call set_layout first");
+    if (n_prior < 0 || (n_prior && (!src || !type || !p1 || !p2 || !norm || !isvar)))
+        return fail(h, LFB_EINVAL, "set_priors: NULL array");
+    for (int k = 0; k < n_prior; ++k) {
+        if (src[k] >= h->ndim) return fail(h, LFB_EINVAL, "set_priors: source column out of range");
+        if (type[k] < 0 || type[k] > LFB_PRIOR_MODJEFF) return fail(h, LFB_EINVAL, "set_priors: unknown prior type");
+    }
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = upload(h, h->psrc, src, sizeof(int) * (size_t)n_prior))) return rc;
+    if ((rc = upload(h, h->ptype, type, sizeof(int) * (size_t)n_prior))) return rc;
+    if ((rc = upload(h, h->pisvar, isvar, sizeof(int) * (size_t)n_prior))) return rc;
+    if ((rc = upload(h, h->pp1, p1, sizeof(double) * (size_t)n_prior))) return rc;
+    if ((rc = upload(h, h->pp2, p2, sizeof(double) * (size_t)n_prior))) return rc;
+    if ((rc = upload(h, h->pnorm, norm, sizeof(double) * (size_t)n_prior))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_prior = n_prior;
+    return LFB_OK;
+}
+
+int lfb_set_lightcurves(lfb_handle* h, int n_ecl, const long long* off, const double* phase, const double* width,
+                        const double* y, const double* ye)
+{
+    if (!h) return LFB_EINVAL;
+    if (!h->have_layout) return fail(h, LFB_ESTATE, "set_lightcurves: call set_layout first");
+    if (n_ecl != h->n_ecl || !off || !phase || !width || !y || !ye)
+        return fail(h, LFB_EINVAL, "set_lightcurves: n_ecl must match the layout; arrays must be non-NULL");
+    if (off[0] != 0) return fail(h, LFB_EINVAL, "set_lightcurves: off[0] must be 0");
+    for (int e = 0; e < n_ecl; ++e)
+        if (off[e + 1] < off[e] || off[e + 1] - off[e] > 0x7fffffffLL) return fail(h, LFB_EINVAL, "set_lightcurves: offsets must ascend");
+    size_t tot = (size_t)off[n_ecl];
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = upload(h, h->lc_off, off, sizeof(long long) * (size_t)(n_ecl + 1)))) return rc;
+    if ((rc = upload(h, h->lc_phase, phase, sizeof(double) * tot))) return rc;
+    if ((rc = upload(h, h->lc_width, width, sizeof(double) * tot))) return rc;
+    if ((rc = upload(h, h->lc_y, y, sizeof(double) * tot))) return rc;
+    if ((rc = upload(h, h->lc_ye, ye, sizeof(double) * tot))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_lc = true;
+    return LFB_OK;
+}
+
+static DevLayout make_layout(lfb_handle* h)
+{
+    DevLayout L;
+    L.ndim = h->ndim;
+    L.n_ecl = h->n_ecl;
+    L.npars = h->npars;
+    L.n_prior = h->n_prior;
+    L.gather = h->gather.as<int>();
+    L.consts = h->consts.as<double>();
+    L.psrc = h->psrc.as<int>();
+    L.ptype = h->ptype.as<int>();
+    L.pisvar = h->pisvar.as<int>();
+    L.pp1 = h->pp1.as<double>();
+    L.pp2 = h->pp2.as<double>();
+    L.pnorm = h->pnorm.as<double>();
+    return L;
+}
+
+static int grid_for(lfb_handle* h, long long njobs)
+{
+    long long cap = (long long)h->sm_count * 8;
+    return (int)(njobs < cap ? (njobs > 0 ? njobs : 1) : cap);
+}
+
+int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, double* out, double* chisq_out,
+                 void* stream_v)
+{
+    if (!h) return LFB_EINVAL;
+    if (!h->have_layout) return fail(h, LFB_ESTATE, "log_prob: call set_layout first");
+    if (what != LFB_LN_PRIOR && !h->have_lc) return fail(h, LFB_ESTATE, "log_prob: call set_lightcurves first");
+    if (what < LFB_LN_PRIOR || what > LFB_LN_PROB || n < 0 || (n && (!theta || !out)))
+        return fail(h, LFB_EINVAL, "log_prob: bad arguments");
+    if (n == 0) return LFB_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    const long long njobs = n * h->n_ecl;
+    const size_t th_bytes = sizeof(double) * (size_t)n * (size_t)(h->ndim > 0 ? h->ndim : 1);
+    const bool th_dev = is_device_ptr(theta), out_dev = is_device_ptr(out);
+    const bool chi_dev = chisq_out && is_device_ptr(chisq_out);
+    const double* d_theta = theta;
+    if (!th_dev) {
+        CK(h->theta.reserve(th_bytes));
+        CK(h->h_in.reserve(th_bytes));
+        memcpy(h->h_in.p, theta, sizeof(double) * (size_t)n * h->ndim);
+        CK(cudaMemcpyAsync(h->theta.p, h->h_in.p, sizeof(double) * (size_t)n * h->ndim, cudaMemcpyHostToDevice, st));
+        d_theta = h->theta.as<double>();
+    }
+    double* d_out = out;
+    if (!out_dev) {
+        CK(h->out.reserve(sizeof(double) * (size_t)n));
+        d_out = h->out.as<double>();
+    }
+    double* d_chi = chi_dev ? chisq_out : nullptr;
+    if (!chi_dev) {
+        CK(h->chisq.reserve(sizeof(double) * (size_t)njobs));
+        d_chi = h->chisq.as<double>();
+    }
+    CK(h->ws.reserve(sizeof(WalkerScal) * (size_t)n));
+    CK(h->js.reserve(sizeof(JobScal) * (size_t)njobs));
+    DevLayout L = make_layout(h);
+    walker_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, what, 0, n, d_theta, h->ws.as<WalkerScal>());
+    h->launches++;
+    stream_kernel<<<(unsigned)((njobs + 63) / 64), 64, 0, st>>>(L, what, 0, njobs, d_theta, h->ws.as<WalkerScal>(),
+                                                                 h->js.as<JobScal>());
+    h->launches++;
+    if (what != LFB_LN_PRIOR) {
+        LCArgs A;
+        A.L = L;
+        A.lc = DevLC{h->lc_off.as<long long>(), h->lc_phase.as<double>(), h->lc_width.as<double>(),
+                     h->lc_y.as<double>(), h->lc_ye.as<double>()};
+        A.G = h->grid;
+        A.what = what;
+        A.flags = 0;
+        A.mode = 0;
+        A.njobs = njobs;
+        A.theta = d_theta;
+        A.ws = h->ws.as<WalkerScal>();
+        A.js = h->js.as<JobScal>();
+        A.chisq = d_chi;
+        A.flux_tot = nullptr;
+        A.flux_comp = nullptr;
+        CK(cudaEventRecord(h->ev0, st));
+        lightcurve_kernel<<<grid_for(h, njobs), kThreads, h->smem_bytes, st>>>(A);
+        CK(cudaEventRecord(h->ev1, st));
+        h->ev_valid = true;
+        h->launches++;
+    }
+    finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(what, h->n_ecl, n, h->ws.as<WalkerScal>(), d_chi, d_out);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (!out_dev || (chisq_out && !chi_dev)) {
+        CK(h->h_out.reserve(sizeof(double) * (size_t)n));
+        if (!out_dev) CK(cudaMemcpyAsync(h->h_out.p, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (chisq_out && !chi_dev) {
+            CK(h->h_chisq.reserve(sizeof(double) * (size_t)njobs));
+            if (what == LFB_LN_PRIOR) CK(cudaMemsetAsync(d_chi, 0xff, sizeof(double) * (size_t)njobs, st));
+            CK(cudaMemcpyAsync(h->h_chisq.p, d_chi, sizeof(double) * (size_t)njobs, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        if (!out_dev) memcpy(out, h->h_out.p, sizeof(double) * (size_t)n);
+        if (chisq_out && !chi_dev) memcpy(chisq_out, h->h_chisq.p, sizeof(double) * (size_t)njobs);
+    }
+    return LFB_OK;
+}
+
+int lfb_calc_flux(lfb_handle* h, long long n_sets, const double* pars, int npars, int flags, int n_ph,
+                  const double* phase, const double* width, double* out_total, double* out_comp, void* stream_v)
+{
+    if (!h) return LFB_EINVAL;
+    if (n_sets < 0 || (npars != 14 && npars != 18) || n_ph < 0 || (n_sets && !pars) || (n_ph && (!phase || !out_total)))
+        return fail(h, LFB_EINVAL, "calc_flux: need npars in {14, 18} and non-NULL arrays");
+    if (n_sets == 0 || n_ph == 0) return LFB_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    std::vector<int> gather(LFB_NPAR, 0);
+    for (int k = 0; k < LFB_NPAR; ++k) gather[k] = k < npars ? k : 0;
+    long long off[2] = {0, n_ph};
+    std::vector<double> zeros;
+    if (!width) zeros.assign(n_ph, 0.0);
+    const size_t cur = sizeof(double) * (size_t)n_sets * n_ph;
+    CK(h->cf_gather.reserve(sizeof(int) * LFB_NPAR));
+    CK(h->cf_off.reserve(sizeof(off)));
+    CK(h->cf_phase.reserve(sizeof(double) * n_ph));
+    CK(h->cf_width.reserve(sizeof(double) * n_ph));
+    CK(cudaMemcpyAsync(h->cf_gather.p, gather.data(), sizeof(int) * LFB_NPAR, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->cf_off.p, off, sizeof(off), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->cf_phase.p, phase, sizeof(double) * n_ph, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(h->cf_width.p, width ? width : zeros.data(), sizeof(double) * n_ph, cudaMemcpyDefault, st));
+    const double* d_pars = pars;
+    if (!is_device_ptr(pars)) {
+        CK(h->cf_pars.reserve(sizeof(double) * (size_t)n_sets * npars));
+        CK(cudaMemcpyAsync(h->cf_pars.p, pars, sizeof(double) * (size_t)n_sets * npars, cudaMemcpyHostToDevice, st));
+        d_pars = h->cf_pars.as<double>();
+    }
+    const bool tot_dev = is_device_ptr(out_total), comp_dev = out_comp && is_device_ptr(out_comp);
+    double* d_tot = out_total;
+    if (!tot_dev) {
+        CK(h->cf_tot.reserve(cur));
+        d_tot = h->cf_tot.as<double>();
+    }
+    double* d_comp = comp_dev ? out_comp : nullptr;
+    if (out_comp && !comp_dev) {
+        CK(h->cf_comp.reserve(4 * cur));
+        d_comp = h->cf_comp.as<double>();
+    }
+    CK(h->ws.reserve(sizeof(WalkerScal) * (size_t)n_sets));
+    CK(h->js.reserve(sizeof(JobScal) * (size_t)n_sets));
+    DevLayout L;
+    memset(&L, 0, sizeof(L));
+    L.ndim = npars;
+    L.n_ecl = 1;
+    L.npars = npars;
+    L.n_prior = 0;
+    L.gather = h->cf_gather.as<int>();
+    walker_kernel<<<(unsigned)((n_sets + 127) / 128), 128, 0, st>>>(L, LFB_LN_LIKE, flags, n_sets, d_pars, h->ws.as<WalkerScal>());
+    stream_kernel<<<(unsigned)((n_sets + 63) / 64), 64, 0, st>>>(L, LFB_LN_LIKE, flags, n_sets, d_pars, h->ws.as<WalkerScal>(),
+                                                                  h->js.as<JobScal>());
+    LCArgs A;
+    A.L = L;
+    A.lc = DevLC{h->cf_off.as<long long>(), h->cf_phase.as<double>(), h->cf_width.as<double>(), nullptr, nullptr};
+    A.G = h->grid;
+    A.what = LFB_LN_LIKE;
+    A.flags = flags;
+    A.mode = 1;
+    A.njobs = n_sets;
+    A.theta = d_pars;
+    A.ws = h->ws.as<WalkerScal>();
+    A.js = h->js.as<JobScal>();
+    A.chisq = nullptr;
+    A.flux_tot = d_tot;
+    A.flux_comp = d_comp;
+    lightcurve_kernel<<<grid_for(h, n_sets), kThreads, h->smem_bytes, st>>>(A);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    if (!tot_dev) CK(cudaMemcpyAsync(out_total, d_tot, cur, cudaMemcpyDeviceToHost, st));
+    if (out_comp && !comp_dev) CK(cudaMemcpyAsync(out_comp, d_comp, 4 * cur, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LFB_OK;
+}
+
+int lfb_roche(lfb_handle* h, int which, long long n, const double* a, const double* b, double* out, int* ok)
+{
+    if (!h) return LFB_EINVAL;
+    if (which < LFB_ROCHE_XL1 || which > LFB_ROCHE_BSPOT || n < 0 || (n && (!a || !out || !ok)) ||
+        (n && which != LFB_ROCHE_XL1 && !b))
+        return fail(h, LFB_EINVAL, "roche: bad arguments");
+    if (n == 0) return LFB_OK;
+    CK(cudaSetDevice(h->device));
+    DevBuf da, db, dout, dok;
+    auto cleanup = [&]() { da.release(); db.release(); dout.release(); dok.release(); };
+    cudaError_t e;
+    if ((e = da.reserve(sizeof(double) * n)) != cudaSuccess || (e = db.reserve(sizeof(double) * n)) != cudaSuccess ||
+        (e = dout.reserve(sizeof(double) * 4 * n)) != cudaSuccess || (e = dok.reserve(sizeof(int) * n)) != cudaSuccess) {
+        cleanup();
+        return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    }
+    cudaMemcpyAsync(da.p, a, sizeof(double) * n, cudaMemcpyDefault, h->stream);
+    if (b) cudaMemcpyAsync(db.p, b, sizeof(double) * n, cudaMemcpyDefault, h->stream);
+    else cudaMemsetAsync(db.p, 0, sizeof(double) * n, h->stream);
+    roche_kernel<<<(unsigned)((n + 63) / 64), 64, 0, h->stream>>>(which, n, da.as<double>(), db.as<double>(),
+                                                                  dout.as<double>(), dok.as<int>());
+    h->launches++;
+    cudaMemcpyAsync(out, dout.p, sizeof(double) * 4 * n, cudaMemcpyDefault, h->stream);
+    cudaMemcpyAsync(ok, dok.p, sizeof(int) * n, cudaMemcpyDefault, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    return LFB_OK;
+}
+
+}  // extern "C"

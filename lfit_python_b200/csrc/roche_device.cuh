@@ -1,0 +1,534 @@
+// roche_device.cuh -- FP64 Roche geometry for the sm_100a kernels.
+//
+// Replaces, on the device, what the reference calls in trm.roche and inside
+// lfit (neither is under /root/reference; call sites CVModel.py:222,288,460,561
+// and CVModel.py:138): L1, the inclination for a given eclipse width, the
+// ballistic stream, and the ingress/egress phases of a surface element behind
+// the donor's critical lobe.
+//
+// Frame: a = 1, white dwarf at the origin, donor at (1,0,0), mu = q/(1+q),
+//   Phi = -(1-mu)/r1 - mu/r2 - ((x-mu)^2 + y^2)/2,
+//   earth(th) = (si cos th, -si sin th, ci), th = 2 pi phase.
+// An element sees the donor when the potential along its line of sight (LOS),
+// inside the sphere of radius 1-xl1 about the donor, dips below Phi(L1).
+//
+// Everything here is written so that it also compiles as plain C++ (LFB_HD
+// empty): tests/ builds a host harness from this header to check the device
+// arithmetic on a machine without a GPU.  That harness is not part of the
+// product library.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define LFB_HD __host__ __device__ __forceinline__
+#define LFB_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define LFB_HD inline
+#define LFB_HD_NOINLINE inline
+#endif
+
+#ifndef __CUDACC__
+inline double rsqrt(double v) { return 1.0 / sqrt(v); }
+#endif
+
+namespace lfb {
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kTwoPi = 6.28318530717958647692528676655900577;
+constexpr double kDeg = kPi / 180.0;
+constexpr double kBig = 1e30;
+
+struct Roche {
+    double mu, omu, xl1, rs, phic, rin;  // rin: 0.9 x polar radius of the lobe (inscribed sphere)
+};
+
+struct Point {  // surface element: p0 fixed in the rotating frame + (xi, eta) fixed on the sky
+    double x, y, z, xi, eta;
+};
+
+struct Derivs {
+    double S, St, Sl, Stt, Stl, Sll;
+};
+
+LFB_HD void sincos_(double a, double* s, double* c)
+{
+#ifdef __CUDA_ARCH__
+    sincos(a, s, c);
+#else
+    *s = sin(a);
+    *c = cos(a);
+#endif
+}
+
+LFB_HD double clampd(double v, double lim) { return v > lim ? lim : (v < -lim ? -lim : v); }
+
+LFB_HD double pot(const Roche& R, double x, double y, double z)
+{
+    double yz = y * y + z * z, x2 = x - 1.0, xc = x - R.mu;
+    return -R.omu / sqrt(x * x + yz) - R.mu / sqrt(x2 * x2 + yz) - 0.5 * (xc * xc + y * y);
+}
+
+// L1: Newton on dPhi/dx along the line of centres from the Hill-radius estimate.
+LFB_HD bool roche_init(double q, Roche& R)
+{
+    if (!(q > 0.0) || !(q < 1e6)) return false;
+    double mu = q / (1.0 + q), omu = 1.0 - mu;
+    double m = mu < 0.5 ? mu : omu;
+    double h = cbrt(m / 3.0);
+    double rh = h * (1.0 - h / 3.0 - h * h / 9.0);
+    double x = mu < 0.5 ? 1.0 - rh : rh;
+    for (int it = 0; it < 10; ++it) {
+        double omx = 1.0 - x;
+        double f = omu / (x * x) - mu / (omx * omx) - (x - mu);
+        double fp = -2.0 * omu / (x * x * x) - 2.0 * mu / (omx * omx * omx) - 1.0;
+        x -= f / fp;
+        x = x < 1e-4 ? 1e-4 : (x > 1.0 - 1e-4 ? 1.0 - 1e-4 : x);
+    }
+    R.mu = mu;
+    R.omu = omu;
+    R.xl1 = x;
+    R.rs = 1.0 - x;
+    R.phic = pot(R, x, 0.0, 0.0);
+    // polar radius of the critical lobe, Phi(1, 0, z) = Phi_c, approached from inside
+    double q13 = cbrt(q), q23 = q13 * q13;
+    double z = 0.8 * 0.49 * q23 / (0.6 * q23 + log(1.0 + q13));
+    double cst = 0.5 * omu * omu + R.phic;
+    for (int it = 0; it < 12; ++it) {
+        double r1sq = 1.0 + z * z, ir1 = 1.0 / sqrt(r1sq);
+        double f = -omu * ir1 - mu / z - cst;
+        double fp = omu * z * ir1 * ir1 * ir1 + mu / (z * z);
+        z -= f / fp;
+    }
+    R.rin = 0.9 * z;
+    return true;
+}
+
+// Potential along LOS from the white-dwarf centre with sin(i) = u at cos(th) = c.
+struct OriginPot {
+    double P, Pu, Pc, Pl, Pll, Pul, Pcl;
+};
+LFB_HD void origin_pot(const Roche& R, double u, double c, double lam, OriginPot& o)
+{
+    double mu = R.mu;
+    double Dd = 1.0 + lam * lam - 2.0 * lam * u * c;
+    double isq = 1.0 / sqrt(Dd), i3 = isq * isq * isq, i5 = i3 * isq * isq;
+    double Dl = 2.0 * lam - 2.0 * u * c, Du = -2.0 * lam * c, Dc = -2.0 * lam * u;
+    double il = 1.0 / lam;
+    o.P = -R.omu * il - mu * isq - 0.5 * lam * lam * u * u + mu * lam * u * c - 0.5 * mu * mu;
+    o.Pl = R.omu * il * il + 0.5 * mu * i3 * Dl - lam * u * u + mu * u * c;
+    o.Pu = 0.5 * mu * i3 * Du - lam * lam * u + mu * lam * c;
+    o.Pc = 0.5 * mu * i3 * Dc + mu * lam * u;
+    o.Pll = -2.0 * R.omu * il * il * il + 0.5 * mu * (-1.5 * i5 * Dl * Dl + 2.0 * i3) - u * u;
+    o.Pul = 0.5 * mu * (-1.5 * i5 * Dl * Du - 2.0 * c * i3) - 2.0 * lam * u + mu * c;
+    o.Pcl = 0.5 * mu * (-1.5 * i5 * Dl * Dc - 2.0 * u * i3) + mu * u;
+}
+
+// roche.findphi(q, 90): full phase width of the eclipse of the white-dwarf centre seen edge-on.
+LFB_HD double findphi90(const Roche& R)
+{
+    double rl = R.rin / 0.9;
+    double c = sqrt(1.0 - rl * rl), lam = c;
+    OriginPot o;
+    for (int it = 0; it < 12; ++it) {
+        origin_pot(R, 1.0, c, lam, o);
+        double F1 = o.P - R.phic, F2 = o.Pl;
+        double det = o.Pc * o.Pll - o.Pl * o.Pcl;
+        c += (-F1 * o.Pll + F2 * o.Pl) / det;
+        lam += (-o.Pc * F2 + o.Pcl * F1) / det;
+    }
+    return acos(c) / kPi;
+}
+
+// roche.findi(q, dphi): sin(i) for which the white-dwarf centre is eclipsed for dphi of the orbit.
+LFB_HD bool findi(const Roche& R, double dphi, double maxphi, double& sini)
+{
+    if (!(dphi > 0.0) || !(dphi < maxphi)) return false;
+    double c = cos(kPi * dphi);
+    double u = cos(kPi * maxphi) / c, lam = u * c;
+    OriginPot o;
+    for (int it = 0; it < 12; ++it) {
+        origin_pot(R, u, c, lam, o);
+        double F1 = o.P - R.phic, F2 = o.Pl;
+        double det = o.Pu * o.Pll - o.Pl * o.Pul;
+        u += (-F1 * o.Pll + F2 * o.Pl) / det;
+        lam += (-o.Pu * F2 + o.Pul * F1) / det;
+    }
+    if (!(u > 0.0) || !(u <= 1.0)) return false;
+    sini = u;
+    return true;
+}
+
+// Potential and its derivatives over the (th, lam) family of LOS of one element.
+LFB_HD void ray_eval(const Roche& R, double si, double ci, const Point& T, double th, double lam, Derivs& D)
+{
+    double s, c;
+    sincos_(th, &s, &c);
+    double ex = si * c, ey = -si * s;
+    double dx = fma(lam, ex, -T.xi * s - T.eta * ci * c);
+    double dy = fma(lam, ey, -T.xi * c + T.eta * ci * s);
+    double dz = fma(lam, ci, T.eta * si);
+    double x = T.x + dx, y = T.y + dy, z = T.z + dz;
+    double tx = dy, ty = -dx;  // d/dth of the part that turns with the observer
+    double x2 = x - 1.0;
+    double yz = y * y + z * z;
+    double ir1 = rsqrt(x * x + yz), ir2 = rsqrt(x2 * x2 + yz);
+    double a1 = R.omu * ir1 * ir1 * ir1, a2 = R.mu * ir2 * ir2 * ir2;
+    double b1 = 3.0 * a1 * ir1 * ir1, b2 = 3.0 * a2 * ir2 * ir2;
+    double a12 = a1 + a2, xc = x - R.mu;
+    double gx = a1 * x + a2 * x2 - xc, gy = a12 * y - y, gz = a12 * z;
+    double x_e = x * ex + y * ey + z * ci, d_e = x_e - ex;
+    double x_t = x * tx + y * ty, d_t = x_t - tx;
+    double t_t = tx * tx + ty * ty, e_t = ex * tx + ey * ty, e_xy = ex * ex + ey * ey;
+    D.S = -R.omu * ir1 - R.mu * ir2 - 0.5 * (xc * xc + y * y);
+    D.St = gx * tx + gy * ty;
+    D.Sl = gx * ex + gy * ey + gz * ci;
+    D.Sll = a12 - b1 * x_e * x_e - b2 * d_e * d_e - e_xy;
+    D.Stt = (a12 - 1.0) * t_t - b1 * x_t * x_t - b2 * d_t * d_t - (gx * dx + gy * dy);
+    D.Stl = (a12 - 1.0) * e_t - b1 * x_e * x_t - b2 * d_e * d_t + (gx * ey - gy * ex);
+}
+
+// min over the chord of the LOS inside the bounding sphere of Phi - Phi_c (robust path only)
+LFB_HD_NOINLINE double chord_min(const Roche& R, double si, double ci, const Point& T, double th)
+{
+    double s, c;
+    sincos_(th, &s, &c);
+    double ex = si * c, ey = -si * s, ez = ci;
+    double ox = T.x - T.xi * s - T.eta * ci * c, oy = T.y - T.xi * c + T.eta * ci * s, oz = T.z + T.eta * si;
+    double wx = 1.0 - ox, wy = -oy, wz = -oz;
+    double b = wx * ex + wy * ey + wz * ez;
+    double d2 = wx * wx + wy * wy + wz * wz - b * b;
+    if (d2 >= R.rs * R.rs) return 1.0;
+    double half = sqrt(R.rs * R.rs - d2);
+    double l1 = b - half, l2 = b + half;
+    if (l1 < 0.0) l1 = 0.0;
+    if (l2 <= l1) return 1.0;
+    const int NS = 48;
+    double best = 1e300;
+    int kb = 0;
+    for (int k = 0; k < NS; ++k) {
+        double lam = l1 + (l2 - l1) * k / (NS - 1);
+        double v = pot(R, ox + lam * ex, oy + lam * ey, oz + lam * ez);
+        if (v < best) { best = v; kb = k; }
+    }
+    int ka = kb > 0 ? kb - 1 : 0, kc = kb < NS - 1 ? kb + 1 : NS - 1;
+    double a = l1 + (l2 - l1) * ka / (NS - 1), cc = l1 + (l2 - l1) * kc / (NS - 1);
+    const double gr = 0.6180339887498949;
+    double x1 = cc - gr * (cc - a), x2 = a + gr * (cc - a);
+    double f1 = pot(R, ox + x1 * ex, oy + x1 * ey, oz + x1 * ez);
+    double f2 = pot(R, ox + x2 * ex, oy + x2 * ey, oz + x2 * ez);
+    for (int it = 0; it < 70; ++it) {
+        if (f1 < f2) {
+            cc = x2; x2 = x1; f2 = f1;
+            x1 = cc - gr * (cc - a);
+            f1 = pot(R, ox + x1 * ex, oy + x1 * ey, oz + x1 * ez);
+        } else {
+            a = x1; x1 = x2; f1 = f2;
+            x2 = a + gr * (cc - a);
+            f2 = pot(R, ox + x2 * ex, oy + x2 * ey, oz + x2 * ez);
+        }
+    }
+    double v = f1 < f2 ? f1 : f2;
+    if (best < v) v = best;
+    return v - R.phic;
+}
+
+// Last-resort ingress/egress: phase scan + golden section + bisection.  Taken by
+// about one element in 10^6; kept out of line so it costs no registers on the fast path.
+LFB_HD_NOINLINE int ingress_egress_robust(const Roche& R, double si, double ci, const Point& T, double* ph_in,
+                                          double* ph_out)
+{
+    const int NSCAN = 384;
+    double psi = atan2(T.y, 1.0 - T.x);
+    double half = 0.5 * kPi, step = 2.0 * half / (NSCAN - 1), th_lo = psi - half;
+    int kb = 0;
+    double best = 1e300;
+    for (int k = 0; k < NSCAN; ++k) {
+        double g = chord_min(R, si, ci, T, th_lo + step * k);
+        if (g < best) { best = g; kb = k; }
+    }
+    if (kb == 0 || kb == NSCAN - 1) return 0;
+    double a = th_lo + step * (kb - 1), cc = th_lo + step * (kb + 1);
+    const double gr = 0.6180339887498949;
+    double x1 = cc - gr * (cc - a), x2 = a + gr * (cc - a);
+    double f1 = chord_min(R, si, ci, T, x1), f2 = chord_min(R, si, ci, T, x2);
+    for (int it = 0; it < 60; ++it) {
+        if (f1 < f2) {
+            cc = x2; x2 = x1; f2 = f1;
+            x1 = cc - gr * (cc - a);
+            f1 = chord_min(R, si, ci, T, x1);
+        } else {
+            a = x1; x1 = x2; f1 = f2;
+            x2 = a + gr * (cc - a);
+            f2 = chord_min(R, si, ci, T, x2);
+        }
+    }
+    double thm = f1 < f2 ? x1 : x2, gm = f1 < f2 ? f1 : f2;
+    if (best < gm) { gm = best; thm = th_lo + step * kb; }
+    if (!(gm < 0.0)) return 0;
+    int kl = (int)floor((thm - th_lo) / step);
+    while (kl > 0 && chord_min(R, si, ci, T, th_lo + step * kl) < 0.0) --kl;
+    int kr = (int)ceil((thm - th_lo) / step);
+    while (kr < NSCAN - 1 && chord_min(R, si, ci, T, th_lo + step * kr) < 0.0) ++kr;
+    if (chord_min(R, si, ci, T, th_lo + step * kl) < 0.0 || chord_min(R, si, ci, T, th_lo + step * kr) < 0.0)
+        return 0;
+    double lo = th_lo + step * kl, hi = thm;
+    for (int it = 0; it < 90; ++it) {
+        double m = 0.5 * (lo + hi);
+        if (chord_min(R, si, ci, T, m) < 0.0) hi = m; else lo = m;
+    }
+    *ph_in = 0.5 * (lo + hi) / kTwoPi;
+    lo = thm;
+    hi = th_lo + step * kr;
+    for (int it = 0; it < 90; ++it) {
+        double m = 0.5 * (lo + hi);
+        if (chord_min(R, si, ci, T, m) < 0.0) lo = m; else hi = m;
+    }
+    *ph_out = 0.5 * (lo + hi) / kTwoPi;
+    return 1;
+}
+
+constexpr int kMinIters = 12;   // deepest-LOS Newton (shallow elements only), early exit
+constexpr int kRootIters = 16;  // grazing-LOS Newton, early exit
+
+// Ingress/egress phases (cycles) of one element; 0 if it is never eclipsed.
+// Fast path: 2-D Newton on (th, lam) for the two LOS that graze the critical
+// surface (Phi = Phi_c, dPhi/dlam = 0), started from the tangents to a sphere
+// inscribed in the lobe (deep elements) or from the osculating parabola at the
+// deepest LOS (shallow elements); every root is verified, anything unverified
+// goes to ingress_egress_robust.
+LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, double* ph_in, double* ph_out)
+{
+    double psi = atan2(T.y - T.xi, 1.0 - T.x + T.eta * ci);
+    double th = psi, s, c;
+    sincos_(th, &s, &c);
+    double ex = si * c, ey = -si * s;
+    double wx = 1.0 - (T.x - T.xi * s - T.eta * ci * c);
+    double wy = -(T.y - T.xi * c + T.eta * ci * s);
+    double wz = -(T.z + T.eta * si);
+    double lam = wx * ex + wy * ey + wz * ci;
+    double w2 = wx * wx + wy * wy + wz * wz;
+    if (w2 - lam * lam >= R.rs * R.rs || lam <= 0.0) return 0;
+    double rxy = si * sqrt(wx * wx + wy * wy);
+    double tang = sqrt(w2 - R.rin * R.rin);
+    double cosd = (tang - wz * ci) / rxy;
+    Derivs D;
+    double th0, th1, lam0, lam1, thm = psi;
+    if (cosd < 0.995) {
+        double del = acos(cosd > -1.0 ? cosd : -1.0);
+        th0 = psi - del;
+        th1 = psi + del;
+        lam0 = lam1 = tang;
+    } else {
+        for (int it = 0; it < 5; ++it) {
+            ray_eval(R, si, ci, T, th, lam, D);
+            if (!(D.Sll > 0.0)) return 0;  // no potential minimum along the closest LOS: out of reach
+            lam += clampd(-D.Sl / D.Sll, 0.1);
+        }
+        bool conv = false;
+        for (int it = 0; it < kMinIters; ++it) {
+            ray_eval(R, si, ci, T, th, lam, D);
+            double det = D.Stt * D.Sll - D.Stl * D.Stl;
+            if (!(D.Sll > 0.0) || !(det > 0.0)) {
+                if (D.S >= R.phic) return 0;
+                return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
+            }
+            double dth = clampd(-(D.St * D.Sll - D.Sl * D.Stl) / det, 0.1);
+            double dl = clampd(-(D.Sl * D.Stt - D.St * D.Stl) / det, 0.1);
+            th += dth;
+            lam += dl;
+            if (fabs(dth) < 1e-7 && fabs(dl) < 1e-7) { conv = true; break; }
+        }
+        if (!conv) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
+        ray_eval(R, si, ci, T, th, lam, D);
+        double g0 = D.S - R.phic;
+        if (!(g0 < 0.0)) return 0;  // the deepest LOS clears the lobe
+        double kappa = D.Stt - D.Stl * D.Stl / D.Sll;
+        if (!(D.Sll > 0.0) || !(kappa > 0.0)) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
+        double del = sqrt(-2.0 * g0 / kappa), slope = -D.Stl / D.Sll;
+        thm = th;
+        th0 = th - del;
+        th1 = th + del;
+        lam0 = lam - slope * del;
+        lam1 = lam + slope * del;
+    }
+    double res[2];
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        double sg = side ? 1.0 : -1.0;
+        th = side ? th1 : th0;
+        lam = side ? lam1 : lam0;
+        bool conv = false;
+        for (int it = 0; it < kRootIters; ++it) {
+            ray_eval(R, si, ci, T, th, lam, D);
+            double F1 = D.S - R.phic, F2 = D.Sl;
+            double idet = 1.0 / (D.St * D.Sll - D.Sl * D.Stl);
+            double dth = clampd((-F1 * D.Sll + F2 * D.Sl) * idet, 0.2);
+            double dl = clampd((-D.St * F2 + D.Stl * F1) * idet, 0.2);
+            if (sg * (th + dth - thm) <= 0.0) {  // stay on this side of the deepest LOS
+                dth = 0.5 * (thm - th);
+                dl *= 0.5;
+            }
+            th += dth;
+            lam += dl;
+            if (fabs(dth) < 1e-13 && fabs(dl) < 1e-10) { conv = true; break; }
+        }
+        // accept only a converged grazing LOS of the right kind
+        ray_eval(R, si, ci, T, th, lam, D);
+        sincos_(th, &s, &c);
+        double xx = T.x - T.xi * s - T.eta * ci * c + lam * si * c - 1.0;
+        double yy = T.y - T.xi * c + T.eta * ci * s - lam * si * s;
+        double zz = T.z + T.eta * si + lam * ci;
+        bool ok = conv && D.Sll > 0.0 && lam > 0.0 && xx * xx + yy * yy + zz * zz <= R.rs * R.rs &&
+                  (side ? D.St > 0.0 : D.St < 0.0) && fabs(th - psi) < 0.5 * kPi;
+        if (!ok) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
+        res[side] = th;
+    }
+    if (!(res[0] < res[1])) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
+    *ph_in = res[0] * (1.0 / kTwoPi);
+    *ph_out = res[1] * (1.0 / kTwoPi);
+    return 1;
+}
+
+// ---- ballistic stream from L1 (roche.bspot): fixed-sequence Gragg-Bulirsch-Stoer ----
+constexpr double kStreamEps = 1e-5;
+constexpr double kStreamH0 = 0.6;
+constexpr int kStreamMaxSteps = 400;
+
+LFB_HD void stream_rhs(const Roche& R, const double y[4], double f[4])
+{
+    double x = y[0], yy = y[1], x2 = x - 1.0;
+    double ysq = yy * yy;
+    double ir1 = rsqrt(x * x + ysq), ir2 = rsqrt(x2 * x2 + ysq);
+    double a1 = R.omu * ir1 * ir1 * ir1, a2 = R.mu * ir2 * ir2 * ir2;
+    f[0] = y[2];
+    f[1] = y[3];
+    f[2] = -(a1 * x + a2 * x2 - (x - R.mu)) + 2.0 * y[3];
+    f[3] = -((a1 + a2) * yy - yy) - 2.0 * y[2];
+}
+
+LFB_HD_NOINLINE void gbs_step(const Roche& R, const double y0[4], double H, double yout[4])
+{
+    double T[6][4];
+    double f0[4];
+    stream_rhs(R, y0, f0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        int n = 2 * (k + 1);
+        double h = H / n;
+        double z0[4], z1[4], f[4];
+        for (int j = 0; j < 4; ++j) { z0[j] = y0[j]; z1[j] = y0[j] + h * f0[j]; }
+        for (int m = 1; m < n; ++m) {
+            stream_rhs(R, z1, f);
+            for (int j = 0; j < 4; ++j) {
+                double t = z0[j] + 2.0 * h * f[j];
+                z0[j] = z1[j];
+                z1[j] = t;
+            }
+        }
+        stream_rhs(R, z1, f);
+        for (int j = 0; j < 4; ++j) T[k][j] = 0.5 * (z0[j] + z1[j] + h * f[j]);
+#pragma unroll
+        for (int m = k - 1; m >= 0; --m) {
+            double ratio = (double)(k + 1) / (double)(m + 1);
+            double fac = 1.0 / (ratio * ratio - 1.0);
+            for (int j = 0; j < 4; ++j) T[m][j] = T[m + 1][j] + (T[m + 1][j] - T[m][j]) * fac;
+        }
+    }
+    for (int j = 0; j < 4; ++j) yout[j] = T[0][j];
+}
+
+// (x, y, vx, vy) where the stream from L1 first reaches radius rad from the white dwarf;
+// false if it passes closest approach without getting there (roche.bspot raises).
+LFB_HD bool bspot(const Roche& R, double rad, double out[4])
+{
+    if (!(rad > 0.0) || !(rad < R.xl1 - 2.0 * kStreamEps)) return false;
+    double A = R.omu / (R.xl1 * R.xl1 * R.xl1) + R.mu / (R.rs * R.rs * R.rs);
+    double l2 = 0.5 * ((A - 2.0) + sqrt(A * (9.0 * A - 8.0)));
+    double l1 = sqrt(l2);
+    double m1 = (l2 - 2.0 * A - 1.0) / (2.0 * l1);
+    double y[4] = {R.xl1 - kStreamEps, -m1 * kStreamEps, -l1 * kStreamEps, -l1 * m1 * kStreamEps};
+    for (int step = 0; step < kStreamMaxSteps; ++step) {
+        double x2 = y[0] - 1.0, ysq = y[1] * y[1];
+        double r1sq = y[0] * y[0] + ysq, r2sq = x2 * x2 + ysq;
+        double w2 = R.omu / (r1sq * sqrt(r1sq)) + R.mu / (r2sq * sqrt(r2sq)) + 1.0;
+        double H = kStreamH0 / sqrt(w2);
+        double yn[4];
+        gbs_step(R, y, H, yn);
+        double r0 = sqrt(r1sq), rn = sqrt(yn[0] * yn[0] + yn[1] * yn[1]);
+        if (rn <= rad) {
+            double h = H * (r0 - rad) / (r0 - rn);
+            for (int it = 0; it < 8; ++it) {
+                gbs_step(R, y, h, yn);
+                rn = sqrt(yn[0] * yn[0] + yn[1] * yn[1]);
+                h -= (rn - rad) * rn / (yn[0] * yn[2] + yn[1] * yn[3]);
+            }
+            gbs_step(R, y, h, yn);
+            for (int j = 0; j < 4; ++j) out[j] = yn[j];
+            return true;
+        }
+        if (yn[0] * yn[2] + yn[1] * yn[3] >= 0.0) return false;
+        for (int j = 0; j < 4; ++j) y[j] = yn[j];
+    }
+    return false;
+}
+
+// Radius of the critical surface from the donor's centre along unit vector d, plus the
+// potential gradient there.  Newton from inside the lobe (monotone), then one safeguarded polish.
+LFB_HD double donor_radius(const Roche& R, double dx, double dy, double dz, double g[3])
+{
+    double r = R.rin;
+    double gx = 0, gy = 0, gz = 0;
+    for (int it = 0; it < 40; ++it) {
+        double x = 1.0 + r * dx, y = r * dy, z = r * dz;
+        double yz = y * y + z * z;
+        double ir1 = rsqrt(x * x + yz), ir2 = 1.0 / r;
+        double a1 = R.omu * ir1 * ir1 * ir1, a2 = R.mu * ir2 * ir2 * ir2;
+        double xc = x - R.mu;
+        double f = -R.omu * ir1 - R.mu * ir2 - 0.5 * (xc * xc + y * y) - R.phic;
+        gx = a1 * x + a2 * (x - 1.0) - xc;
+        gy = (a1 + a2) * y - y;
+        gz = (a1 + a2) * z;
+        double fp = gx * dx + gy * dy + gz * dz;
+        double dr = -f / fp;
+        if (r + dr > R.rs) dr = 0.5 * (R.rs - r);
+        r += dr;
+        if (fabs(dr) < 1e-15) break;
+    }
+    double x = 1.0 + r * dx, y = r * dy, z = r * dz;
+    double yz = y * y + z * z;
+    double ir1 = rsqrt(x * x + yz), ir2 = 1.0 / r;
+    double a1 = R.omu * ir1 * ir1 * ir1, a2 = R.mu * ir2 * ir2 * ir2;
+    g[0] = a1 * x + a2 * (x - 1.0) - (x - R.mu);
+    g[1] = (a1 + a2) * y - y;
+    g[2] = (a1 + a2) * z;
+    (void)gx; (void)gy; (void)gz;
+    return r;
+}
+
+// Prior.ln_prob (model.py:83-113)
+LFB_HD double prior_ln_prob(int type, double p1, double p2, double norm, double val)
+{
+    const double kLnSqrt2Pi = 0.91893853320467274178;
+    const double kLnMinDenormal = -744.44007192138126;
+    const double ninf = -INFINITY;
+    switch (type) {
+    case 1:
+        if (val <= 0.0) return ninf;
+        // fall through
+    case 0: {
+        double z = (val - p1) / p2;
+        double t = -0.5 * z * z - kLnSqrt2Pi;
+        if (!(t >= kLnMinDenormal)) return ninf;  // scipy's pdf underflows to 0 (model.py:85-89)
+        return t - log(p2);
+    }
+    case 2:
+        return (val > p1 && val < p2) ? log(1.0 / fabs(p1 - p2)) : ninf;
+    case 3:
+        return (val > p1 && val < p2) ? log(1.0 / norm / val) : ninf;
+    case 4:
+        return (val > 0.0 && val < p2) ? log(1.0 / norm / (val + p1)) : ninf;
+    }
+    return ninf;
+}
+
+}  // namespace lfb
