@@ -119,6 +119,10 @@ long long lfb_launch_count(const lfb_handle *h);
  * the stream it ran on; valid after the stream is synchronised.  <0 if none. */
 float lfb_last_kernel_ms(lfb_handle *h);
 
+/* Measurement aid (no reference counterpart): sustained FP64 FMA rate of the device in
+ * TFLOP/s (FMA = 2), the roofline denominator bench.py reports against. */
+int lfb_measure_fp64_peak(lfb_handle *h, int iters, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ PRIOR_CODES = {"gauss": 0, "gaussPos": 1, "uniform": 2, "log_uniform": 3, "mod_j
 EXPORTS = (
     "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_get_config", "lfb_set_layout",
     "lfb_set_priors", "lfb_set_lightcurves", "lfb_log_prob", "lfb_calc_flux", "lfb_roche",
-    "lfb_launch_count", "lfb_last_kernel_ms",
+    "lfb_launch_count", "lfb_last_kernel_ms", "lfb_measure_fp64_peak",
 )
 
 
@@ -71,6 +71,7 @@ def load():
     lib.lfb_launch_count.restype = C.c_longlong
     lib.lfb_last_kernel_ms.argtypes = [vp]
     lib.lfb_last_kernel_ms.restype = C.c_float
+    lib.lfb_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
     _lib = lib
     return lib
 
@@ -136,6 +137,12 @@ class Engine:
 
     def last_kernel_ms(self):
         return float(self._lib.lfb_last_kernel_ms(self._h))
+
+    def measure_fp64_peak(self, iters=20000):
+        """Sustained DFMA rate of this device in TFLOP/s (roofline denominator)."""
+        out = C.c_double()
+        self._check(self._lib.lfb_measure_fp64_peak(self._h, int(iters), C.byref(out)), "lfb_measure_fp64_peak")
+        return out.value
 
     # -- flattened tree -----------------------------------------------------------------
     def set_layout(self, ndim, npars, gather, consts):

@@ -521,6 +521,24 @@ __global__ void roche_kernel(int which, long long n, const double* __restrict__ 
     ok[i] = good;
 }
 
+// ---------------------------------------------------------------- fp64_peak_kernel
+// DFMA throughput probe: the FP64 roofline denominator is measured on the device the
+// numbers are taken on (MEASURED_PEAKS.json has no FP64 vector figure).
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double x, double y, double* __restrict__ sink)
+{
+    double a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = fma(a[k], x, y);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    if (s == 123.456) sink[0] = s;
+}
+
 }  // namespace
 
 // ================================================================= host side / C ABI
@@ -1025,6 +1043,34 @@ int lfb_roche(lfb_handle* h, int which, long long n, const double* a, const doub
     cleanup();
     if (e != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
     if ((e = cudaGetLastError()) != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    return LFB_OK;
+}
+
+int lfb_measure_fp64_peak(lfb_handle* h, int iters, double* tflops)
+{
+    if (!h || !tflops || iters <= 0) return LFB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(h->out.reserve(64));
+    const int blocks = h->sm_count * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, h->stream);
+        fp64_peak_kernel<<<blocks, 256, 0, h->stream>>>(iters, 0.999999, 1e-7, h->out.as<double>());
+        cudaEventRecord(e1, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(h, LFB_ECUDA, cudaGetErrorString(e)); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 16.0 * iters * 256.0 * blocks / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    h->launches += 5;
+    *tflops = best;
     return LFB_OK;
 }
 
