@@ -36,7 +36,7 @@ UNIT = "lightcurve evals/s"
 # FP64 operations one lightcurve evaluation of the bench workload executes (FMA = 2;
 # add/mul/compare-select = 1), from the ncu instruction counters of the same command
 # (profiles/): see DESIGN.md "Roofline accounting".  Keyed by kernel revision.
-FLOPS_PER_LIGHTCURVE = {"r1-direct": None}
+FLOPS_PER_LIGHTCURVE = {"r1-direct": None, "r1-events": None}
 
 
 def env_int(name, default):
@@ -210,7 +210,7 @@ def run_gpu(args, rank, local_rank, world):
         dist.barrier()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms = []
+    kernel_ms, stage_ms = [], []
     for i in range(args.steps):
         flush.fill_(float(i))  # evict L2 between timed iterations (outside the event pair)
         ev[i][0].record()
@@ -218,6 +218,7 @@ def run_gpu(args, rank, local_rank, world):
         ev[i][1].record()
         ev[i][1].synchronize()
         kernel_ms.append(eng.last_kernel_ms())
+        stage_ms.append(eng.last_stage_ms())
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -248,7 +249,8 @@ def run_gpu(args, rank, local_rank, world):
         value = evals_per_step * args.steps / (total_ms * 1e-3)
         k_ms = float(np.mean(kernel_ms))
         flops_lc = FLOPS_PER_LIGHTCURVE.get(args.kernel_rev)
-        roof = {"bound": "fp64", "kernel": "lightcurve_kernel", "kernel_ms": k_ms,
+        stages = {k: float(np.mean([d[k] for d in stage_ms])) for k in stage_ms[0]}
+        roof = {"bound": "fp64", "kernel": "elements_kernel + flux_kernel", "kernel_ms": k_ms, "stage_ms": stages,
                 "kernel_share_of_step": k_ms / (total_ms / args.steps),
                 "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "DFMA probe on this device, this run",
                 "traffic": None, "flops_per_lightcurve": flops_lc}
@@ -303,7 +305,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0, help="reference arm: walkers per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--kernel-rev", default="r1-direct")
+    ap.add_argument("--kernel-rev", default="r1-events")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":

@@ -115,8 +115,11 @@ int lfb_roche(lfb_handle *h, int which, long long n, const double *a, const doub
 
 /* counters for bench.py: kernels launched by this handle since creation */
 long long lfb_launch_count(const lfb_handle *h);
-/* device time (ms) of the last lfb_log_prob's lightcurve kernel, measured with CUDA events on
- * the stream it ran on; valid after the stream is synchronised.  <0 if none. */
+/* Device time (ms) of the stages of the last lfb_log_prob (its last batch), from CUDA events
+ * recorded on the stream the kernels ran on; valid once that stream is synchronised.
+ * out = {walker, stream, elements (4 launches), flux, finish, total}. */
+int lfb_last_stage_ms(lfb_handle *h, float out[6]);
+/* elements + flux of the same call, <0 if none */
 float lfb_last_kernel_ms(lfb_handle *h);
 
 /* Measurement aid (no reference counterpart): sustained FP64 FMA rate of the device in

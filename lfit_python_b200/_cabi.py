@@ -21,7 +21,7 @@ PRIOR_CODES = {"gauss": 0, "gaussPos": 1, "uniform": 2, "log_uniform": 3, "mod_j
 EXPORTS = (
     "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_get_config", "lfb_set_layout",
     "lfb_set_priors", "lfb_set_lightcurves", "lfb_log_prob", "lfb_calc_flux", "lfb_roche",
-    "lfb_launch_count", "lfb_last_kernel_ms", "lfb_measure_fp64_peak",
+    "lfb_launch_count", "lfb_last_kernel_ms", "lfb_last_stage_ms", "lfb_measure_fp64_peak",
 )
 
 
@@ -72,6 +72,7 @@ def load():
     lib.lfb_last_kernel_ms.argtypes = [vp]
     lib.lfb_last_kernel_ms.restype = C.c_float
     lib.lfb_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
+    lib.lfb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = lib
     return lib
 
@@ -137,6 +138,12 @@ class Engine:
 
     def last_kernel_ms(self):
         return float(self._lib.lfb_last_kernel_ms(self._h))
+
+    def last_stage_ms(self):
+        """Device ms of {walker, stream, elements, flux, finish, total} of the last log_prob."""
+        out = (C.c_float * 6)()
+        self._check(self._lib.lfb_last_stage_ms(self._h, out), "lfb_last_stage_ms")
+        return dict(zip(("walker", "stream", "elements", "flux", "finish", "total"), [float(x) for x in out]))
 
     def measure_fp64_peak(self, iters=20000):
         """Sustained DFMA rate of this device in TFLOP/s (roofline denominator)."""

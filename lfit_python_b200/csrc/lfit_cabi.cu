@@ -1,0 +1,733 @@
+// lfit_cabi.cu -- C ABI (include/lfit_b200.h) over the sm_100a kernels in cv_kernels.cuh.
+//
+// Host side only: buffer management, the one-off preprocessing of light curves into
+// sorted exposure samples, and kernel launches.  There is no CPU implementation of the
+// model here: without a CUDA device lfb_create fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "cv_kernels.cuh"
+
+using namespace lfb;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned_host = false;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        release();
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    void release()
+    {
+        if (p) { if (pinned_host) cudaFreeHost(p); else cudaFree(p); }
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() { return (T*)p; }
+};
+
+// Sorted exposure samples of a set of light curves (device copies)
+struct SampleSet {
+    DevBuf lc_off, y, ye, S, cosS, sinS, pos, chunk_off, chunk_j;
+    int max_nph = 0;
+    long long total = 0;
+    void release()
+    {
+        DevBuf* b[] = {&lc_off, &y, &ye, &S, &cosS, &sinS, &pos, &chunk_off, &chunk_j};
+        for (DevBuf* x : b) x->release();
+    }
+    DevSamples view()
+    {
+        DevSamples v;
+        v.lc_off = lc_off.as<long long>();
+        v.y = y.as<double>();
+        v.ye = ye.as<double>();
+        v.S = S.as<double>();
+        v.cosS = cosS.as<double>();
+        v.sinS = sinS.as<double>();
+        v.pos = pos.as<int>();
+        v.chunk_off = chunk_off.as<long long>();
+        v.chunk_j = chunk_j.as<int>();
+        return v;
+    }
+};
+
+enum { ST_WALKER = 0, ST_STREAM, ST_ELEMENTS, ST_FLUX, ST_FINISH, ST_COUNT };
+
+}  // namespace
+
+struct lfb_handle {
+    int device = 0;
+    lfb_config cfg{};
+    GridCfg grid{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    bool ev_valid = false;
+    std::string err;
+    long long launches = 0;
+    int sm_count = 148;
+    int max_smem = 0;
+    int Mc = 512;
+    long long max_jobs_per_batch = 262144;
+    // layout
+    bool have_layout = false, have_lc = false;
+    int ndim = 0, n_ecl = 0, npars = 0, n_prior = 0;
+    DevBuf gather, consts, psrc, ptype, pisvar, pp1, pp2, pnorm, donor_off;
+    SampleSet lc, cf_lc;
+    // calc_flux scratch
+    DevBuf cf_gather, cf_pars, cf_tot, cf_comp;
+    // work
+    DevBuf theta, out, chisq, ws, js, wd_io, don, disc_io, bs_io, bs_b, model_scratch;
+    DevBuf h_in, h_out, h_chisq;
+    lfb_handle() { h_in.pinned_host = h_out.pinned_host = h_chisq.pinned_host = true; }
+};
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return LFB_ECUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+static int fail(lfb_handle* h, int code, const std::string& msg)
+{
+    h->err = msg;
+    return code;
+}
+
+static bool is_device_ptr(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int upload(lfb_handle* h, DevBuf& b, const void* src, size_t bytes)
+{
+    CK(b.reserve(bytes ? bytes : 8));
+    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyDefault, h->stream));
+    return LFB_OK;
+}
+
+static int donor_ring_count(int nth, int k)
+{
+    double th = (k + 0.5) * lfb::kPi / nth;
+    return (int)fmax(1.0, floor(0.5 * nth * sin(th) + 0.5));
+}
+
+// Merge the K exposure samples of every point of every light curve, wrap them to
+// [-0.5, 0.5], sort per eclipse, and record where each (point, node) landed.  Done once
+// per set_lightcurves / per calc_flux phase grid; shared by all walkers.
+static int build_samples(lfb_handle* h, SampleSet& ss, int n_ecl, const long long* off, const double* phase,
+                         const double* width, const double* y, const double* ye)
+{
+    const GridCfg& G = h->grid;
+    const int K = G.n_quad, Mc = h->Mc;
+    const long long total = off[n_ecl];
+    std::vector<double> S((size_t)total * K), cS((size_t)total * K), sS((size_t)total * K);
+    std::vector<int> pos((size_t)total * K);
+    std::vector<long long> chunk_off(n_ecl + 1, 0);
+    std::vector<int> chunk_j;
+    int max_nph = 0;
+    std::vector<int> order;
+    std::vector<double> raw;
+    for (int e = 0; e < n_ecl; ++e) {
+        const long long o = off[e];
+        const int n_ph = (int)(off[e + 1] - o), M = n_ph * K;
+        max_nph = std::max(max_nph, n_ph);
+        raw.resize(M);
+        order.resize(M);
+        for (int j = 0; j < n_ph; ++j)
+            for (int k = 0; k < K; ++k) {
+                double s = phase[o + j] + G.quad_off[k] * (width ? width[o + j] : 0.0);
+                raw[j * K + k] = s - rint(s);
+            }
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return raw[a] < raw[b]; });
+        for (int r = 0; r < M; ++r) {
+            int src = order[r];
+            S[o * K + r] = raw[src];
+            cS[o * K + r] = cos(kTwoPi * raw[src]);
+            sS[o * K + r] = sin(kTwoPi * raw[src]);
+            pos[o * K + src] = r;
+        }
+        const int n_chunks = (M + Mc - 1) / Mc;
+        chunk_off[e + 1] = chunk_off[e] + n_chunks;
+        for (int c = 0; c < n_chunks; ++c) {
+            int jlo = n_ph, jhi = -1;
+            for (int r = c * Mc; r < std::min(M, (c + 1) * Mc); ++r) {
+                int j = order[r] / K;
+                jlo = std::min(jlo, j);
+                jhi = std::max(jhi, j);
+            }
+            chunk_j.push_back(jlo);
+            chunk_j.push_back(jhi);
+        }
+    }
+    if (chunk_j.empty()) chunk_j.assign(2, 0);
+    std::vector<double> zeros, ones;
+    if (!y) zeros.assign((size_t)total, 0.0);
+    if (!ye) ones.assign((size_t)total, 1.0);
+    int rc;
+    if ((rc = upload(h, ss.lc_off, off, sizeof(long long) * (size_t)(n_ecl + 1)))) return rc;
+    if ((rc = upload(h, ss.y, y ? y : zeros.data(), sizeof(double) * (size_t)total))) return rc;
+    if ((rc = upload(h, ss.ye, ye ? ye : ones.data(), sizeof(double) * (size_t)total))) return rc;
+    if ((rc = upload(h, ss.S, S.data(), sizeof(double) * S.size()))) return rc;
+    if ((rc = upload(h, ss.cosS, cS.data(), sizeof(double) * cS.size()))) return rc;
+    if ((rc = upload(h, ss.sinS, sS.data(), sizeof(double) * sS.size()))) return rc;
+    if ((rc = upload(h, ss.pos, pos.data(), sizeof(int) * pos.size()))) return rc;
+    if ((rc = upload(h, ss.chunk_off, chunk_off.data(), sizeof(long long) * chunk_off.size()))) return rc;
+    if ((rc = upload(h, ss.chunk_j, chunk_j.data(), sizeof(int) * chunk_j.size()))) return rc;
+    CK(cudaStreamSynchronize(h->stream));  // the host vectors die here
+    ss.max_nph = max_nph;
+    ss.total = total;
+    return LFB_OK;
+}
+
+static size_t flux_smem_fixed(const GridCfg& G, int Mc, int nF)
+{
+    size_t NI = (size_t)G.n_wd + G.n_disc + G.n_bs, NDQ = (size_t)G.n_donor_q;
+    return 8 * (3 * NI + 4 * NDQ + 20 * NDQ + (size_t)kNumArr * Mc + (size_t)nF * Mc + G.n_disc_r + G.n_wd_rings);
+}
+
+// One pass of the pipeline over walkers [0, n) (device pointers, one batch).
+static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleSet& ss, int what, int flags, int mode,
+                     long long n, const double* d_theta, double* d_out, double* d_chi, double* d_tot, double* d_comp,
+                     bool record)
+{
+    const GridCfg& G = h->grid;
+    const long long njobs = n * L.n_ecl;
+    CK(h->ws.reserve(sizeof(WalkerScal) * (size_t)n));
+    CK(h->js.reserve(sizeof(JobScal) * (size_t)njobs));
+    CK(h->wd_io.reserve(sizeof(double2) * (size_t)n * G.n_wd_half));
+    CK(h->don.reserve(sizeof(double4) * (size_t)n * G.n_donor_q));
+    CK(h->disc_io.reserve(sizeof(double2) * (size_t)njobs * G.n_disc_half));
+    CK(h->bs_io.reserve(sizeof(double2) * (size_t)njobs * G.n_bs));
+    CK(h->bs_b.reserve(sizeof(double) * (size_t)njobs * G.n_bs));
+    if (record) CK(cudaEventRecord(h->ev[ST_WALKER], st));
+    walker_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, what, flags, n, d_theta, h->ws.as<WalkerScal>());
+    if (record) CK(cudaEventRecord(h->ev[ST_STREAM], st));
+    stream_kernel<<<(unsigned)((njobs + 63) / 64), 64, 0, st>>>(L, what, flags, njobs, d_theta, h->ws.as<WalkerScal>(),
+                                                                 h->js.as<JobScal>());
+    h->launches += 2;
+    if (record) CK(cudaEventRecord(h->ev[ST_ELEMENTS], st));
+    if (what != LFB_LN_PRIOR) {
+        ElemArgs E;
+        E.L = L;
+        E.G = G;
+        E.what = what;
+        E.flags = flags;
+        E.n = n;
+        E.njobs = njobs;
+        E.theta = d_theta;
+        E.ws = h->ws.as<WalkerScal>();
+        E.js = h->js.as<JobScal>();
+        E.wd_io = h->wd_io.as<double2>();
+        E.don = h->don.as<double4>();
+        E.disc_io = h->disc_io.as<double2>();
+        E.bs_io = h->bs_io.as<double2>();
+        E.bs_b = h->bs_b.as<double>();
+        auto blocks = [&](long long units, int per_unit) {
+            long long padded = (per_unit + 31) & ~31;
+            return (unsigned)((units * padded + kElemThreads - 1) / kElemThreads);
+        };
+        if (!(flags & LFB_FLAG_SKIP_DISC)) {
+            elements_kernel<1><<<blocks(njobs, G.n_disc_half), kElemThreads, 0, st>>>(E);
+            h->launches++;
+        }
+        if (!(flags & LFB_FLAG_SKIP_BS)) {
+            elements_kernel<2><<<blocks(njobs, G.n_bs), kElemThreads, 0, st>>>(E);
+            h->launches++;
+        }
+        if (!(flags & LFB_FLAG_SKIP_WD)) {
+            elements_kernel<0><<<blocks(n, G.n_wd_half), kElemThreads, 0, st>>>(E);
+            h->launches++;
+        }
+        if (!(flags & LFB_FLAG_SKIP_DONOR)) {
+            elements_kernel<3><<<blocks(n, G.n_donor_q), kElemThreads, 0, st>>>(E);
+            h->launches++;
+        }
+        if (record) CK(cudaEventRecord(h->ev[ST_FLUX], st));
+        FluxArgs A;
+        A.L = L;
+        A.G = G;
+        A.smp = ss.view();
+        A.what = what;
+        A.flags = flags;
+        A.mode = mode;
+        A.Mc = h->Mc;
+        A.max_nph = ss.max_nph;
+        A.njobs = njobs;
+        A.theta = d_theta;
+        A.ws = E.ws;
+        A.js = E.js;
+        A.wd_io = E.wd_io;
+        A.don = E.don;
+        A.disc_io = E.disc_io;
+        A.bs_io = E.bs_io;
+        A.bs_b = E.bs_b;
+        A.chisq = d_chi;
+        A.flux_tot = d_tot;
+        A.flux_comp = d_comp;
+        const int nF = mode ? 4 : 1;
+        size_t fixed = flux_smem_fixed(G, h->Mc, nF);
+        size_t model_bytes = sizeof(double) * (size_t)nF * ss.max_nph;
+        size_t budget = (size_t)h->max_smem - 2048;
+        if (fixed > budget) return fail(h, LFB_EINVAL, "surface grid too dense for the flux kernel's shared memory");
+        // two CTAs per SM if possible: per-point partial sums go through L2 when they do not fit
+        const size_t two_cta = (size_t)112 * 1024;
+        if (fixed + model_bytes <= two_cta) A.model_in_smem = 1;
+        else if (fixed <= two_cta) A.model_in_smem = 0;
+        else A.model_in_smem = fixed + model_bytes <= budget ? 1 : 0;
+        size_t smem = fixed + (A.model_in_smem ? model_bytes : 0);
+        int grid = (int)std::min<long long>(njobs, (long long)h->sm_count * 16);
+        if (grid < 1) grid = 1;
+        A.model_scratch = nullptr;
+        if (!A.model_in_smem) {
+            CK(h->model_scratch.reserve(sizeof(double) * (size_t)grid * nF * ss.max_nph));
+            A.model_scratch = h->model_scratch.as<double>();
+        }
+        CK(cudaFuncSetAttribute(flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        flux_kernel<<<grid, kFluxThreads, smem, st>>>(A);
+        h->launches++;
+    } else if (record) {
+        CK(cudaEventRecord(h->ev[ST_FLUX], st));
+    }
+    if (record) CK(cudaEventRecord(h->ev[ST_FINISH], st));
+    if (d_out) {
+        finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(what, L.n_ecl, n, h->ws.as<WalkerScal>(), d_chi, d_out);
+        h->launches++;
+    }
+    if (record) {
+        CK(cudaEventRecord(h->ev[ST_COUNT], st));
+        h->ev_valid = true;
+    }
+    CK(cudaGetLastError());
+    return LFB_OK;
+}
+
+extern "C" {
+
+int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
+{
+    if (!out) return LFB_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                         " (this engine has no CPU fallback)";
+        cudaGetLastError();
+        return LFB_ECUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "device index out of range";
+        return LFB_EINVAL;
+    }
+    lfb_config c{};
+    if (cfg_in) c = *cfg_in;
+    if (c.n_wd_rings <= 0) c.n_wd_rings = 10;
+    if (c.n_disc_r <= 0) c.n_disc_r = 25;
+    if (c.n_disc_th <= 0) c.n_disc_th = 40;
+    if (c.n_bs <= 0) c.n_bs = 200;
+    if (c.n_donor_th <= 0) c.n_donor_th = 18;
+    if (c.n_quad <= 0) c.n_quad = 3;
+    if (!(c.donor_ulimb != 0.0)) c.donor_ulimb = 0.8;
+    if (!(c.donor_gdexp != 0.0)) c.donor_gdexp = 0.32;
+    if ((c.n_disc_th & 1) || !(c.n_quad & 1) || c.n_quad > kMaxQuad || c.n_donor_th > kMaxDonorRings ||
+        c.n_bs < 2 || c.n_wd_rings > 256 || c.n_disc_r > 4096) {
+        g_create_error = "bad grid configuration (n_disc_th even, n_quad odd <= 15, n_donor_th <= 128, n_bs >= 2)";
+        return LFB_EINVAL;
+    }
+    lfb_handle* h = new lfb_handle();
+    h->device = device;
+    h->cfg = c;
+    auto bail = [&](const char* what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        delete h;
+        return LFB_ECUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (int i = 0; i <= ST_COUNT; ++i)
+        if ((e = cudaEventCreate(&h->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    GridCfg& G = h->grid;
+    G.n_wd_rings = c.n_wd_rings;
+    G.n_wd = 4 * c.n_wd_rings * c.n_wd_rings;
+    G.n_wd_half = G.n_wd / 2;
+    G.n_disc_r = c.n_disc_r;
+    G.n_disc_th = c.n_disc_th;
+    G.n_disc = c.n_disc_r * c.n_disc_th;
+    G.n_disc_half = G.n_disc / 2;
+    G.n_bs = c.n_bs;
+    G.n_donor_th = c.n_donor_th;
+    G.n_quad = c.n_quad;
+    G.donor_ulimb = c.donor_ulimb;
+    G.donor_gdexp = c.donor_gdexp;
+    std::vector<int> off(c.n_donor_th + 1, 0);
+    for (int k = 0; k < c.n_donor_th; ++k) off[k + 1] = off[k] + donor_ring_count(c.n_donor_th, k);
+    G.n_donor_q = off[c.n_donor_th];
+    if (h->donor_off.reserve(off.size() * sizeof(int)) != cudaSuccess ||
+        cudaMemcpy(h->donor_off.p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail("donor ring table", cudaGetLastError());
+    G.donor_ring_off = h->donor_off.as<int>();
+    // composite Simpson nodes on [-1, 1] (exposure = phase +- width, CVModel.py:64)
+    if (c.n_quad == 1) {
+        G.quad_off[0] = 0.0;
+        G.quad_w[0] = 1.0;
+    } else {
+        int nint = c.n_quad - 1;
+        for (int k = 0; k < c.n_quad; ++k) {
+            G.quad_off[k] = -1.0 + 2.0 * k / nint;
+            double cw = (k == 0 || k == nint) ? 1.0 : ((k & 1) ? 4.0 : 2.0);
+            G.quad_w[k] = cw / (3.0 * nint);
+        }
+    }
+    // samples per chunk of the flux kernel: as large as leaves room for two CTAs per SM
+    h->Mc = 512;
+    while (h->Mc > 256 && flux_smem_fixed(G, h->Mc, 1) > (size_t)96 * 1024) h->Mc -= 256;
+    if (flux_smem_fixed(G, h->Mc, 4) > (size_t)h->max_smem - 2048) {
+        g_create_error = "surface grid too dense for shared memory";
+        delete h;
+        return LFB_EINVAL;
+    }
+    *out = h;
+    return LFB_OK;
+}
+
+void lfb_destroy(lfb_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->gather, &h->consts, &h->psrc, &h->ptype, &h->pisvar, &h->pp1, &h->pp2, &h->pnorm,
+                      &h->donor_off, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
+                      &h->chisq, &h->ws, &h->js, &h->wd_io, &h->don, &h->disc_io, &h->bs_io, &h->bs_b,
+                      &h->model_scratch, &h->h_in, &h->h_out, &h->h_chisq};
+    for (DevBuf* b : bufs) b->release();
+    h->lc.release();
+    h->cf_lc.release();
+    for (int i = 0; i <= ST_COUNT; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* lfb_last_error(const lfb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lfb_get_config(const lfb_handle* h, lfb_config* out)
+{
+    if (!h || !out) return LFB_EINVAL;
+    *out = h->cfg;
+    return LFB_OK;
+}
+
+long long lfb_launch_count(const lfb_handle* h) { return h ? h->launches : 0; }
+
+int lfb_last_stage_ms(lfb_handle* h, float out[6])
+{
+    if (!h || !out) return LFB_EINVAL;
+    for (int i = 0; i < 6; ++i) out[i] = -1.0f;
+    if (!h->ev_valid) return LFB_ESTATE;
+    for (int i = 0; i < ST_COUNT; ++i)
+        if (cudaEventElapsedTime(&out[i], h->ev[i], h->ev[i + 1]) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, LFB_ECUDA, "stage events not complete: synchronise the stream first");
+        }
+    cudaEventElapsedTime(&out[5], h->ev[0], h->ev[ST_COUNT]);
+    return LFB_OK;
+}
+
+float lfb_last_kernel_ms(lfb_handle* h)
+{
+    float t[6];
+    if (lfb_last_stage_ms(h, t) != LFB_OK) return -1.0f;
+    return t[ST_ELEMENTS] + t[ST_FLUX];
+}
+
+int lfb_set_layout(lfb_handle* h, int ndim, int n_ecl, int npars, const int* gather, int n_consts,
+                   const double* consts)
+{
+    if (!h) return LFB_EINVAL;
+    if (ndim < 0 || n_ecl < 1 || (npars != 14 && npars != 18) || !gather || n_consts < 0 || (n_consts && !consts))
+        return fail(h, LFB_EINVAL, "set_layout: need n_ecl >= 1, npars in {14, 18}, gather");
+    for (int e = 0; e < n_ecl; ++e)
+        for (int k = 0; k < npars; ++k) {
+            int g = gather[e * LFB_NPAR + k];
+            if (g >= ndim || (g < 0 && -g - 1 >= n_consts)) return fail(h, LFB_EINVAL, "set_layout: gather index out of range");
+        }
+    // q, dphi and rwd live on the root of the tree (LCModel.node_par_names, CVModel.py:434)
+    for (int e = 1; e < n_ecl; ++e)
+        if (gather[e * LFB_NPAR + P_Q] != gather[P_Q] || gather[e * LFB_NPAR + P_DPHI] != gather[P_DPHI] ||
+            gather[e * LFB_NPAR + P_RWD] != gather[P_RWD])
+            return fail(h, LFB_EINVAL, "set_layout: q, dphi and rwd must be shared by every eclipse");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = upload(h, h->gather, gather, sizeof(int) * (size_t)n_ecl * LFB_NPAR))) return rc;
+    if ((rc = upload(h, h->consts, consts, sizeof(double) * (size_t)n_consts))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->ndim = ndim;
+    h->n_ecl = n_ecl;
+    h->npars = npars;
+    h->have_layout = true;
+    h->have_lc = false;
+    h->n_prior = 0;
+    return LFB_OK;
+}
+
+int lfb_set_priors(lfb_handle* h, int n_prior, const int* src, const int* type, const double* p1, const double* p2,
+                   const double* norm, const int* isvar)
+{
+    if (!h) return LFB_EINVAL;
+    if (!h->have_layout) return fail(h, LFB_ESTATE, "set_priors: call set_layout first");
+    if (n_prior < 0 || (n_prior && (!src || !type || !p1 || !p2 || !norm || !isvar)))
+        return fail(h, LFB_EINVAL, "set_priors: NULL array");
+    for (int k = 0; k < n_prior; ++k) {
+        if (src[k] >= h->ndim) return fail(h, LFB_EINVAL, "set_priors: source column out of range");
+        if (type[k] < 0 || type[k] > LFB_PRIOR_MODJEFF) return fail(h, LFB_EINVAL, "set_priors: unknown prior type");
+    }
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = upload(h, h->psrc, src, sizeof(int) * (size_t)n_prior))) return rc;
+    if ((rc = upload(h, h->ptype, type, sizeof(int) * (size_t)n_prior))) return rc;
+    if ((rc = upload(h, h->pisvar, isvar, sizeof(int) * (size_t)n_prior))) return rc;
+    if ((rc = upload(h, h->pp1, p1, sizeof(double) * (size_t)n_prior))) return rc;
+    if ((rc = upload(h, h->pp2, p2, sizeof(double) * (size_t)n_prior))) return rc;
+    if ((rc = upload(h, h->pnorm, norm, sizeof(double) * (size_t)n_prior))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_prior = n_prior;
+    return LFB_OK;
+}
+
+int lfb_set_lightcurves(lfb_handle* h, int n_ecl, const long long* off, const double* phase, const double* width,
+                        const double* y, const double* ye)
+{
+    if (!h) return LFB_EINVAL;
+    if (!h->have_layout) return fail(h, LFB_ESTATE, "set_lightcurves: call set_layout first");
+    if (n_ecl != h->n_ecl || !off || !phase || !width || !y || !ye)
+        return fail(h, LFB_EINVAL, "set_lightcurves: n_ecl must match the layout; arrays must be non-NULL");
+    if (off[0] != 0) return fail(h, LFB_EINVAL, "set_lightcurves: off[0] must be 0");
+    for (int e = 0; e < n_ecl; ++e)
+        if (off[e + 1] < off[e] || off[e + 1] - off[e] > 100000000LL) return fail(h, LFB_EINVAL, "set_lightcurves: offsets must ascend");
+    CK(cudaSetDevice(h->device));
+    int rc = build_samples(h, h->lc, n_ecl, off, phase, width, y, ye);
+    if (rc) return rc;
+    h->have_lc = true;
+    return LFB_OK;
+}
+
+static DevLayout make_layout(lfb_handle* h)
+{
+    DevLayout L;
+    L.ndim = h->ndim;
+    L.n_ecl = h->n_ecl;
+    L.npars = h->npars;
+    L.n_prior = h->n_prior;
+    L.gather = h->gather.as<int>();
+    L.consts = h->consts.as<double>();
+    L.psrc = h->psrc.as<int>();
+    L.ptype = h->ptype.as<int>();
+    L.pisvar = h->pisvar.as<int>();
+    L.pp1 = h->pp1.as<double>();
+    L.pp2 = h->pp2.as<double>();
+    L.pnorm = h->pnorm.as<double>();
+    return L;
+}
+
+int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, double* out, double* chisq_out,
+                 void* stream_v)
+{
+    if (!h) return LFB_EINVAL;
+    if (!h->have_layout) return fail(h, LFB_ESTATE, "log_prob: call set_layout first");
+    if (what != LFB_LN_PRIOR && !h->have_lc) return fail(h, LFB_ESTATE, "log_prob: call set_lightcurves first");
+    if (what < LFB_LN_PRIOR || what > LFB_LN_PROB || n < 0 || (n && (!theta || !out)))
+        return fail(h, LFB_EINVAL, "log_prob: bad arguments");
+    if (n == 0) return LFB_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    const long long njobs = n * h->n_ecl;
+    const size_t th_bytes = sizeof(double) * (size_t)n * (size_t)(h->ndim > 0 ? h->ndim : 1);
+    const bool th_dev = is_device_ptr(theta), out_dev = is_device_ptr(out);
+    const bool chi_dev = chisq_out && is_device_ptr(chisq_out);
+    const double* d_theta = theta;
+    if (!th_dev) {
+        CK(h->theta.reserve(th_bytes));
+        CK(h->h_in.reserve(th_bytes));
+        memcpy(h->h_in.p, theta, sizeof(double) * (size_t)n * h->ndim);
+        CK(cudaMemcpyAsync(h->theta.p, h->h_in.p, sizeof(double) * (size_t)n * h->ndim, cudaMemcpyHostToDevice, st));
+        d_theta = h->theta.as<double>();
+    }
+    double* d_out = out;
+    if (!out_dev) {
+        CK(h->out.reserve(sizeof(double) * (size_t)n));
+        d_out = h->out.as<double>();
+    }
+    double* d_chi = chi_dev ? chisq_out : nullptr;
+    if (!chi_dev) {
+        CK(h->chisq.reserve(sizeof(double) * (size_t)njobs));
+        d_chi = h->chisq.as<double>();
+    }
+    if (what == LFB_LN_PRIOR && chisq_out) CK(cudaMemsetAsync(d_chi, 0xff, sizeof(double) * (size_t)njobs, st));
+    DevLayout L = make_layout(h);
+    // bounded batches of walkers keep the element buffers small (16 B x ~900 elements per job)
+    long long per = std::max<long long>(1, h->max_jobs_per_batch / h->n_ecl);
+    for (long long w0 = 0; w0 < n; w0 += per) {
+        long long nb = std::min(per, n - w0);
+        int rc = run_batch(h, st, L, h->lc, what, 0, 0, nb, d_theta + w0 * h->ndim, d_out + w0, d_chi + w0 * h->n_ecl,
+                           nullptr, nullptr, w0 + per >= n);
+        if (rc) return rc;
+    }
+    if (!out_dev || (chisq_out && !chi_dev)) {
+        CK(h->h_out.reserve(sizeof(double) * (size_t)n));
+        if (!out_dev) CK(cudaMemcpyAsync(h->h_out.p, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (chisq_out && !chi_dev) {
+            CK(h->h_chisq.reserve(sizeof(double) * (size_t)njobs));
+            CK(cudaMemcpyAsync(h->h_chisq.p, d_chi, sizeof(double) * (size_t)njobs, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        if (!out_dev) memcpy(out, h->h_out.p, sizeof(double) * (size_t)n);
+        if (chisq_out && !chi_dev) memcpy(chisq_out, h->h_chisq.p, sizeof(double) * (size_t)njobs);
+    }
+    return LFB_OK;
+}
+
+int lfb_calc_flux(lfb_handle* h, long long n_sets, const double* pars, int npars, int flags, int n_ph,
+                  const double* phase, const double* width, double* out_total, double* out_comp, void* stream_v)
+{
+    if (!h) return LFB_EINVAL;
+    if (n_sets < 0 || (npars != 14 && npars != 18) || n_ph < 0 || (n_sets && !pars) || (n_ph && (!phase || !out_total)))
+        return fail(h, LFB_EINVAL, "calc_flux: need npars in {14, 18} and non-NULL arrays");
+    if (n_sets == 0 || n_ph == 0) return LFB_OK;
+    if (is_device_ptr(phase) || (width && is_device_ptr(width)))
+        return fail(h, LFB_EINVAL, "calc_flux: phase and width are host arrays");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    std::vector<int> gather(LFB_NPAR, 0);
+    for (int k = 0; k < LFB_NPAR; ++k) gather[k] = k < npars ? k : 0;
+    long long off[2] = {0, n_ph};
+    int rc = build_samples(h, h->cf_lc, 1, off, phase, width, nullptr, nullptr);
+    if (rc) return rc;
+    CK(h->cf_gather.reserve(sizeof(int) * LFB_NPAR));
+    CK(cudaMemcpyAsync(h->cf_gather.p, gather.data(), sizeof(int) * LFB_NPAR, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    const double* d_pars = pars;
+    if (!is_device_ptr(pars)) {
+        CK(h->cf_pars.reserve(sizeof(double) * (size_t)n_sets * npars));
+        CK(cudaMemcpyAsync(h->cf_pars.p, pars, sizeof(double) * (size_t)n_sets * npars, cudaMemcpyHostToDevice, st));
+        d_pars = h->cf_pars.as<double>();
+    }
+    const size_t cur = sizeof(double) * (size_t)n_sets * n_ph;
+    const bool tot_dev = is_device_ptr(out_total), comp_dev = out_comp && is_device_ptr(out_comp);
+    double* d_tot = out_total;
+    if (!tot_dev) {
+        CK(h->cf_tot.reserve(cur));
+        d_tot = h->cf_tot.as<double>();
+    }
+    double* d_comp = comp_dev ? out_comp : nullptr;
+    if (out_comp && !comp_dev) {
+        CK(h->cf_comp.reserve(4 * cur));
+        d_comp = h->cf_comp.as<double>();
+    }
+    DevLayout L;
+    memset(&L, 0, sizeof(L));
+    L.ndim = npars;
+    L.n_ecl = 1;
+    L.npars = npars;
+    L.n_prior = 0;
+    L.gather = h->cf_gather.as<int>();
+    rc = run_batch(h, st, L, h->cf_lc, LFB_LN_LIKE, flags, 1, n_sets, d_pars, nullptr, nullptr, d_tot, d_comp, false);
+    if (rc) return rc;
+    if (!tot_dev) CK(cudaMemcpyAsync(out_total, d_tot, cur, cudaMemcpyDeviceToHost, st));
+    if (out_comp && !comp_dev) CK(cudaMemcpyAsync(out_comp, d_comp, 4 * cur, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LFB_OK;
+}
+
+int lfb_roche(lfb_handle* h, int which, long long n, const double* a, const double* b, double* out, int* ok)
+{
+    if (!h) return LFB_EINVAL;
+    if (which < LFB_ROCHE_XL1 || which > LFB_ROCHE_BSPOT || n < 0 || (n && (!a || !out || !ok)) ||
+        (n && which != LFB_ROCHE_XL1 && !b))
+        return fail(h, LFB_EINVAL, "roche: bad arguments");
+    if (n == 0) return LFB_OK;
+    CK(cudaSetDevice(h->device));
+    DevBuf da, db, dout, dok;
+    auto cleanup = [&]() { da.release(); db.release(); dout.release(); dok.release(); };
+    cudaError_t e;
+    if ((e = da.reserve(sizeof(double) * n)) != cudaSuccess || (e = db.reserve(sizeof(double) * n)) != cudaSuccess ||
+        (e = dout.reserve(sizeof(double) * 4 * n)) != cudaSuccess || (e = dok.reserve(sizeof(int) * n)) != cudaSuccess) {
+        cleanup();
+        return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    }
+    cudaMemcpyAsync(da.p, a, sizeof(double) * n, cudaMemcpyDefault, h->stream);
+    if (b) cudaMemcpyAsync(db.p, b, sizeof(double) * n, cudaMemcpyDefault, h->stream);
+    else cudaMemsetAsync(db.p, 0, sizeof(double) * n, h->stream);
+    roche_kernel<<<(unsigned)((n + 63) / 64), 64, 0, h->stream>>>(which, n, da.as<double>(), db.as<double>(),
+                                                                  dout.as<double>(), dok.as<int>());
+    h->launches++;
+    cudaMemcpyAsync(out, dout.p, sizeof(double) * 4 * n, cudaMemcpyDefault, h->stream);
+    cudaMemcpyAsync(ok, dok.p, sizeof(int) * n, cudaMemcpyDefault, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    return LFB_OK;
+}
+
+int lfb_measure_fp64_peak(lfb_handle* h, int iters, double* tflops)
+{
+    if (!h || !tflops || iters <= 0) return LFB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(h->out.reserve(64));
+    const int blocks = h->sm_count * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, h->stream);
+        fp64_peak_kernel<<<blocks, 256, 0, h->stream>>>(iters, 0.999999, 1e-7, h->out.as<double>());
+        cudaEventRecord(e1, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 16.0 * iters * 256.0 * blocks / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    h->launches += 5;
+    *tflops = best;
+    return LFB_OK;
+}
+
+}  // extern "C"
