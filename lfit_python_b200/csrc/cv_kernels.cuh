@@ -364,89 +364,138 @@ struct FluxArgs {
     double* model_scratch;  // [gridDim.x][nF * max_nph] when !model_in_smem
 };
 
-// first index in [lo, hi) with S[idx] > v (strict = true) or S[idx] >= v (strict = false)
-__device__ __forceinline__ int bound_search(const double* __restrict__ S, int lo, int hi, double v, bool strict)
+// Sorted sample phases of one eclipse, with what the interpolating search needs.
+struct SampleAxis {
+    const double* S;
+    int M;
+    double s_first, s_last, scale;  // scale = (M - 1) / (s_last - s_first)
+};
+
+// First index with S[idx] > v (strict) or S[idx] >= v (!strict); M if none.  Light curves are
+// close to uniformly sampled, so start from the interpolated position and gallop: a couple of
+// loads instead of log2(M).
+__device__ __forceinline__ int sample_search(const SampleAxis& X, double v, bool strict)
 {
+    const double* __restrict__ S = X.S;
+    const int M = X.M;
+    double gf = (v - X.s_first) * X.scale;
+    int g = gf <= 0.0 ? 0 : (gf >= (double)(M - 1) ? M - 1 : (int)gf);
+    int lo, hi;
+    double sg = __ldg(S + g);
+    if (strict ? (sg <= v) : (sg < v)) {
+        lo = g + 1;
+        hi = M;
+        for (int step = 1; lo < M; step <<= 1) {
+            int j = min(M - 1, g + step);
+            double s = __ldg(S + j);
+            if (strict ? (s <= v) : (s < v)) {
+                lo = j + 1;
+                if (j == M - 1) break;
+            } else {
+                hi = j;
+                break;
+            }
+        }
+    } else {
+        hi = g;
+        lo = 0;
+        for (int step = 1; hi > 0; step <<= 1) {
+            int j = max(0, g - step);
+            double s = __ldg(S + j);
+            if (strict ? (s <= v) : (s < v)) {
+                lo = j + 1;
+                break;
+            } else {
+                hi = j;
+                if (j == 0) break;
+            }
+        }
+    }
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
         double s = __ldg(S + mid);
-        bool right = strict ? (s <= v) : (s < v);
-        if (right) lo = mid + 1; else hi = mid;
+        if (strict ? (s <= v) : (s < v)) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
 
-struct ChunkView {
-    const double* S;  // sorted sample phases of this eclipse
-    int M, m0, m1;
-    double s_first, s_last;     // S[0], S[M-1]
-    double s_before, s_end;     // S[m0-1] (or -inf), S[m1-1]
-};
-
-// Add weight w to array `arr` for every sample with a < S < b (cycles, any integer shift):
-// +w at the first sample after a, -w at the first sample at or after b.  Events before the
-// first sample go to the caller's base accumulator; events of other chunks are ignored.
-__device__ __forceinline__ void scatter_interval(const ChunkView& C, unsigned long long* D, long long* base, double a,
-                                                 double b, long long w)
+// The samples with a < S + n < b for integer n: since S lies in [-0.5, 0.5] and b - a < 1 at
+// most two shifts contribute.  Each piece is (first sample inside, first sample at or past the
+// end); -1 marks "no event": an opening at sample 0 is returned through *open_at_start instead
+// (the caller adds the weight to the running sum's start value), a closing past the last sample
+// never happens.
+__device__ __forceinline__ int4 interval_pieces(const SampleAxis& X, double a, double b, int* open_at_start)
 {
-    if (!(a < b) || !(a > -1e29) || !(b < 1e29)) return;
-    int n_lo = (int)ceil(C.s_first - b), n_hi = (int)floor(C.s_last - a);
-    for (int n = n_lo; n <= n_hi; ++n) {
+    int4 p = make_int4(-1, -1, -1, -1);
+    *open_at_start = 0;
+    if (!(a < b) || !(a > -1e29) || !(b < 1e29)) return p;
+    int n_lo = (int)ceil(X.s_first - b), n_hi = (int)floor(X.s_last - a);
+    int np = 0;
+    for (int n = n_lo; n <= n_hi && np < 2; ++n) {
         double an = a + n, bn = b + n;
-        // opening event at p = first sample with S > an
-        if (an < C.s_first) {
-            if (C.m0 == 0) *base += w;
-        } else if (C.s_before <= an && C.s_end > an) {
-            int p = bound_search(C.S, C.m0, C.m1, an, true);
-            atomicAdd(D + (p - C.m0), (unsigned long long)w);
-        }
-        // closing event at p = first sample with S >= bn
-        if (bn <= C.s_first) {
-            if (C.m0 == 0) *base -= w;
-        } else if (C.s_before < bn && C.s_end >= bn) {
-            int p = bound_search(C.S, C.m0, C.m1, bn, false);
-            atomicAdd(D + (p - C.m0), (unsigned long long)(-w));
-        }
+        int po = an < X.s_first ? 0 : sample_search(X, an, true);
+        int pc = bn > X.s_last ? X.M : sample_search(X, bn, false);
+        if (pc <= po) continue;  // no sample inside
+        if (po == 0) { *open_at_start += 1; po = -1; }
+        if (pc >= X.M) pc = -1;
+        if (np == 0) { p.x = po; p.y = pc; } else { p.z = po; p.w = pc; }
+        ++np;
     }
+    return p;
+}
+
+__device__ __forceinline__ void add_event(unsigned long long* Darr, int p, int m0, int m1, long long w)
+{
+    if (p >= m0 && p < m1) atomicAdd(Darr + (p - m0), (unsigned long long)w);
+}
+
+// five moments (1, c, s, c^2, c s) of W m (1 - u + u m), m = A c + B s + D, in 2^-56 fixed point
+__device__ __forceinline__ void donor_moments(double sc, double ud, double Aq, double Bi, double Di, long long mo[5])
+{
+    mo[0] = llrint(sc * ((1.0 - ud) * Di + ud * (Di * Di + Bi * Bi)));
+    mo[1] = llrint(sc * ((1.0 - ud) * Aq + 2.0 * ud * Aq * Di));
+    mo[2] = llrint(sc * ((1.0 - ud) * Bi + 2.0 * ud * Bi * Di));
+    mo[3] = llrint(sc * (ud * (Aq * Aq - Bi * Bi)));
+    mo[4] = llrint(sc * (2.0 * ud * Aq * Bi));
 }
 
 __global__ void __launch_bounds__(kFluxThreads) flux_kernel(const __grid_constant__ FluxArgs A)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     const GridCfg& G = A.G;
+    constexpr int NW = kFluxThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NI = G.n_wd + G.n_disc + G.n_bs;   // eclipse intervals (mirrors included)
     const int NDQ = G.n_donor_q;
     const int Mc = A.Mc, R = Mc / kFluxThreads;  // samples per thread per chunk
     const int nF = A.mode ? 4 : 1;
-    // shared-memory carve-up
-    double* iv_a = (double*)smraw;
-    double* iv_b = iv_a + NI;
-    long long* iv_w = (long long*)(iv_b + NI);
-    double* dn_c = (double*)(iv_w + NI);            // donor image centre (cycles)       [2*NDQ]
-    double* dn_h = dn_c + 2 * NDQ;                  // donor image half width (cycles)   [2*NDQ]
-    long long* dn_m = (long long*)(dn_h + 2 * NDQ); // donor moments of the 4 images     [4*NDQ][5]
-    unsigned long long* D = (unsigned long long*)(dn_m + 20 * NDQ);  // [kNumArr][Mc]
-    double* Fs = (double*)(D + kNumArr * Mc);       // [nF][Mc]
-    double* ringw = Fs + nF * Mc;                   // [n_disc_r + n_wd_rings]
-    double* model_sm = ringw + G.n_disc_r + G.n_wd_rings;  // [nF * n_ph] when model_in_smem
+    // shared-memory carve-up (16-byte aligned pieces first)
+    int4* iv_p = (int4*)smraw;                            // [NI]      sample positions of each interval's events
+    int4* dn_p = iv_p + NI;                               // [4 NDQ]   same for the donor tile images
+    double4* dn_q = (double4*)(dn_p + 4 * NDQ);           // [NDQ]     (A, B, D, scaled weight) of a quarter tile
+    unsigned long long* D = (unsigned long long*)(dn_q + NDQ);  // [kNumArr][Mc] events, then nothing else
+    long long* part = (long long*)(D + kNumArr * Mc);     // [kNumArr][kFluxThreads] scan partials
+    double* Fs = (double*)(part + kNumArr * kFluxThreads);  // [nF][Mc] flux per sample of the chunk
+    long long* wq_bs = (long long*)(Fs + nF * Mc);        // [n_bs]    fixed-point strip weights
+    long long* wq_ring = wq_bs + G.n_bs;                  // [n_disc_r + n_wd_rings]
+    double* ringw = (double*)(wq_ring + G.n_disc_r + G.n_wd_rings);  // [n_disc_r + n_wd_rings]
+    double* model_sm = ringw + G.n_disc_r + G.n_wd_rings; // [nF * n_ph] when model_in_smem
     __shared__ double s_par[LFB_NPAR];
-    __shared__ double red[kFluxThreads / 32];
-    __shared__ long long wtot[kNumArr][kFluxThreads / 32];
-    __shared__ long long s_base[kNumArr];
+    __shared__ double red[NW];
+    __shared__ long long wtot[kNumArr][NW];
+    __shared__ long long s_tot[kNumArr];
 
     const bool do_wd = !(A.flags & LFB_FLAG_SKIP_WD), do_disc = !(A.flags & LFB_FLAG_SKIP_DISC);
     const bool do_bs = !(A.flags & LFB_FLAG_SKIP_BS), do_don = !(A.flags & LFB_FLAG_SKIP_DONOR);
 
     for (long long job = blockIdx.x; job < A.njobs; job += gridDim.x) {
         const long long w = job / A.L.n_ecl;
-        const int e = A.mode ? 0 : (int)(job - w * A.L.n_ecl);
         const int egather = (int)(job - w * A.L.n_ecl);
+        const int e = A.mode ? 0 : egather;
         const long long lc0 = A.smp.lc_off[e];
         const int n_ph = (int)(A.smp.lc_off[e + 1] - lc0);
         const int K = G.n_quad;
         const int M = n_ph * K;
-        const double* S = A.smp.S + lc0 * K;
         const double* cosS = A.smp.cosS + lc0 * K;
         const double* sinS = A.smp.sinS + lc0 * K;
         const int* pos = A.smp.pos + lc0 * K;
@@ -477,6 +526,12 @@ __global__ void __launch_bounds__(kFluxThreads) flux_kernel(const __grid_constan
             }
             continue;
         }
+        SampleAxis X;
+        X.S = A.smp.S + lc0 * K;
+        X.M = M;
+        X.s_first = __ldg(X.S);
+        X.s_last = __ldg(X.S + M - 1);
+        X.scale = X.s_last > X.s_first ? (double)(M - 1) / (X.s_last - X.s_first) : 0.0;
         const Roche Rr = W.R;
         const double si = W.si, ci = W.ci;
         const double rwd_a = s_par[P_RWD] * Rr.xl1, rdisc_a = s_par[P_RDISC] * Rr.xl1;
@@ -535,178 +590,204 @@ __global__ void __launch_bounds__(kFluxThreads) flux_kernel(const __grid_constan
         const double f_wd = do_wd ? s_par[P_WDFLUX] : 0.0, f_d = do_disc ? s_par[P_DFLUX] : 0.0;
         const double f_s = (do_bs && beam_norm > 0.0 && tot_s > 0.0) ? s_par[P_SFLUX] / beam_norm : 0.0;
         const double f_rs = do_don ? s_par[P_RSFLUX] / tot_rs * (tot_rw * kInvFix) : 0.0;
+        // fixed-point (2^-56) weights: per ring for the white dwarf and the disc, per element for the strip
+        long long* wq_disc = wq_ring;
+        long long* wq_wd = wq_ring + G.n_disc_r;
+        for (int m = tid; m < G.n_disc_r; m += kFluxThreads) wq_disc[m] = do_disc ? llrint(ringw[m] / tot_d * kFix) : 0;
+        for (int k = tid; k < G.n_wd_rings; k += kFluxThreads) wq_wd[k] = do_wd ? llrint(wdw[k] / tot_wd * kFix) : 0;
+        for (int t = tid; t < G.n_bs; t += kFluxThreads) wq_bs[t] = (do_bs && tot_s > 0.0) ? llrint(bsb[t] / tot_s * kFix) : 0;
+        for (int j = tid; j < nF * n_ph; j += kFluxThreads) model[j] = 0.0;
+        __syncthreads();
 
-        // ---- eclipse intervals in data-phase coordinates, weights in 2^-56 fixed point ----
+        // ---- pass 1: every eclipse / facing interval -> positions of its events on the sample axis ----
+        long long base[kNumArr];
+#pragma unroll
+        for (int a = 0; a < kNumArr; ++a) base[a] = 0;
         const double2* wdio = A.wd_io + w * G.n_wd_half;
         const double2* dio = A.disc_io + job * G.n_disc_half;
         const double2* bio = A.bs_io + job * G.n_bs;
-        for (int t = tid; t < G.n_wd_half; t += kFluxThreads) {
-            int k = (int)sqrt(0.5 * (double)t);
-            while (2 * k * k > t) --k;
-            while (2 * (k + 1) * (k + 1) <= t) ++k;
-            double2 io = do_wd ? wdio[t] : make_double2(kBig, -kBig);
-            long long wq = do_wd ? llrint(wdw[k] / tot_wd * kFix) : 0;
-            bool ecl = io.y > io.x;
-            iv_a[2 * t] = ecl ? io.x + phi0w : kBig;
-            iv_b[2 * t] = ecl ? io.y + phi0w : -kBig;
-            iv_w[2 * t] = wq;
-            iv_a[2 * t + 1] = ecl ? -io.y + phi0w : kBig;  // mirror image xi -> -xi
-            iv_b[2 * t + 1] = ecl ? -io.x + phi0w : -kBig;
-            iv_w[2 * t + 1] = wq;
+        const int n_half = G.n_wd_half + G.n_disc_half;
+        for (int t = tid; t < n_half + G.n_bs; t += kFluxThreads) {
+            double2 io;
+            int i0, arr;
+            long long wq;
+            bool mirror = t < n_half;
+            if (t < G.n_wd_half) {
+                int k = (int)sqrt(0.5 * (double)t);
+                while (2 * k * k > t) --k;
+                while (2 * (k + 1) * (k + 1) <= t) ++k;
+                io = do_wd ? wdio[t] : make_double2(kBig, -kBig);
+                wq = wq_wd[k];
+                i0 = 2 * t;
+                arr = 0;
+            } else if (t < n_half) {
+                int h = t - G.n_wd_half;
+                io = do_disc ? dio[h] : make_double2(kBig, -kBig);
+                wq = wq_disc[h / (G.n_disc_th / 2)];
+                i0 = G.n_wd + 2 * h;
+                arr = 1;
+            } else {
+                int h = t - n_half;
+                io = do_bs ? bio[h] : make_double2(kBig, -kBig);
+                wq = wq_bs[h];
+                i0 = G.n_wd + G.n_disc + h;
+                arr = 2;
+            }
+            const bool ecl = io.y > io.x;
+            int nopen = 0;
+            int4 p = ecl ? interval_pieces(X, io.x + phi0w, io.y + phi0w, &nopen) : make_int4(-1, -1, -1, -1);
+            iv_p[i0] = p;
+            long long b0 = nopen * wq;
+            if (mirror) {  // the y -> -y image is eclipsed from -egress to -ingress
+                p = ecl ? interval_pieces(X, -io.y + phi0w, -io.x + phi0w, &nopen) : make_int4(-1, -1, -1, -1);
+                iv_p[i0 + 1] = p;
+                b0 += nopen * wq;
+            }
+            base[0] += arr == 0 ? b0 : 0;
+            base[1] += arr == 1 ? b0 : 0;
+            base[2] += arr == 2 ? b0 : 0;
         }
-        for (int t = tid; t < G.n_disc_half; t += kFluxThreads) {
-            int m = t / (G.n_disc_th / 2);
-            double2 io = do_disc ? dio[t] : make_double2(kBig, -kBig);
-            long long wq = do_disc ? llrint(ringw[m] / tot_d * kFix) : 0;
-            bool ecl = io.y > io.x;
-            int i = G.n_wd + 2 * t;
-            iv_a[i] = ecl ? io.x + phi0w : kBig;
-            iv_b[i] = ecl ? io.y + phi0w : -kBig;
-            iv_w[i] = wq;
-            iv_a[i + 1] = ecl ? -io.y + phi0w : kBig;  // mirror image y -> -y
-            iv_b[i + 1] = ecl ? -io.x + phi0w : -kBig;
-            iv_w[i + 1] = wq;
-        }
-        for (int t = tid; t < G.n_bs; t += kFluxThreads) {
-            double2 io = do_bs ? bio[t] : make_double2(kBig, -kBig);
-            bool ecl = io.y > io.x;
-            int i = G.n_wd + G.n_disc + t;
-            iv_a[i] = ecl ? io.x + phi0w : kBig;
-            iv_b[i] = ecl ? io.y + phi0w : -kBig;
-            iv_w[i] = (do_bs && tot_s > 0.0) ? llrint(bsb[t] / tot_s * kFix) : 0;
-        }
-        // donor: every tile faces the observer for |phase - centre| < half width; while it does it
-        // adds W m (1 - u + u m), m = A c + B s + D, i.e. five moments of (1, c, s, c^2, c s)
+        // donor: every tile image faces the observer for |phase - centre| < half width; while it does it
+        // adds W m (1 - u + u m), m = A c + B s + D
         for (int t = tid; t < NDQ; t += kFluxThreads) {
             double4 q = do_don ? don[t] : make_double4(1.0, 0.0, 0.0, 0.0);
             double Aq = si * q.x, Bq = -si * q.y, Dq = ci * q.z;
             double rho = sqrt(Aq * Aq + Bq * Bq);
             double psi = atan2(Bq, Aq) * (1.0 / kTwoPi);
             double ratio = rho > 0.0 ? Dq / rho : (Dq > 0.0 ? 2.0 : -2.0);
-            // image with +D: facing iff cos(th - psi) > -D/rho
+            // image with +D faces the observer iff cos(th - psi) > -D/rho
             double hp = ratio >= 1.0 ? 0.5 : (ratio <= -1.0 ? -1.0 : acos(-ratio) * (1.0 / kTwoPi));
             double hm = ratio <= -1.0 ? 0.5 : (ratio >= 1.0 ? -1.0 : acos(ratio) * (1.0 / kTwoPi));
-            dn_c[2 * t] = psi + phi0w;       // images (B, +-D)
-            dn_c[2 * t + 1] = -psi + phi0w;  // images (-B, +-D)
-            dn_h[2 * t] = hp;                // images (+-B, +D)
-            dn_h[2 * t + 1] = hm;            // images (+-B, -D)
             double sc = do_don ? q.w / tot_rw * kFix : 0.0;
+            dn_q[t] = make_double4(Aq, Bq, Dq, sc);
 #pragma unroll
             for (int im = 0; im < 4; ++im) {
-                double Bi = (im & 1) ? -Bq : Bq, Di = (im & 2) ? -Dq : Dq;
-                long long* mo = dn_m + (4 * t + im) * 5;
-                mo[0] = llrint(sc * ((1.0 - ud) * Di + ud * (Di * Di + Bi * Bi)));
-                mo[1] = llrint(sc * ((1.0 - ud) * Aq + 2.0 * ud * Aq * Di));
-                mo[2] = llrint(sc * ((1.0 - ud) * Bi + 2.0 * ud * Bi * Di));
-                mo[3] = llrint(sc * (ud * (Aq * Aq - Bi * Bi)));
-                mo[4] = llrint(sc * (2.0 * ud * Aq * Bi));
+                double cen = ((im & 1) ? -psi : psi) + phi0w, hw = (im & 2) ? hm : hp;
+                int4 p = make_int4(-1, -1, -1, -1);
+                int nopen = 0;
+                if (!do_don || hw < 0.0) {
+                    // never faces the observer
+                } else if (hw >= 0.5) {
+                    nopen = 1;  // always does
+                } else {
+                    p = interval_pieces(X, cen - hw, cen + hw, &nopen);
+                }
+                dn_p[4 * t + im] = p;
+                if (nopen) {
+                    long long mo[5];
+                    donor_moments(sc, ud, Aq, (im & 1) ? -Bq : Bq, (im & 2) ? -Dq : Dq, mo);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) base[3 + k] += nopen * mo[k];
+                }
             }
         }
-        for (int j = tid; j < nF * n_ph; j += kFluxThreads) model[j] = 0.0;
-        __syncthreads();
-
-        // ---- chunks of the sorted sample axis ----
+        // running sums start from the intervals already open at the first sample (exact integer reduction)
         long long carry[kNumArr];
 #pragma unroll
-        for (int a = 0; a < kNumArr; ++a) carry[a] = 0;
+        for (int a = 0; a < kNumArr; ++a) {
+            long long v = base[a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) wtot[a][wid] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < kNumArr; ++a) {
+            long long v = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) v += wtot[a][i];
+            carry[a] = v;
+        }
+
+        // ---- pass 2: chunks of the sorted sample axis ----
         const int n_chunks = (M + Mc - 1) / Mc;
         for (int c = 0; c < n_chunks; ++c) {
-            ChunkView C;
-            C.S = S;
-            C.M = M;
-            C.m0 = c * Mc;
-            C.m1 = min(M, C.m0 + Mc);
-            C.s_first = __ldg(S);
-            C.s_last = __ldg(S + M - 1);
-            C.s_before = C.m0 > 0 ? __ldg(S + C.m0 - 1) : -INFINITY;
-            C.s_end = __ldg(S + C.m1 - 1);
+            const int m0 = c * Mc, m1 = min(M, m0 + Mc);
             for (int i = tid; i < kNumArr * Mc; i += kFluxThreads) D[i] = 0ull;
             __syncthreads();
-            long long base[kNumArr];
-#pragma unroll
-            for (int a = 0; a < kNumArr; ++a) base[a] = 0;
             for (int i = tid; i < NI; i += kFluxThreads) {
-                int arr = i < G.n_wd ? 0 : (i < G.n_wd + G.n_disc ? 1 : 2);
-                long long b0 = 0;
-                scatter_interval(C, D + arr * Mc, &b0, iv_a[i], iv_b[i], iv_w[i]);
-                base[0] += arr == 0 ? b0 : 0;
-                base[1] += arr == 1 ? b0 : 0;
-                base[2] += arr == 2 ? b0 : 0;
+                const int4 p = iv_p[i];
+                if (!((p.x >= m0 && p.x < m1) || (p.y >= m0 && p.y < m1) || (p.z >= m0 && p.z < m1) ||
+                      (p.w >= m0 && p.w < m1)))
+                    continue;
+                int arr;
+                long long wq;
+                if (i < G.n_wd) {
+                    int t = i >> 1;
+                    int k = (int)sqrt(0.5 * (double)t);
+                    while (2 * k * k > t) --k;
+                    while (2 * (k + 1) * (k + 1) <= t) ++k;
+                    wq = wq_wd[k];
+                    arr = 0;
+                } else if (i < G.n_wd + G.n_disc) {
+                    wq = wq_disc[((i - G.n_wd) >> 1) / (G.n_disc_th / 2)];
+                    arr = 1;
+                } else {
+                    wq = wq_bs[i - G.n_wd - G.n_disc];
+                    arr = 2;
+                }
+                unsigned long long* Da = D + arr * Mc;
+                add_event(Da, p.x, m0, m1, wq);
+                add_event(Da, p.y, m0, m1, -wq);
+                add_event(Da, p.z, m0, m1, wq);
+                add_event(Da, p.w, m0, m1, -wq);
             }
             if (do_don)
                 for (int i = tid; i < 4 * NDQ; i += kFluxThreads) {
-                    int t = i >> 2, im = i & 3;
-                    double cen = dn_c[2 * t + (im & 1)], hw = dn_h[2 * t + ((im >> 1) & 1)];
-                    if (hw < 0.0) continue;  // never faces the observer
-                    const long long* mo = dn_m + i * 5;
-                    if (hw >= 0.5) {
-                        // always facing: present from the first sample on
-                        if (c == 0)
-#pragma unroll
-                            for (int k = 0; k < 5; ++k) base[3 + k] += mo[k];
-                        continue;
-                    }
+                    const int4 p = dn_p[i];
+                    const bool hx = p.x >= m0 && p.x < m1, hy = p.y >= m0 && p.y < m1;
+                    const bool hz = p.z >= m0 && p.z < m1, hw_ = p.w >= m0 && p.w < m1;
+                    if (!(hx || hy || hz || hw_)) continue;
+                    const double4 q = dn_q[i >> 2];
+                    long long mo[5];
+                    donor_moments(q.w, ud, q.x, (i & 1) ? -q.y : q.y, (i & 2) ? -q.z : q.z, mo);
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
-                        long long b0 = 0;
-                        if (mo[k] != 0) scatter_interval(C, D + (3 + k) * Mc, &b0, cen - hw, cen + hw, mo[k]);
-                        base[3 + k] += b0;
+                        unsigned long long* Da = D + (3 + k) * Mc;
+                        if (hx) atomicAdd(Da + (p.x - m0), (unsigned long long)mo[k]);
+                        if (hy) atomicAdd(Da + (p.y - m0), (unsigned long long)(-mo[k]));
+                        if (hz) atomicAdd(Da + (p.z - m0), (unsigned long long)mo[k]);
+                        if (hw_) atomicAdd(Da + (p.w - m0), (unsigned long long)(-mo[k]));
                     }
                 }
-            // events before the first sample: exact integer reduction over the CTA
-            if (c == 0) {
-#pragma unroll
-                for (int a = 0; a < kNumArr; ++a) {
-                    long long v = base[a];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (lane == 0) wtot[a][wid] = v;
-                }
-                __syncthreads();
-                if (tid < kNumArr) {
-                    long long v = 0;
-                    for (int i = 0; i < kFluxThreads / 32; ++i) v += wtot[tid][i];
-                    s_base[tid] = v;
-                }
-                __syncthreads();
-#pragma unroll
-                for (int a = 0; a < kNumArr; ++a) carry[a] = s_base[a];
-            }
             __syncthreads();
-            // block scan: thread t owns samples m0 + t*R .. m0 + t*R + R-1
-            long long pre[kNumArr];
+            // block scan: thread t owns samples m0 + t*R .. +R-1; warp a scans the partials of array a
 #pragma unroll
             for (int a = 0; a < kNumArr; ++a) {
                 long long v = 0;
                 for (int r = 0; r < R; ++r) v += (long long)D[a * Mc + tid * R + r];
-                long long inc = v;
+                part[a * kFluxThreads + tid] = v;
+            }
+            __syncthreads();
+            for (int a = wid; a < kNumArr; a += NW) {
+                long long* pa = part + a * kFluxThreads + lane * NW;
+                long long loc[NW], t = 0;
+#pragma unroll
+                for (int j = 0; j < NW; ++j) { loc[j] = t; t += pa[j]; }
+                long long inc = t;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     long long u = __shfl_up_sync(0xffffffffu, inc, o);
                     if (lane >= o) inc += u;
                 }
-                if (lane == 31) wtot[a][wid] = inc;
-                pre[a] = inc - v;  // exclusive within the warp
+                long long exc = inc - t;
+#pragma unroll
+                for (int j = 0; j < NW; ++j) pa[j] = exc + loc[j];
+                if (lane == 31) s_tot[a] = inc;
             }
             __syncthreads();
+            long long pre[kNumArr];
 #pragma unroll
             for (int a = 0; a < kNumArr; ++a) {
-                long long off = carry[a], all = 0;
-#pragma unroll
-                for (int i = 0; i < kFluxThreads / 32; ++i) {
-                    long long v = wtot[a][i];
-                    if (i < wid) off += v;
-                    all += v;
-                }
-                pre[a] += off;
-                carry[a] += all;
+                pre[a] = carry[a] + part[a * kFluxThreads + tid];
+                carry[a] += s_tot[a];
             }
             // per-sample flux
             for (int r = 0; r < R; ++r) {
-                int ml = tid * R + r, m = C.m0 + ml;
+                int ml = tid * R + r, m = m0 + ml;
 #pragma unroll
                 for (int a = 0; a < kNumArr; ++a) pre[a] += (long long)D[a * Mc + ml];
-                if (m >= C.m1) break;
+                if (m >= m1) break;
                 double c0 = __ldg(cosS + m), s0 = __ldg(sinS + m);
                 double cc = c0 * cphi + s0 * sphi, ss = s0 * cphi - c0 * sphi;
                 double v_wd = 1.0 - (double)pre[0] * kInvFix;
@@ -734,14 +815,14 @@ __global__ void __launch_bounds__(kFluxThreads) flux_kernel(const __grid_constan
                 bool any = false;
                 for (int k = 0; k < K; ++k) {
                     int p = __ldg(pos + j * K + k);
-                    if (p >= C.m0 && p < C.m1) {
+                    if (p >= m0 && p < m1) {
                         any = true;
                         double qw = G.quad_w[k];
-                        acc[0] += qw * Fs[p - C.m0];
+                        acc[0] += qw * Fs[p - m0];
                         if (A.mode) {
-                            acc[1] += qw * Fs[Mc + p - C.m0];
-                            acc[2] += qw * Fs[2 * Mc + p - C.m0];
-                            acc[3] += qw * Fs[3 * Mc + p - C.m0];
+                            acc[1] += qw * Fs[Mc + p - m0];
+                            acc[2] += qw * Fs[2 * Mc + p - m0];
+                            acc[3] += qw * Fs[3 * Mc + p - m0];
                         }
                     }
                 }

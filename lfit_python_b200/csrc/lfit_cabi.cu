@@ -209,7 +209,8 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int n_ecl, const long lon
 static size_t flux_smem_fixed(const GridCfg& G, int Mc, int nF)
 {
     size_t NI = (size_t)G.n_wd + G.n_disc + G.n_bs, NDQ = (size_t)G.n_donor_q;
-    return 8 * (3 * NI + 4 * NDQ + 20 * NDQ + (size_t)kNumArr * Mc + (size_t)nF * Mc + G.n_disc_r + G.n_wd_rings);
+    return 16 * (NI + 4 * NDQ) + 32 * NDQ + 8 * ((size_t)kNumArr * Mc + (size_t)kNumArr * kFluxThreads + (size_t)nF * Mc +
+                                                  G.n_bs + 2 * (size_t)(G.n_disc_r + G.n_wd_rings));
 }
 
 // One pass of the pipeline over walkers [0, n) (device pointers, one batch).
