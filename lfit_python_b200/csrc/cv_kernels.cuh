@@ -56,11 +56,13 @@ struct DevLayout {
 // the map from (point, quadrature node) to sorted position.
 struct DevSamples {
     const long long* lc_off;     // [n_ecl + 1] data-point offsets
-    const double *y, *ye;        // [total]
+    const double *y, *ye;        // [total] in phase order
     const double *S, *cosS, *sinS;  // [K * total] sorted per eclipse
-    const int* pos;              // [total * K]
-    const long long* chunk_off;  // [n_ecl + 1] offsets into chunk_j
-    const int* chunk_j;          // [2 * n_chunks] first / last data point touching each chunk
+    const int* bins;             // [K * total + n_ecl] per eclipse M + 1 entries (see SampleAxis)
+    const int* pos;              // [total * K] sorted position of each (point, node); points in phase order
+    const int* pt_index;         // [total] original index of each phase-ordered point
+    const long long* chunk_off;  // [n_ecl + 1] offsets into chunks
+    const int4* chunks;          // per chunk: first point, one past last point, first sample, last sample
 };
 
 struct GridCfg {
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(kElemThreads) elements_kernel(const __grid_con
     }
 }
 
-// ---------------------------------------------------------------- flux_kernel
+// ---------------------------------------------------------------- flux stage: prep / positions / flux
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -328,6 +330,7 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // Sum over the CTA, result in every thread.  Fixed tree: deterministic.
+template <int NT>
 __device__ __forceinline__ double block_sum(double v, double* red)
 {
     v = warp_sum(v);
@@ -337,18 +340,29 @@ __device__ __forceinline__ double block_sum(double v, double* red)
     __syncthreads();
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < kFluxThreads / 32; ++i) t += red[i];
+    for (int i = 0; i < NT / 32; ++i) t += red[i];
     return t;
 }
+
+constexpr int kNoEvent = 0x7fffffff;  // event position: never happens
+constexpr int kAtStart = -1;          // event position: before the first sample
+
+// Per-job constants of the flux stage (written by prep_kernel)
+struct JobConst {
+    double f_wd, f_d, f_s, f_rs;        // flux scale of each component's running sum
+    double beam_a, beam_b, beam_d, fis; // bright-spot beaming: fis + (1-fis) max(0, a c + b s + d)
+    double cphi, sphi, phi0w;           // phase offset wrapped to [-0.5, 0.5]
+    double don_sc;                      // 2^56 / sum of donor tile weights
+};
 
 struct FluxArgs {
     DevLayout L;
     GridCfg G;
     DevSamples smp;
     int what, flags, mode;  // mode 0: chi-squared, 1: flux curves
-    int Mc;                 // samples per chunk (multiple of kFluxThreads)
-    int model_in_smem;      // per-point partial sums live in shared memory (else in model_scratch)
-    int max_nph;
+    int Mc;                 // capacity of a chunk in samples
+    int max_chunks;         // chunks of the longest light curve (stride of chi_part)
+    int ni_total;           // event records per job: n_wd + n_disc + n_bs + 4 n_donor_q
     long long njobs;
     const double* theta;
     const WalkerScal* ws;
@@ -358,95 +372,291 @@ struct FluxArgs {
     const double2* disc_io;
     const double2* bs_io;
     const double* bs_b;
-    double* chisq;          // [njobs]
+    JobConst* jc;           // [njobs]
+    long long* wq;          // [njobs][n_wd_rings + n_disc_r + n_bs] fixed-point element weights
+    ulonglong2* ivp;        // [njobs][ni_total] event records (EventRec) of every eclipse / facing interval
+    double* chi_part;       // [njobs][max_chunks]
     double* flux_tot;       // mode 1: [njobs][n_ph]
     double* flux_comp;      // mode 1 (optional): [4][njobs][n_ph]
-    double* model_scratch;  // [gridDim.x][nF * max_nph] when !model_in_smem
 };
 
-// Sorted sample phases of one eclipse, with what the interpolating search needs.
+__device__ __forceinline__ bool job_live(const FluxArgs& A, const WalkerScal& W, const JobScal& J)
+{
+    if (J.status != 0) return false;
+    if (A.what != LFB_LN_LIKE && !(W.lnprior > -INFINITY)) return false;  // prior said no: not evaluated
+    return true;
+}
+
+// prep_kernel: one warp per job.  Component totals ("flux at maximum light", README.md:24-28),
+// fixed-point (2^-56) element weights, beaming and phase-offset constants.
+__global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FluxArgs A)
+{
+    const GridCfg& G = A.G;
+    const int lane = threadIdx.x & 31;
+    const long long job = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (job >= A.njobs) return;
+    const long long w = job / A.L.n_ecl;
+    const int e = (int)(job - w * A.L.n_ecl);
+    const WalkerScal& W = A.ws[w];
+    const JobScal& J = A.js[job];
+    if (!job_live(A, W, J)) return;
+    const double* th = A.theta + w * A.L.ndim;
+    const int* g = A.L.gather + e * LFB_NPAR;
+    auto par = [&](int k, double dflt) { return k < A.L.npars ? fetch(A.L, th, g[k]) : dflt; };
+    const bool do_wd = !(A.flags & LFB_FLAG_SKIP_WD), do_disc = !(A.flags & LFB_FLAG_SKIP_DISC);
+    const bool do_bs = !(A.flags & LFB_FLAG_SKIP_BS), do_don = !(A.flags & LFB_FLAG_SKIP_DONOR);
+    const double si = W.si, ci = W.ci, xl1 = W.R.xl1;
+    const double rwd_a = par(P_RWD, 0.0) * xl1, rdisc_a = par(P_RDISC, 0.0) * xl1;
+    const double ulimb = par(P_ULIMB, 0.0), dexp = par(P_DEXP, 0.0);
+    long long* wq_wd = A.wq + job * (G.n_wd_rings + G.n_disc_r + G.n_bs);
+    long long* wq_disc = wq_wd + G.n_wd_rings;
+    long long* wq_bs = wq_disc + G.n_disc_r;
+    // white dwarf rings: equal-area tiles, weight (1 - u) + u <mu>_ring
+    double p = 0.0;
+    for (int k = lane; k < G.n_wd_rings; k += 32) {
+        double inv = 1.0 / G.n_wd_rings, ra = k * inv, rb = (k + 1) * inv;
+        double ua = 1.0 - ra * ra, ub = 1.0 - rb * rb;
+        double mubar = (2.0 / 3.0) * (ua * sqrt(ua) - ub * sqrt(ub)) / (rb * rb - ra * ra);
+        p += 4.0 * (2 * k + 1) * ((1.0 - ulimb) + ulimb * mubar);
+    }
+    const double tot_wd = warp_sum(p);
+    for (int k = lane; k < G.n_wd_rings; k += 32) {
+        double inv = 1.0 / G.n_wd_rings, ra = k * inv, rb = (k + 1) * inv;
+        double ua = 1.0 - ra * ra, ub = 1.0 - rb * rb;
+        double mubar = (2.0 / 3.0) * (ua * sqrt(ua) - ub * sqrt(ub)) / (rb * rb - ra * ra);
+        wq_wd[k] = do_wd ? llrint(((1.0 - ulimb) + ulimb * mubar) / tot_wd * kFix) : 0;
+    }
+    // disc rings: brightness r^-dexp times area ~ r
+    p = 0.0;
+    for (int m = lane; m < G.n_disc_r; m += 32) {
+        double r = rwd_a + (m + 0.5) * (rdisc_a - rwd_a) / G.n_disc_r;
+        p += G.n_disc_th * pow(r, 1.0 - dexp);
+    }
+    const double tot_d = warp_sum(p);
+    for (int m = lane; m < G.n_disc_r; m += 32) {
+        double r = rwd_a + (m + 0.5) * (rdisc_a - rwd_a) / G.n_disc_r;
+        wq_disc[m] = do_disc ? llrint(pow(r, 1.0 - dexp) / tot_d * kFix) : 0;
+    }
+    // bright-spot strip
+    const double* bsb = A.bs_b + job * G.n_bs;
+    p = 0.0;
+    if (do_bs) for (int t = lane; t < G.n_bs; t += 32) p += bsb[t];
+    const double tot_s = warp_sum(p);
+    for (int t = lane; t < G.n_bs; t += 32) wq_bs[t] = (do_bs && tot_s > 0.0) ? llrint(bsb[t] / tot_s * kFix) : 0;
+    // donor: normalised at quadrature (phase 0.25: c = 0, s = 1)
+    const double4* don = A.don + w * G.n_donor_q;
+    const double ud = G.donor_ulimb;
+    double p_rs = 0.0, p_rw = 0.0;
+    if (do_don)
+        for (int t = lane; t < G.n_donor_q; t += 32) {
+            double4 q = don[t];
+            double b = si * q.y, d = ci * q.z, m;
+            m = -b + d; if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
+            m = b + d;  if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
+            m = -b - d; if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
+            m = b - d;  if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
+            p_rw += 4.0 * q.w;
+        }
+    const double tot_rs = warp_sum(p_rs), tot_rw = warp_sum(p_rw);
+    if (lane == 0) {
+        JobConst C;
+        // beamed part of the spot: polar angle tilt from +z, azimuth az - 90 + yaw
+        const double fis = par(P_FIS, 0.0);
+        double st, ct, sp, cp;
+        sincos_(par(P_TILT, 90.0) * kDeg, &st, &ct);
+        sincos_((par(P_AZ, 0.0) - 90.0 + par(P_YAW, 0.0)) * kDeg, &sp, &cp);
+        C.beam_a = si * st * cp;
+        C.beam_b = -si * st * sp;
+        C.beam_d = ci * ct;
+        C.fis = fis;
+        double cmax = si * st + ci * ct;  // cos(i - tilt): best alignment over an orbit
+        double beam_norm = fis + (1.0 - fis) * (cmax > 0.0 ? cmax : 0.0);
+        C.f_wd = do_wd ? par(P_WDFLUX, 0.0) : 0.0;
+        C.f_d = do_disc ? par(P_DFLUX, 0.0) : 0.0;
+        C.f_s = (do_bs && beam_norm > 0.0 && tot_s > 0.0) ? par(P_SFLUX, 0.0) / beam_norm : 0.0;
+        C.f_rs = do_don ? par(P_RSFLUX, 0.0) / tot_rs * (tot_rw * kInvFix) : 0.0;
+        double phi0w = par(P_PHI0, 0.0);
+        phi0w -= rint(phi0w);
+        C.phi0w = phi0w;
+        sincos_(kTwoPi * phi0w, &C.sphi, &C.cphi);
+        C.don_sc = do_don ? kFix / tot_rw : 0.0;
+        A.jc[job] = C;
+    }
+}
+
+// Sorted sample phases of one eclipse plus a bin table: bins[b] is the first sample whose phase
+// falls in or after the b-th of M equal phase bins, so a search is a table look-up and a short
+// walk instead of log2(M) dependent loads.
 struct SampleAxis {
     const double* S;
+    const int* bins;  // [M + 1]
     int M;
-    double s_first, s_last, scale;  // scale = (M - 1) / (s_last - s_first)
+    double s_first, s_last, inv_binw;
 };
 
-// First index with S[idx] > v (strict) or S[idx] >= v (!strict); M if none.  Light curves are
-// close to uniformly sampled, so start from the interpolated position and gallop: a couple of
-// loads instead of log2(M).
+__device__ __forceinline__ SampleAxis sample_axis(const DevSamples& smp, int e, int K)
+{
+    SampleAxis X;
+    const long long lc0 = smp.lc_off[e];
+    X.M = (int)(smp.lc_off[e + 1] - lc0) * K;
+    X.S = smp.S + lc0 * K;
+    X.bins = smp.bins + lc0 * K + e;
+    X.s_first = X.M > 0 ? __ldg(X.S) : 0.0;
+    X.s_last = X.M > 0 ? __ldg(X.S + X.M - 1) : 0.0;
+    X.inv_binw = X.s_last > X.s_first ? (double)X.M / (X.s_last - X.s_first) : 0.0;
+    return X;
+}
+
+// First index with S[idx] > v (strict) or S[idx] >= v (!strict); M if none.  The bin only seeds
+// the walk, so host/device rounding of the bin index cannot change the answer.
 __device__ __forceinline__ int sample_search(const SampleAxis& X, double v, bool strict)
 {
     const double* __restrict__ S = X.S;
     const int M = X.M;
-    double gf = (v - X.s_first) * X.scale;
-    int g = gf <= 0.0 ? 0 : (gf >= (double)(M - 1) ? M - 1 : (int)gf);
-    int lo, hi;
-    double sg = __ldg(S + g);
-    if (strict ? (sg <= v) : (sg < v)) {
-        lo = g + 1;
-        hi = M;
-        for (int step = 1; lo < M; step <<= 1) {
-            int j = min(M - 1, g + step);
-            double s = __ldg(S + j);
-            if (strict ? (s <= v) : (s < v)) {
-                lo = j + 1;
-                if (j == M - 1) break;
-            } else {
-                hi = j;
-                break;
-            }
-        }
-    } else {
-        hi = g;
-        lo = 0;
-        for (int step = 1; hi > 0; step <<= 1) {
-            int j = max(0, g - step);
-            double s = __ldg(S + j);
-            if (strict ? (s <= v) : (s < v)) {
-                lo = j + 1;
-                break;
-            } else {
-                hi = j;
-                if (j == 0) break;
-            }
-        }
+    double gf = (v - X.s_first) * X.inv_binw;
+    int b = gf <= 0.0 ? 0 : (gf >= (double)(M - 1) ? M - 1 : (int)gf);
+    int p = __ldg(X.bins + b);
+    while (p < M) {
+        double s = __ldg(S + p);
+        if (!(strict ? (s <= v) : (s < v))) break;
+        ++p;
     }
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        double s = __ldg(S + mid);
-        if (strict ? (s <= v) : (s < v)) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// The samples with a < S + n < b for integer n: since S lies in [-0.5, 0.5] and b - a < 1 at
-// most two shifts contribute.  Each piece is (first sample inside, first sample at or past the
-// end); -1 marks "no event": an opening at sample 0 is returned through *open_at_start instead
-// (the caller adds the weight to the running sum's start value), a closing past the last sample
-// never happens.
-__device__ __forceinline__ int4 interval_pieces(const SampleAxis& X, double a, double b, int* open_at_start)
-{
-    int4 p = make_int4(-1, -1, -1, -1);
-    *open_at_start = 0;
-    if (!(a < b) || !(a > -1e29) || !(b < 1e29)) return p;
-    int n_lo = (int)ceil(X.s_first - b), n_hi = (int)floor(X.s_last - a);
-    int np = 0;
-    for (int n = n_lo; n <= n_hi && np < 2; ++n) {
-        double an = a + n, bn = b + n;
-        int po = an < X.s_first ? 0 : sample_search(X, an, true);
-        int pc = bn > X.s_last ? X.M : sample_search(X, bn, false);
-        if (pc <= po) continue;  // no sample inside
-        if (po == 0) { *open_at_start += 1; po = -1; }
-        if (pc >= X.M) pc = -1;
-        if (np == 0) { p.x = po; p.y = pc; } else { p.z = po; p.w = pc; }
-        ++np;
+    while (p > 0) {
+        double s = __ldg(S + p - 1);
+        if (strict ? (s <= v) : (s < v)) break;
+        --p;
     }
     return p;
 }
 
-__device__ __forceinline__ void add_event(unsigned long long* Darr, int p, int m0, int m1, long long w)
+// Event record of one eclipse / facing interval: up to three pieces (open, close) of sample
+// positions, six 21-bit fields in 128 bits.  Field value 0 = before the first sample
+// (kAtStart), 0x1FFFFF = no event, else position + 1.  Positions ascend from field 0 to 5.
+typedef ulonglong2 EventRec;
+constexpr unsigned kFieldNone = 0x1FFFFFu;
+constexpr int kMaxSamples = (1 << 21) - 3;
+
+__device__ __forceinline__ unsigned long long enc_pos(int p)
 {
-    if (p >= m0 && p < m1) atomicAdd(Darr + (p - m0), (unsigned long long)w);
+    return p == kNoEvent ? (unsigned long long)kFieldNone : (unsigned long long)(unsigned)(p + 1);
+}
+__device__ __forceinline__ int dec_pos(unsigned long long word, int k)
+{
+    unsigned f = (unsigned)(word >> (21 * k)) & kFieldNone;
+    return f == kFieldNone ? kNoEvent : (int)f - 1;
+}
+__device__ __forceinline__ EventRec no_events()
+{
+    const unsigned long long w = (unsigned long long)kFieldNone | ((unsigned long long)kFieldNone << 21) |
+                                 ((unsigned long long)kFieldNone << 42);
+    return make_ulonglong2(w, w);
+}
+
+// The samples with a < S + n < b for integer n.  Points are wrapped to [-0.5, 0.5) as a whole
+// and exposures are shorter than an orbit, so the axis spans less than two cycles and b - a < 1:
+// at most three shifts contribute.  Each piece is (first sample inside, first sample at or past
+// the end); kAtStart = open before the first sample, kNoEvent = nothing.
+__device__ __forceinline__ EventRec interval_pieces(const SampleAxis& X, double a, double b)
+{
+    int ev[6] = {kNoEvent, kNoEvent, kNoEvent, kNoEvent, kNoEvent, kNoEvent};
+    if ((a < b) && (a > -1e29) && (b < 1e29) && X.M > 0) {
+        int n_lo = (int)ceil(X.s_first - b), n_hi = (int)floor(X.s_last - a);
+        int np = 0;
+        for (int n = n_lo; n <= n_hi && np < 3; ++n) {
+            double an = a + n, bn = b + n;
+            int po = an < X.s_first ? 0 : sample_search(X, an, true);
+            int pc = bn > X.s_last ? X.M : sample_search(X, bn, false);
+            if (pc <= po) continue;  // no sample inside
+            if (po == 0) po = kAtStart;
+            if (pc >= X.M) pc = kNoEvent;
+            if (np == 0) { ev[0] = po; ev[1] = pc; }
+            else if (np == 1) { ev[2] = po; ev[3] = pc; }
+            else { ev[4] = po; ev[5] = pc; }
+            ++np;
+        }
+    }
+    return make_ulonglong2(enc_pos(ev[0]) | (enc_pos(ev[1]) << 21) | (enc_pos(ev[2]) << 42),
+                           enc_pos(ev[3]) | (enc_pos(ev[4]) << 21) | (enc_pos(ev[5]) << 42));
+}
+
+// positions_kernel: one thread per solved element (or donor quarter tile) of a job: where on the
+// job's sorted sample axis its eclipse (facing) intervals open and close.
+__global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ FluxArgs A)
+{
+    const GridCfg& G = A.G;
+    const int per_job = G.n_wd_half + G.n_disc_half + G.n_bs + G.n_donor_q;
+    const int padded = (per_job + 31) & ~31;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long job = gid / padded;
+    const int t = (int)(gid - job * padded);
+    if (job >= A.njobs || t >= per_job) return;
+    const long long w = job / A.L.n_ecl;
+    const int egather = (int)(job - w * A.L.n_ecl);
+    const int e = A.mode ? 0 : egather;
+    const WalkerScal& W = A.ws[w];
+    if (!job_live(A, W, A.js[job])) return;
+    const SampleAxis X = sample_axis(A.smp, e, G.n_quad);
+    const JobConst& C = A.jc[job];
+    const double phi0w = C.phi0w;
+    EventRec* ivp = A.ivp + job * A.ni_total;
+    const int n_half = G.n_wd_half + G.n_disc_half;
+    const EventRec none = no_events();
+    if (t < n_half + G.n_bs) {
+        double2 io;
+        int i0;
+        bool on, mirror = t < n_half;
+        if (t < G.n_wd_half) {
+            on = !(A.flags & LFB_FLAG_SKIP_WD);
+            io = on ? A.wd_io[w * G.n_wd_half + t] : make_double2(kBig, -kBig);
+            i0 = 2 * t;
+        } else if (t < n_half) {
+            int h = t - G.n_wd_half;
+            on = !(A.flags & LFB_FLAG_SKIP_DISC);
+            io = on ? A.disc_io[job * G.n_disc_half + h] : make_double2(kBig, -kBig);
+            i0 = G.n_wd + 2 * h;
+        } else {
+            int h = t - n_half;
+            on = !(A.flags & LFB_FLAG_SKIP_BS);
+            io = on ? A.bs_io[job * G.n_bs + h] : make_double2(kBig, -kBig);
+            i0 = G.n_wd + G.n_disc + h;
+        }
+        const bool ecl = io.y > io.x;
+        ivp[i0] = ecl ? interval_pieces(X, io.x + phi0w, io.y + phi0w) : none;
+        // the y -> -y image is eclipsed from -egress to -ingress
+        if (mirror) ivp[i0 + 1] = ecl ? interval_pieces(X, -io.y + phi0w, -io.x + phi0w) : none;
+    } else {
+        // donor: every tile image faces the observer for |phase - centre| < half width
+        const int h = t - n_half - G.n_bs;
+        const bool on = !(A.flags & LFB_FLAG_SKIP_DONOR);
+        double4 q = on ? A.don[w * G.n_donor_q + h] : make_double4(1.0, 0.0, 0.0, 0.0);
+        double Aq = W.si * q.x, Bq = -W.si * q.y, Dq = W.ci * q.z;
+        double rho = sqrt(Aq * Aq + Bq * Bq);
+        double psi = atan2(Bq, Aq) * (1.0 / kTwoPi);
+        double ratio = rho > 0.0 ? Dq / rho : (Dq > 0.0 ? 2.0 : -2.0);
+        // image with +D faces the observer iff cos(th - psi) > -D/rho
+        double hp = ratio >= 1.0 ? 0.5 : (ratio <= -1.0 ? -1.0 : acos(-ratio) * (1.0 / kTwoPi));
+        double hm = ratio <= -1.0 ? 0.5 : (ratio >= 1.0 ? -1.0 : acos(ratio) * (1.0 / kTwoPi));
+        EventRec* dnp = ivp + G.n_wd + G.n_disc + G.n_bs + 4 * h;
+#pragma unroll
+        for (int im = 0; im < 4; ++im) {
+            double cen = ((im & 1) ? -psi : psi) + phi0w, hw = (im & 2) ? hm : hp;
+            EventRec p = none;
+            if (on && hw >= 0.5) p.x = (p.x & ~(unsigned long long)kFieldNone) | enc_pos(kAtStart);  // always faces the observer
+            else if (on && hw >= 0.0) p = interval_pieces(X, cen - hw, cen + hw);
+            dnp[im] = p;
+        }
+    }
+}
+
+// A record matters to the chunk [m0, m1) unless all its events come after the chunk (positions
+// ascend, so the first one decides) or every piece has closed before it (then +w and -w cancel
+// in the chunk's start value).
+__device__ __forceinline__ bool rec_irrelevant(const EventRec& rec, int m0, int m1)
+{
+    if (dec_pos(rec.x, 0) >= m1) return true;
+    const int o1 = dec_pos(rec.x, 2), o2 = dec_pos(rec.y, 1);
+    const int last_close = o2 != kNoEvent ? dec_pos(rec.y, 2) : (o1 != kNoEvent ? dec_pos(rec.y, 0) : dec_pos(rec.x, 1));
+    return last_close < m0;
 }
 
 // five moments (1, c, s, c^2, c s) of W m (1 - u + u m), m = A c + B s + D, in 2^-56 fixed point
@@ -459,425 +669,254 @@ __device__ __forceinline__ void donor_moments(double sc, double ud, double Aq, d
     mo[4] = llrint(sc * (2.0 * ud * Aq * Bi));
 }
 
+// An event of weight w at sample position p, seen from the chunk [m0, m1): before the chunk it
+// belongs to the chunk's start value, inside it goes to the chunk's event array.
+__device__ __forceinline__ void put_event(unsigned long long* Darr, long long* base, int p, int m0, int m1, long long w)
+{
+    if (p < m0) *base += w;
+    else if (p < m1) atomicAdd(Darr + (p - m0), (unsigned long long)w);
+}
+
+// flux_kernel: one CTA per (job, chunk of consecutive data points).  The chunk's samples are a
+// contiguous range [m0, m1) of the sorted sample axis.  All interval records of the job are
+// streamed once from L2: events inside the range go to shared-memory event arrays (exact
+// fixed-point atomics), events before it into the start values; a block scan gives the
+// eclipsed / facing sums at every sample, then component mix, exposure quadrature, residuals.
 __global__ void __launch_bounds__(kFluxThreads) flux_kernel(const __grid_constant__ FluxArgs A)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     const GridCfg& G = A.G;
     constexpr int NW = kFluxThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int NI = G.n_wd + G.n_disc + G.n_bs;   // eclipse intervals (mirrors included)
-    const int NDQ = G.n_donor_q;
-    const int Mc = A.Mc, R = Mc / kFluxThreads;  // samples per thread per chunk
-    const int nF = A.mode ? 4 : 1;
-    // shared-memory carve-up (16-byte aligned pieces first)
-    int4* iv_p = (int4*)smraw;                            // [NI]      sample positions of each interval's events
-    int4* dn_p = iv_p + NI;                               // [4 NDQ]   same for the donor tile images
-    double4* dn_q = (double4*)(dn_p + 4 * NDQ);           // [NDQ]     (A, B, D, scaled weight) of a quarter tile
-    unsigned long long* D = (unsigned long long*)(dn_q + NDQ);  // [kNumArr][Mc] events, then nothing else
-    long long* part = (long long*)(D + kNumArr * Mc);     // [kNumArr][kFluxThreads] scan partials
-    double* Fs = (double*)(part + kNumArr * kFluxThreads);  // [nF][Mc] flux per sample of the chunk
-    long long* wq_bs = (long long*)(Fs + nF * Mc);        // [n_bs]    fixed-point strip weights
-    long long* wq_ring = wq_bs + G.n_bs;                  // [n_disc_r + n_wd_rings]
-    double* ringw = (double*)(wq_ring + G.n_disc_r + G.n_wd_rings);  // [n_disc_r + n_wd_rings]
-    double* model_sm = ringw + G.n_disc_r + G.n_wd_rings; // [nF * n_ph] when model_in_smem
-    __shared__ double s_par[LFB_NPAR];
+    const int Mc = A.Mc;
+    unsigned long long* D = (unsigned long long*)smraw;     // [kNumArr][Mc] events
+    long long* part = (long long*)(D + kNumArr * Mc);       // [kNumArr][kFluxThreads] scan partials
+    double* Fs = (double*)(part + kNumArr * kFluxThreads);  // [nF][Mc] flux per sample
     __shared__ double red[NW];
     __shared__ long long wtot[kNumArr][NW];
-    __shared__ long long s_tot[kNumArr];
 
-    const bool do_wd = !(A.flags & LFB_FLAG_SKIP_WD), do_disc = !(A.flags & LFB_FLAG_SKIP_DISC);
-    const bool do_bs = !(A.flags & LFB_FLAG_SKIP_BS), do_don = !(A.flags & LFB_FLAG_SKIP_DONOR);
-
-    for (long long job = blockIdx.x; job < A.njobs; job += gridDim.x) {
-        const long long w = job / A.L.n_ecl;
-        const int egather = (int)(job - w * A.L.n_ecl);
-        const int e = A.mode ? 0 : egather;
-        const long long lc0 = A.smp.lc_off[e];
-        const int n_ph = (int)(A.smp.lc_off[e + 1] - lc0);
-        const int K = G.n_quad;
-        const int M = n_ph * K;
-        const double* cosS = A.smp.cosS + lc0 * K;
-        const double* sinS = A.smp.sinS + lc0 * K;
-        const int* pos = A.smp.pos + lc0 * K;
-        const int* chunk_j = A.smp.chunk_j + 2 * A.smp.chunk_off[e];
-        double* model = A.model_in_smem ? model_sm : A.model_scratch + (size_t)blockIdx.x * nF * A.max_nph;
-        __syncthreads();
-        if (tid < LFB_NPAR) {
-            double v = 0.0;
-            if (tid < A.L.npars) v = fetch(A.L, A.theta + w * A.L.ndim, A.L.gather[egather * LFB_NPAR + tid]);
-            else if (tid == P_EXP1) v = 2.0;
-            else if (tid == P_EXP2) v = 1.0;
-            else if (tid == P_TILT) v = 90.0;
-            s_par[tid] = v;
-        }
-        __syncthreads();
-        const WalkerScal W = A.ws[w];
-        const JobScal J = A.js[job];
-        const bool vetoed = A.what != LFB_LN_LIKE && !(W.lnprior > -INFINITY);  // prior said no: not evaluated
-        if (J.status != 0 || n_ph == 0 || vetoed) {
-            if (A.mode == 0) {
-                if (tid == 0) A.chisq[job] = (J.status == 4 || vetoed) ? NAN : (J.status != 0 ? INFINITY : 0.0);
-            } else {
-                for (int j = tid; j < n_ph; j += kFluxThreads) {
-                    A.flux_tot[job * n_ph + j] = NAN;
-                    if (A.flux_comp)
-                        for (int cidx = 0; cidx < 4; ++cidx) A.flux_comp[((long long)cidx * A.njobs + job) * n_ph + j] = NAN;
-                }
-            }
-            continue;
-        }
-        SampleAxis X;
-        X.S = A.smp.S + lc0 * K;
-        X.M = M;
-        X.s_first = __ldg(X.S);
-        X.s_last = __ldg(X.S + M - 1);
-        X.scale = X.s_last > X.s_first ? (double)(M - 1) / (X.s_last - X.s_first) : 0.0;
-        const Roche Rr = W.R;
-        const double si = W.si, ci = W.ci;
-        const double rwd_a = s_par[P_RWD] * Rr.xl1, rdisc_a = s_par[P_RDISC] * Rr.xl1;
-        double phi0w = s_par[P_PHI0];
-        phi0w -= rint(phi0w);
-        double sphi, cphi;
-        sincos_(kTwoPi * phi0w, &sphi, &cphi);
-
-        // ---- ring weights and component totals ("flux at maximum light", README.md:24-28) ----
-        double* wdw = ringw + G.n_disc_r;
-        if (do_disc)
-            for (int m = tid; m < G.n_disc_r; m += kFluxThreads) {
-                double r = rwd_a + (m + 0.5) * (rdisc_a - rwd_a) / G.n_disc_r;
-                ringw[m] = pow(r, 1.0 - s_par[P_DEXP]);
-            }
-        if (do_wd)
-            for (int k = tid; k < G.n_wd_rings; k += kFluxThreads) {
-                double inv = 1.0 / G.n_wd_rings, ra = k * inv, rb = (k + 1) * inv;
-                double ua = 1.0 - ra * ra, ub = 1.0 - rb * rb;
-                double mubar = (2.0 / 3.0) * (ua * sqrt(ua) - ub * sqrt(ub)) / (rb * rb - ra * ra);
-                wdw[k] = (1.0 - s_par[P_ULIMB]) + s_par[P_ULIMB] * mubar;
-            }
-        const double* bsb = A.bs_b + job * G.n_bs;
-        const double4* don = A.don + w * NDQ;
-        double p_s = 0.0, p_rs = 0.0, p_rw = 0.0;
-        if (do_bs) for (int t = tid; t < G.n_bs; t += kFluxThreads) p_s += bsb[t];
-        const double ud = G.donor_ulimb;
-        if (do_don)
-            for (int t = tid; t < NDQ; t += kFluxThreads) {
-                // donor at quadrature (phase 0.25): c = 0, s = 1
-                double4 q = don[t];
-                double b = si * q.y, d = ci * q.z, m;
-                m = -b + d; if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
-                m = b + d;  if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
-                m = -b - d; if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
-                m = b - d;  if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
-                p_rw += 4.0 * q.w;
-            }
-        const double tot_s = block_sum(p_s, red), tot_rs = block_sum(p_rs, red), tot_rw = block_sum(p_rw, red);
-        double tot_wd = 0.0, tot_d = 0.0;  // after block_sum's barriers the ring weights are visible
-        for (int k = 0; k < G.n_wd_rings; ++k) tot_wd += 4.0 * (2 * k + 1) * wdw[k];
-        for (int m = 0; m < G.n_disc_r; ++m) tot_d += G.n_disc_th * ringw[m];
-        // beamed part of the spot: polar angle tilt from +z, azimuth az - 90 + yaw
-        double beam_a = 0.0, beam_b = 0.0, beam_d = 0.0, beam_norm = 1.0;
-        const double fis = s_par[P_FIS];
-        if (do_bs) {
-            double st, ct, sp, cp;
-            sincos_(s_par[P_TILT] * kDeg, &st, &ct);
-            sincos_((s_par[P_AZ] - 90.0 + s_par[P_YAW]) * kDeg, &sp, &cp);
-            beam_a = si * st * cp;
-            beam_b = -si * st * sp;
-            beam_d = ci * ct;
-            double cmax = si * st + ci * ct;
-            beam_norm = fis + (1.0 - fis) * (cmax > 0.0 ? cmax : 0.0);
-        }
-        const double f_wd = do_wd ? s_par[P_WDFLUX] : 0.0, f_d = do_disc ? s_par[P_DFLUX] : 0.0;
-        const double f_s = (do_bs && beam_norm > 0.0 && tot_s > 0.0) ? s_par[P_SFLUX] / beam_norm : 0.0;
-        const double f_rs = do_don ? s_par[P_RSFLUX] / tot_rs * (tot_rw * kInvFix) : 0.0;
-        // fixed-point (2^-56) weights: per ring for the white dwarf and the disc, per element for the strip
-        long long* wq_disc = wq_ring;
-        long long* wq_wd = wq_ring + G.n_disc_r;
-        for (int m = tid; m < G.n_disc_r; m += kFluxThreads) wq_disc[m] = do_disc ? llrint(ringw[m] / tot_d * kFix) : 0;
-        for (int k = tid; k < G.n_wd_rings; k += kFluxThreads) wq_wd[k] = do_wd ? llrint(wdw[k] / tot_wd * kFix) : 0;
-        for (int t = tid; t < G.n_bs; t += kFluxThreads) wq_bs[t] = (do_bs && tot_s > 0.0) ? llrint(bsb[t] / tot_s * kFix) : 0;
-        for (int j = tid; j < nF * n_ph; j += kFluxThreads) model[j] = 0.0;
-        __syncthreads();
-
-        // ---- pass 1: every eclipse / facing interval -> positions of its events on the sample axis ----
-        long long base[kNumArr];
-#pragma unroll
-        for (int a = 0; a < kNumArr; ++a) base[a] = 0;
-        const double2* wdio = A.wd_io + w * G.n_wd_half;
-        const double2* dio = A.disc_io + job * G.n_disc_half;
-        const double2* bio = A.bs_io + job * G.n_bs;
-        const int n_half = G.n_wd_half + G.n_disc_half;
-        for (int t = tid; t < n_half + G.n_bs; t += kFluxThreads) {
-            double2 io;
-            int i0, arr;
-            long long wq;
-            bool mirror = t < n_half;
-            if (t < G.n_wd_half) {
-                int k = (int)sqrt(0.5 * (double)t);
-                while (2 * k * k > t) --k;
-                while (2 * (k + 1) * (k + 1) <= t) ++k;
-                io = do_wd ? wdio[t] : make_double2(kBig, -kBig);
-                wq = wq_wd[k];
-                i0 = 2 * t;
-                arr = 0;
-            } else if (t < n_half) {
-                int h = t - G.n_wd_half;
-                io = do_disc ? dio[h] : make_double2(kBig, -kBig);
-                wq = wq_disc[h / (G.n_disc_th / 2)];
-                i0 = G.n_wd + 2 * h;
-                arr = 1;
-            } else {
-                int h = t - n_half;
-                io = do_bs ? bio[h] : make_double2(kBig, -kBig);
-                wq = wq_bs[h];
-                i0 = G.n_wd + G.n_disc + h;
-                arr = 2;
-            }
-            const bool ecl = io.y > io.x;
-            int nopen = 0;
-            int4 p = ecl ? interval_pieces(X, io.x + phi0w, io.y + phi0w, &nopen) : make_int4(-1, -1, -1, -1);
-            iv_p[i0] = p;
-            long long b0 = nopen * wq;
-            if (mirror) {  // the y -> -y image is eclipsed from -egress to -ingress
-                p = ecl ? interval_pieces(X, -io.y + phi0w, -io.x + phi0w, &nopen) : make_int4(-1, -1, -1, -1);
-                iv_p[i0 + 1] = p;
-                b0 += nopen * wq;
-            }
-            base[0] += arr == 0 ? b0 : 0;
-            base[1] += arr == 1 ? b0 : 0;
-            base[2] += arr == 2 ? b0 : 0;
-        }
-        // donor: every tile image faces the observer for |phase - centre| < half width; while it does it
-        // adds W m (1 - u + u m), m = A c + B s + D
-        for (int t = tid; t < NDQ; t += kFluxThreads) {
-            double4 q = do_don ? don[t] : make_double4(1.0, 0.0, 0.0, 0.0);
-            double Aq = si * q.x, Bq = -si * q.y, Dq = ci * q.z;
-            double rho = sqrt(Aq * Aq + Bq * Bq);
-            double psi = atan2(Bq, Aq) * (1.0 / kTwoPi);
-            double ratio = rho > 0.0 ? Dq / rho : (Dq > 0.0 ? 2.0 : -2.0);
-            // image with +D faces the observer iff cos(th - psi) > -D/rho
-            double hp = ratio >= 1.0 ? 0.5 : (ratio <= -1.0 ? -1.0 : acos(-ratio) * (1.0 / kTwoPi));
-            double hm = ratio <= -1.0 ? 0.5 : (ratio >= 1.0 ? -1.0 : acos(ratio) * (1.0 / kTwoPi));
-            double sc = do_don ? q.w / tot_rw * kFix : 0.0;
-            dn_q[t] = make_double4(Aq, Bq, Dq, sc);
-#pragma unroll
-            for (int im = 0; im < 4; ++im) {
-                double cen = ((im & 1) ? -psi : psi) + phi0w, hw = (im & 2) ? hm : hp;
-                int4 p = make_int4(-1, -1, -1, -1);
-                int nopen = 0;
-                if (!do_don || hw < 0.0) {
-                    // never faces the observer
-                } else if (hw >= 0.5) {
-                    nopen = 1;  // always does
-                } else {
-                    p = interval_pieces(X, cen - hw, cen + hw, &nopen);
-                }
-                dn_p[4 * t + im] = p;
-                if (nopen) {
-                    long long mo[5];
-                    donor_moments(sc, ud, Aq, (im & 1) ? -Bq : Bq, (im & 2) ? -Dq : Dq, mo);
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) base[3 + k] += nopen * mo[k];
-                }
-            }
-        }
-        // running sums start from the intervals already open at the first sample (exact integer reduction)
-        long long carry[kNumArr];
-#pragma unroll
-        for (int a = 0; a < kNumArr; ++a) {
-            long long v = base[a];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) wtot[a][wid] = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int a = 0; a < kNumArr; ++a) {
-            long long v = 0;
-#pragma unroll
-            for (int i = 0; i < NW; ++i) v += wtot[a][i];
-            carry[a] = v;
-        }
-
-        // ---- pass 2: chunks of the sorted sample axis ----
-        const int n_chunks = (M + Mc - 1) / Mc;
-        for (int c = 0; c < n_chunks; ++c) {
-            const int m0 = c * Mc, m1 = min(M, m0 + Mc);
-            for (int i = tid; i < kNumArr * Mc; i += kFluxThreads) D[i] = 0ull;
-            __syncthreads();
-            for (int i = tid; i < NI; i += kFluxThreads) {
-                const int4 p = iv_p[i];
-                if (!((p.x >= m0 && p.x < m1) || (p.y >= m0 && p.y < m1) || (p.z >= m0 && p.z < m1) ||
-                      (p.w >= m0 && p.w < m1)))
-                    continue;
-                int arr;
-                long long wq;
-                if (i < G.n_wd) {
-                    int t = i >> 1;
-                    int k = (int)sqrt(0.5 * (double)t);
-                    while (2 * k * k > t) --k;
-                    while (2 * (k + 1) * (k + 1) <= t) ++k;
-                    wq = wq_wd[k];
-                    arr = 0;
-                } else if (i < G.n_wd + G.n_disc) {
-                    wq = wq_disc[((i - G.n_wd) >> 1) / (G.n_disc_th / 2)];
-                    arr = 1;
-                } else {
-                    wq = wq_bs[i - G.n_wd - G.n_disc];
-                    arr = 2;
-                }
-                unsigned long long* Da = D + arr * Mc;
-                add_event(Da, p.x, m0, m1, wq);
-                add_event(Da, p.y, m0, m1, -wq);
-                add_event(Da, p.z, m0, m1, wq);
-                add_event(Da, p.w, m0, m1, -wq);
-            }
-            if (do_don)
-                for (int i = tid; i < 4 * NDQ; i += kFluxThreads) {
-                    const int4 p = dn_p[i];
-                    const bool hx = p.x >= m0 && p.x < m1, hy = p.y >= m0 && p.y < m1;
-                    const bool hz = p.z >= m0 && p.z < m1, hw_ = p.w >= m0 && p.w < m1;
-                    if (!(hx || hy || hz || hw_)) continue;
-                    const double4 q = dn_q[i >> 2];
-                    long long mo[5];
-                    donor_moments(q.w, ud, q.x, (i & 1) ? -q.y : q.y, (i & 2) ? -q.z : q.z, mo);
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        unsigned long long* Da = D + (3 + k) * Mc;
-                        if (hx) atomicAdd(Da + (p.x - m0), (unsigned long long)mo[k]);
-                        if (hy) atomicAdd(Da + (p.y - m0), (unsigned long long)(-mo[k]));
-                        if (hz) atomicAdd(Da + (p.z - m0), (unsigned long long)mo[k]);
-                        if (hw_) atomicAdd(Da + (p.w - m0), (unsigned long long)(-mo[k]));
-                    }
-                }
-            __syncthreads();
-            // block scan: thread t owns samples m0 + t*R .. +R-1; warp a scans the partials of array a
-#pragma unroll
-            for (int a = 0; a < kNumArr; ++a) {
-                long long v = 0;
-                for (int r = 0; r < R; ++r) v += (long long)D[a * Mc + tid * R + r];
-                part[a * kFluxThreads + tid] = v;
-            }
-            __syncthreads();
-            for (int a = wid; a < kNumArr; a += NW) {
-                long long* pa = part + a * kFluxThreads + lane * NW;
-                long long loc[NW], t = 0;
-#pragma unroll
-                for (int j = 0; j < NW; ++j) { loc[j] = t; t += pa[j]; }
-                long long inc = t;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    long long u = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += u;
-                }
-                long long exc = inc - t;
-#pragma unroll
-                for (int j = 0; j < NW; ++j) pa[j] = exc + loc[j];
-                if (lane == 31) s_tot[a] = inc;
-            }
-            __syncthreads();
-            long long pre[kNumArr];
-#pragma unroll
-            for (int a = 0; a < kNumArr; ++a) {
-                pre[a] = carry[a] + part[a * kFluxThreads + tid];
-                carry[a] += s_tot[a];
-            }
-            // per-sample flux
-            for (int r = 0; r < R; ++r) {
-                int ml = tid * R + r, m = m0 + ml;
-#pragma unroll
-                for (int a = 0; a < kNumArr; ++a) pre[a] += (long long)D[a * Mc + ml];
-                if (m >= m1) break;
-                double c0 = __ldg(cosS + m), s0 = __ldg(sinS + m);
-                double cc = c0 * cphi + s0 * sphi, ss = s0 * cphi - c0 * sphi;
-                double v_wd = 1.0 - (double)pre[0] * kInvFix;
-                double v_d = 1.0 - (double)pre[1] * kInvFix;
-                double v_s = 1.0 - (double)pre[2] * kInvFix;
-                double bm = beam_a * cc + beam_b * ss + beam_d;
-                double beam = fis + (1.0 - fis) * (bm > 0.0 ? bm : 0.0);
-                double dn = (double)pre[3] + (double)pre[4] * cc + (double)pre[5] * ss + (double)pre[6] * (cc * cc) +
-                            (double)pre[7] * (cc * ss);
-                double fwd = f_wd * v_wd, fd = f_d * v_d, fs = f_s * beam * v_s, frs = f_rs * dn;
-                if (A.mode == 0) {
-                    Fs[ml] = fwd + fd + fs + frs;
-                } else {
-                    Fs[ml] = fwd;
-                    Fs[Mc + ml] = fd;
-                    Fs[2 * Mc + ml] = fs;
-                    Fs[3 * Mc + ml] = frs;
-                }
-            }
-            __syncthreads();
-            // exposure quadrature: every point touching this chunk collects its samples in it
-            const int jlo = chunk_j[2 * c], jhi = chunk_j[2 * c + 1];
-            for (int j = jlo + tid; j <= jhi; j += kFluxThreads) {
-                double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                bool any = false;
-                for (int k = 0; k < K; ++k) {
-                    int p = __ldg(pos + j * K + k);
-                    if (p >= m0 && p < m1) {
-                        any = true;
-                        double qw = G.quad_w[k];
-                        acc[0] += qw * Fs[p - m0];
-                        if (A.mode) {
-                            acc[1] += qw * Fs[Mc + p - m0];
-                            acc[2] += qw * Fs[2 * Mc + p - m0];
-                            acc[3] += qw * Fs[3 * Mc + p - m0];
-                        }
-                    }
-                }
-                if (any) {
-                    model[j] += acc[0];
-                    if (A.mode) {
-                        model[n_ph + j] += acc[1];
-                        model[2 * n_ph + j] += acc[2];
-                        model[3 * n_ph + j] += acc[3];
-                    }
-                }
-            }
-            __syncthreads();
-        }
-
-        // ---- residuals / output ----
+    const long long job = blockIdx.x;
+    const int c = blockIdx.y;
+    const long long w = job / A.L.n_ecl;
+    const int egather = (int)(job - w * A.L.n_ecl);
+    const int e = A.mode ? 0 : egather;
+    const long long ch0 = A.smp.chunk_off[e];
+    const int n_chunks = (int)(A.smp.chunk_off[e + 1] - ch0);
+    if (c >= n_chunks) return;
+    const int4 ch = __ldg(A.smp.chunks + ch0 + c);  // first point, one past last point, first sample, last sample
+    const int j0 = ch.x, j1 = ch.y, m0 = ch.z, m1 = ch.w + 1;
+    const long long lc0 = A.smp.lc_off[e];
+    const int n_ph = (int)(A.smp.lc_off[e + 1] - lc0);
+    const int K = G.n_quad;
+    const WalkerScal& W = A.ws[w];
+    const JobScal& J = A.js[job];
+    if (!job_live(A, W, J)) {
+        const bool skipped = J.status == 4 || J.status == 0;
         if (A.mode == 0) {
-            double chi = 0.0;
-            for (int j = tid; j < n_ph; j += kFluxThreads) {
-                double r = (__ldg(A.smp.y + lc0 + j) - model[j]) / __ldg(A.smp.ye + lc0 + j);
-                chi += r * r;
-            }
-            chi = block_sum(chi, red);
-            if (tid == 0) A.chisq[job] = isnan(chi) ? INFINITY : chi;  // NaN model -> +inf (CVModel.py:163-171)
+            if (tid == 0) A.chi_part[job * A.max_chunks + c] = skipped ? NAN : INFINITY;
         } else {
-            for (int j = tid; j < n_ph; j += kFluxThreads) {
-                double fwd = model[j], fd = model[n_ph + j], fs = model[2 * n_ph + j], frs = model[3 * n_ph + j];
-                A.flux_tot[job * n_ph + j] = fwd + fd + fs + frs;
-                if (A.flux_comp) {
-                    A.flux_comp[((long long)0 * A.njobs + job) * n_ph + j] = fwd;
-                    A.flux_comp[((long long)1 * A.njobs + job) * n_ph + j] = fd;
-                    A.flux_comp[((long long)2 * A.njobs + job) * n_ph + j] = fs;
-                    A.flux_comp[((long long)3 * A.njobs + job) * n_ph + j] = frs;
-                }
+            for (int j = j0 + tid; j < j1; j += kFluxThreads) {
+                const int jo = __ldg(A.smp.pt_index + lc0 + j);
+                A.flux_tot[job * n_ph + jo] = NAN;
+                if (A.flux_comp)
+                    for (int cidx = 0; cidx < 4; ++cidx) A.flux_comp[((long long)cidx * A.njobs + job) * n_ph + jo] = NAN;
             }
         }
+        return;
+    }
+    const JobConst C = A.jc[job];
+    const long long* wq_wd = A.wq + job * (G.n_wd_rings + G.n_disc_r + G.n_bs);
+    const long long* wq_disc = wq_wd + G.n_wd_rings;
+    const long long* wq_bs = wq_disc + G.n_disc_r;
+    const EventRec* ivp = A.ivp + job * A.ni_total;
+    const double ud = G.donor_ulimb;
+
+    for (int i = tid; i < kNumArr * Mc; i += kFluxThreads) D[i] = 0ull;
+    __syncthreads();
+
+    // ---- events: stream the job's interval records ----
+    long long base[kNumArr];
+#pragma unroll
+    for (int a = 0; a < kNumArr; ++a) base[a] = 0;
+    const int n_tile_iv = G.n_wd + G.n_disc + G.n_bs;
+    for (int i = tid; i < n_tile_iv; i += kFluxThreads) {
+        const EventRec rec = ivp[i];
+        if (rec_irrelevant(rec, m0, m1)) continue;
+        int arr;
+        long long wq;
+        if (i < G.n_wd) {
+            int t = i >> 1;
+            int k = (int)sqrt(0.5 * (double)t);
+            while (2 * k * k > t) --k;
+            while (2 * (k + 1) * (k + 1) <= t) ++k;
+            wq = __ldg(wq_wd + k);
+            arr = 0;
+        } else if (i < G.n_wd + G.n_disc) {
+            wq = __ldg(wq_disc + ((i - G.n_wd) >> 1) / (G.n_disc_th / 2));
+            arr = 1;
+        } else {
+            wq = __ldg(wq_bs + (i - G.n_wd - G.n_disc));
+            arr = 2;
+        }
+        long long b0 = 0;
+        unsigned long long* Da = D + arr * Mc;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) put_event(Da, &b0, dec_pos(k < 3 ? rec.x : rec.y, k % 3), m0, m1, (k & 1) ? -wq : wq);
+        base[0] += arr == 0 ? b0 : 0;
+        base[1] += arr == 1 ? b0 : 0;
+        base[2] += arr == 2 ? b0 : 0;
+    }
+    if (!(A.flags & LFB_FLAG_SKIP_DONOR)) {
+        const double4* don = A.don + w * G.n_donor_q;
+        const EventRec* dnp = ivp + n_tile_iv;
+        for (int i = tid; i < 4 * G.n_donor_q; i += kFluxThreads) {
+            const EventRec rec = dnp[i];
+            if (rec_irrelevant(rec, m0, m1)) continue;
+            const double4 q = don[i >> 2];
+            long long mo[5];
+            donor_moments(q.w * C.don_sc, ud, W.si * q.x, (i & 1) ? W.si * q.y : -W.si * q.y,
+                          (i & 2) ? -W.ci * q.z : W.ci * q.z, mo);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
+                if (p >= m1) break;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) put_event(D + (3 + j) * Mc, &base[3 + j], p, m0, m1, (k & 1) ? -mo[j] : mo[j]);
+            }
+        }
+    }
+    // start values of the running sums: exact integer reduction over the CTA
+#pragma unroll
+    for (int a = 0; a < kNumArr; ++a) {
+        long long v = base[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) wtot[a][wid] = v;
+    }
+    __syncthreads();  // also: all events are in D
+
+    // ---- block scan: thread t owns samples m0 + t*R .. +R-1; warp a scans the partials of array a ----
+    const int R = Mc / kFluxThreads;
+#pragma unroll
+    for (int a = 0; a < kNumArr; ++a) {
+        long long v = 0;
+        for (int r = 0; r < R; ++r) v += (long long)D[a * Mc + tid * R + r];
+        part[a * kFluxThreads + tid] = v;
+    }
+    __syncthreads();
+    for (int a = wid; a < kNumArr; a += NW) {
+        long long* pa = part + a * kFluxThreads + lane * NW;
+        long long loc[NW], t = 0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) { loc[j] = t; t += pa[j]; }
+        long long inc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        long long exc = inc - t;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) pa[j] = exc + loc[j];
+    }
+    __syncthreads();
+    long long pre[kNumArr];
+#pragma unroll
+    for (int a = 0; a < kNumArr; ++a) {
+        long long v = part[a * kFluxThreads + tid];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) v += wtot[a][i];
+        pre[a] = v;
+    }
+    // ---- per-sample flux ----
+    const double* cosS = A.smp.cosS + lc0 * K;
+    const double* sinS = A.smp.sinS + lc0 * K;
+    for (int r = 0; r < R; ++r) {
+        const int ml = tid * R + r, m = m0 + ml;
+#pragma unroll
+        for (int a = 0; a < kNumArr; ++a) pre[a] += (long long)D[a * Mc + ml];
+        if (m >= m1) break;
+        const double c0 = __ldg(cosS + m), s0 = __ldg(sinS + m);
+        const double cc = c0 * C.cphi + s0 * C.sphi, ss = s0 * C.cphi - c0 * C.sphi;
+        const double v_wd = 1.0 - (double)pre[0] * kInvFix;
+        const double v_d = 1.0 - (double)pre[1] * kInvFix;
+        const double v_s = 1.0 - (double)pre[2] * kInvFix;
+        const double bm = C.beam_a * cc + C.beam_b * ss + C.beam_d;
+        const double beam = C.fis + (1.0 - C.fis) * (bm > 0.0 ? bm : 0.0);
+        const double dn = (double)pre[3] + (double)pre[4] * cc + (double)pre[5] * ss + (double)pre[6] * (cc * cc) +
+                          (double)pre[7] * (cc * ss);
+        const double fwd = C.f_wd * v_wd, fd = C.f_d * v_d, fs = C.f_s * beam * v_s, frs = C.f_rs * dn;
+        if (A.mode == 0) {
+            Fs[ml] = fwd + fd + fs + frs;
+        } else {
+            Fs[ml] = fwd;
+            Fs[Mc + ml] = fd;
+            Fs[2 * Mc + ml] = fs;
+            Fs[3 * Mc + ml] = frs;
+        }
+    }
+    __syncthreads();
+
+    // ---- exposure quadrature (Simpson over phase +- width), residuals / output ----
+    const int* pos = A.smp.pos + lc0 * K;
+    double chi = 0.0;
+    for (int j = j0 + tid; j < j1; j += kFluxThreads) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < K; ++k) {
+            const int p = __ldg(pos + j * K + k) - m0;
+            const double qw = G.quad_w[k];
+            acc[0] += qw * Fs[p];
+            if (A.mode) {
+                acc[1] += qw * Fs[Mc + p];
+                acc[2] += qw * Fs[2 * Mc + p];
+                acc[3] += qw * Fs[3 * Mc + p];
+            }
+        }
+        if (A.mode == 0) {
+            const double r = (__ldg(A.smp.y + lc0 + j) - acc[0]) / __ldg(A.smp.ye + lc0 + j);
+            chi += r * r;
+        } else {
+            const int jo = __ldg(A.smp.pt_index + lc0 + j);
+            A.flux_tot[job * n_ph + jo] = acc[0] + acc[1] + acc[2] + acc[3];
+            if (A.flux_comp)
+                for (int cidx = 0; cidx < 4; ++cidx)
+                    A.flux_comp[((long long)cidx * A.njobs + job) * n_ph + jo] = acc[cidx];
+        }
+    }
+    if (A.mode == 0) {
+        chi = block_sum<kFluxThreads>(chi, red);
+        if (tid == 0) A.chi_part[job * A.max_chunks + c] = chi;
     }
 }
 
 // ---------------------------------------------------------------- finish_kernel
-__global__ void finish_kernel(int what, int n_ecl, long long n, const WalkerScal* __restrict__ ws,
-                              const double* __restrict__ chisq, double* __restrict__ out)
+// chi^2 of every job from its chunks (fixed order: deterministic), then
+// Node.ln_prob = ln_prior + sum of -chi^2/2 with the -inf rules (model.py:476-498)
+__global__ void finish_kernel(int what, int n_ecl, long long n, int max_chunks, const long long* __restrict__ chunk_off,
+                              const WalkerScal* __restrict__ ws, const double* __restrict__ chi_part,
+                              double* __restrict__ chisq, double* __restrict__ out)
 {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n) return;
     double lnp = ws[w].lnprior;
-    double v;
-    if (what == LFB_LN_PRIOR) {
-        v = lnp;
-    } else {
-        double like = 0.0;
-        if (what == LFB_LN_LIKE || lnp > -INFINITY)
-            for (int e = 0; e < n_ecl; ++e) like += -0.5 * chisq[w * n_ecl + e];
-        v = what == LFB_LN_LIKE ? like : (lnp > -INFINITY ? lnp + like : -INFINITY);
+    double like = 0.0;
+    if (what != LFB_LN_PRIOR) {
+        for (int e = 0; e < n_ecl; ++e) {
+            const int nc = (int)(chunk_off[e + 1] - chunk_off[e]);
+            double chi = 0.0;
+            for (int c = 0; c < nc; ++c) chi += chi_part[(w * n_ecl + e) * max_chunks + c];
+            // NaN marks "not evaluated" (prior veto); a NaN model is +inf (CVModel.py:163-171)
+            const bool skipped = what == LFB_LN_PROB && !(lnp > -INFINITY);
+            if (isnan(chi) && !skipped) chi = INFINITY;
+            if (chisq) chisq[w * n_ecl + e] = skipped ? NAN : chi;
+            like += -0.5 * chi;
+        }
     }
+    if (!out) return;
+    double v;
+    if (what == LFB_LN_PRIOR) v = lnp;
+    else if (what == LFB_LN_LIKE) v = like;
+    else v = lnp > -INFINITY ? lnp + like : -INFINITY;
     if (isnan(v)) v = -INFINITY;  // never NaN towards the sampler (model.py:489-493)
     out[w] = v;
 }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -43,12 +44,13 @@ struct DevBuf {
 
 // Sorted exposure samples of a set of light curves (device copies)
 struct SampleSet {
-    DevBuf lc_off, y, ye, S, cosS, sinS, pos, chunk_off, chunk_j;
+    DevBuf lc_off, y, ye, S, cosS, sinS, bins, pos, pt_index, chunk_off, chunks;
+    int max_chunks = 1;
     int max_nph = 0;
     long long total = 0;
     void release()
     {
-        DevBuf* b[] = {&lc_off, &y, &ye, &S, &cosS, &sinS, &pos, &chunk_off, &chunk_j};
+        DevBuf* b[] = {&lc_off, &y, &ye, &S, &cosS, &sinS, &bins, &pos, &pt_index, &chunk_off, &chunks};
         for (DevBuf* x : b) x->release();
     }
     DevSamples view()
@@ -60,9 +62,11 @@ struct SampleSet {
         v.S = S.as<double>();
         v.cosS = cosS.as<double>();
         v.sinS = sinS.as<double>();
+        v.bins = bins.as<int>();
         v.pos = pos.as<int>();
+        v.pt_index = pt_index.as<int>();
         v.chunk_off = chunk_off.as<long long>();
-        v.chunk_j = chunk_j.as<int>();
+        v.chunks = chunks.as<int4>();
         return v;
     }
 };
@@ -92,7 +96,7 @@ struct lfb_handle {
     // calc_flux scratch
     DevBuf cf_gather, cf_pars, cf_tot, cf_comp;
     // work
-    DevBuf theta, out, chisq, ws, js, wd_io, don, disc_io, bs_io, bs_b, model_scratch;
+    DevBuf theta, out, chisq, ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, ivp, chi_part;
     DevBuf h_in, h_out, h_chisq;
     lfb_handle() { h_in.pinned_host = h_out.pinned_host = h_chisq.pinned_host = true; }
 };
@@ -137,9 +141,10 @@ static int donor_ring_count(int nth, int k)
     return (int)fmax(1.0, floor(0.5 * nth * sin(th) + 0.5));
 }
 
-// Merge the K exposure samples of every point of every light curve, wrap them to
-// [-0.5, 0.5], sort per eclipse, and record where each (point, node) landed.  Done once
-// per set_lightcurves / per calc_flux phase grid; shared by all walkers.
+// Light-curve preprocessing, done once per set_lightcurves / per calc_flux phase grid and shared
+// by all walkers: order the points in (wrapped) phase, merge their K exposure samples, wrap to
+// [-0.5, 0.5], sort, record where each (point, node) landed, build the bin table of the sorted
+// axis, and cut the points into chunks whose samples span at most Mc consecutive sorted samples.
 static int build_samples(lfb_handle* h, SampleSet& ss, int n_ecl, const long long* off, const double* phase,
                          const double* width, const double* y, const double* ye)
 {
@@ -147,23 +152,42 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int n_ecl, const long lon
     const int K = G.n_quad, Mc = h->Mc;
     const long long total = off[n_ecl];
     std::vector<double> S((size_t)total * K), cS((size_t)total * K), sS((size_t)total * K);
-    std::vector<int> pos((size_t)total * K);
+    std::vector<double> ys((size_t)total), yes((size_t)total);
+    std::vector<int> pos((size_t)total * K), bins((size_t)total * K + n_ecl, 0), pt_index((size_t)total);
     std::vector<long long> chunk_off(n_ecl + 1, 0);
-    std::vector<int> chunk_j;
-    int max_nph = 0;
-    std::vector<int> order;
-    std::vector<double> raw;
+    std::vector<int4> chunks;
+    int max_nph = 0, max_chunks = 1;
+    std::vector<int> order, pt;
+    std::vector<double> raw, wph;
     for (int e = 0; e < n_ecl; ++e) {
         const long long o = off[e];
         const int n_ph = (int)(off[e + 1] - o), M = n_ph * K;
         max_nph = std::max(max_nph, n_ph);
+        if (M > kMaxSamples) {
+            h->err = "set_lightcurves: more than 2^21 exposure samples in one light curve";
+            return LFB_EINVAL;
+        }
+        for (int j = 0; j < n_ph; ++j)
+            if (width && !(fabs(width[o + j]) < 0.25)) {
+                h->err = "set_lightcurves: exposure half-width must be below a quarter of the orbit";
+                return LFB_EINVAL;
+            }
+        // points in wrapped-phase order
+        wph.resize(n_ph);
+        pt.resize(n_ph);
+        for (int j = 0; j < n_ph; ++j) wph[j] = phase[o + j] - rint(phase[o + j]);
+        std::iota(pt.begin(), pt.end(), 0);
+        std::stable_sort(pt.begin(), pt.end(), [&](int a, int b) { return wph[a] < wph[b]; });
         raw.resize(M);
         order.resize(M);
-        for (int j = 0; j < n_ph; ++j)
-            for (int k = 0; k < K; ++k) {
-                double s = phase[o + j] + G.quad_off[k] * (width ? width[o + j] : 0.0);
-                raw[j * K + k] = s - rint(s);
-            }
+        for (int jj = 0; jj < n_ph; ++jj) {
+            const int j = pt[jj];
+            pt_index[o + jj] = j;
+            ys[o + jj] = y ? y[o + j] : 0.0;
+            yes[o + jj] = ye ? ye[o + j] : 1.0;
+            // the point is wrapped as a whole: its samples stay together on the axis
+            for (int k = 0; k < K; ++k) raw[jj * K + k] = wph[j] + G.quad_off[k] * (width ? width[o + j] : 0.0);
+        }
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return raw[a] < raw[b]; });
         for (int r = 0; r < M; ++r) {
@@ -173,44 +197,72 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int n_ecl, const long lon
             sS[o * K + r] = sin(kTwoPi * raw[src]);
             pos[o * K + src] = r;
         }
-        const int n_chunks = (M + Mc - 1) / Mc;
-        chunk_off[e + 1] = chunk_off[e] + n_chunks;
-        for (int c = 0; c < n_chunks; ++c) {
-            int jlo = n_ph, jhi = -1;
-            for (int r = c * Mc; r < std::min(M, (c + 1) * Mc); ++r) {
-                int j = order[r] / K;
-                jlo = std::min(jlo, j);
-                jhi = std::max(jhi, j);
+        // bin table: first sample at or after the start of each of M equal phase bins
+        if (M > 0) {
+            int* bt = bins.data() + o * K + e;
+            const double s0 = S[o * K], s1 = S[o * K + M - 1];
+            const double inv_binw = s1 > s0 ? (double)M / (s1 - s0) : 0.0;
+            int r = 0;
+            for (int b = 0; b <= M; ++b) {
+                while (r < M) {
+                    double gf = (S[o * K + r] - s0) * inv_binw;
+                    int br = gf <= 0.0 ? 0 : (gf >= (double)(M - 1) ? M - 1 : (int)gf);
+                    if (br >= b) break;
+                    ++r;
+                }
+                bt[b] = r;
             }
-            chunk_j.push_back(jlo);
-            chunk_j.push_back(jhi);
         }
+        // chunks of consecutive points: all their samples inside [pmin, pmax], pmax - pmin < Mc
+        int nch = 0;
+        for (int j0 = 0; j0 < n_ph;) {
+            int pmin = M, pmax = -1, j1 = j0;
+            while (j1 < n_ph) {
+                int lo = pmin, hi = pmax;
+                for (int k = 0; k < K; ++k) {
+                    lo = std::min(lo, pos[o * K + j1 * K + k]);
+                    hi = std::max(hi, pos[o * K + j1 * K + k]);
+                }
+                if (hi - lo + 1 > Mc) break;
+                pmin = lo;
+                pmax = hi;
+                ++j1;
+            }
+            if (j1 == j0) {
+                h->err = "set_lightcurves: one exposure spans more sorted samples than a chunk holds "
+                         "(width far larger than the sampling); not supported";
+                return LFB_EINVAL;
+            }
+            chunks.push_back(make_int4(j0, j1, pmin, pmax));
+            ++nch;
+            j0 = j1;
+        }
+        chunk_off[e + 1] = chunk_off[e] + nch;
+        max_chunks = std::max(max_chunks, nch);
     }
-    if (chunk_j.empty()) chunk_j.assign(2, 0);
-    std::vector<double> zeros, ones;
-    if (!y) zeros.assign((size_t)total, 0.0);
-    if (!ye) ones.assign((size_t)total, 1.0);
+    if (chunks.empty()) chunks.push_back(make_int4(0, 0, 0, -1));
     int rc;
     if ((rc = upload(h, ss.lc_off, off, sizeof(long long) * (size_t)(n_ecl + 1)))) return rc;
-    if ((rc = upload(h, ss.y, y ? y : zeros.data(), sizeof(double) * (size_t)total))) return rc;
-    if ((rc = upload(h, ss.ye, ye ? ye : ones.data(), sizeof(double) * (size_t)total))) return rc;
+    if ((rc = upload(h, ss.y, ys.data(), sizeof(double) * (size_t)total))) return rc;
+    if ((rc = upload(h, ss.ye, yes.data(), sizeof(double) * (size_t)total))) return rc;
     if ((rc = upload(h, ss.S, S.data(), sizeof(double) * S.size()))) return rc;
     if ((rc = upload(h, ss.cosS, cS.data(), sizeof(double) * cS.size()))) return rc;
     if ((rc = upload(h, ss.sinS, sS.data(), sizeof(double) * sS.size()))) return rc;
+    if ((rc = upload(h, ss.bins, bins.data(), sizeof(int) * bins.size()))) return rc;
     if ((rc = upload(h, ss.pos, pos.data(), sizeof(int) * pos.size()))) return rc;
+    if ((rc = upload(h, ss.pt_index, pt_index.data(), sizeof(int) * pt_index.size()))) return rc;
     if ((rc = upload(h, ss.chunk_off, chunk_off.data(), sizeof(long long) * chunk_off.size()))) return rc;
-    if ((rc = upload(h, ss.chunk_j, chunk_j.data(), sizeof(int) * chunk_j.size()))) return rc;
+    if ((rc = upload(h, ss.chunks, chunks.data(), sizeof(int4) * chunks.size()))) return rc;
     CK(cudaStreamSynchronize(h->stream));  // the host vectors die here
     ss.max_nph = max_nph;
+    ss.max_chunks = max_chunks;
     ss.total = total;
     return LFB_OK;
 }
 
-static size_t flux_smem_fixed(const GridCfg& G, int Mc, int nF)
+static size_t flux_smem_bytes(int Mc, int nF)
 {
-    size_t NI = (size_t)G.n_wd + G.n_disc + G.n_bs, NDQ = (size_t)G.n_donor_q;
-    return 16 * (NI + 4 * NDQ) + 32 * NDQ + 8 * ((size_t)kNumArr * Mc + (size_t)kNumArr * kFluxThreads + (size_t)nF * Mc +
-                                                  G.n_bs + 2 * (size_t)(G.n_disc_r + G.n_wd_rings));
+    return 8 * ((size_t)kNumArr * Mc + (size_t)kNumArr * kFluxThreads + (size_t)nF * Mc);
 }
 
 // One pass of the pipeline over walkers [0, n) (device pointers, one batch).
@@ -279,7 +331,8 @@ static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleS
         A.flags = flags;
         A.mode = mode;
         A.Mc = h->Mc;
-        A.max_nph = ss.max_nph;
+        A.max_chunks = ss.max_chunks;
+        A.ni_total = G.n_wd + G.n_disc + G.n_bs + 4 * G.n_donor_q;
         A.njobs = njobs;
         A.theta = d_theta;
         A.ws = E.ws;
@@ -289,36 +342,32 @@ static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleS
         A.disc_io = E.disc_io;
         A.bs_io = E.bs_io;
         A.bs_b = E.bs_b;
-        A.chisq = d_chi;
+        const size_t nwq = (size_t)G.n_wd_rings + G.n_disc_r + G.n_bs;
+        CK(h->jc.reserve(sizeof(JobConst) * (size_t)njobs));
+        CK(h->wq.reserve(sizeof(long long) * (size_t)njobs * nwq));
+        CK(h->ivp.reserve(sizeof(EventRec) * (size_t)njobs * A.ni_total));
+        CK(h->chi_part.reserve(sizeof(double) * (size_t)njobs * ss.max_chunks));
+        A.jc = h->jc.as<JobConst>();
+        A.wq = h->wq.as<long long>();
+        A.ivp = h->ivp.as<EventRec>();
+        A.chi_part = h->chi_part.as<double>();
         A.flux_tot = d_tot;
         A.flux_comp = d_comp;
-        const int nF = mode ? 4 : 1;
-        size_t fixed = flux_smem_fixed(G, h->Mc, nF);
-        size_t model_bytes = sizeof(double) * (size_t)nF * ss.max_nph;
-        size_t budget = (size_t)h->max_smem - 2048;
-        if (fixed > budget) return fail(h, LFB_EINVAL, "surface grid too dense for the flux kernel's shared memory");
-        // two CTAs per SM if possible: per-point partial sums go through L2 when they do not fit
-        const size_t two_cta = (size_t)112 * 1024;
-        if (fixed + model_bytes <= two_cta) A.model_in_smem = 1;
-        else if (fixed <= two_cta) A.model_in_smem = 0;
-        else A.model_in_smem = fixed + model_bytes <= budget ? 1 : 0;
-        size_t smem = fixed + (A.model_in_smem ? model_bytes : 0);
-        int grid = (int)std::min<long long>(njobs, (long long)h->sm_count * 16);
-        if (grid < 1) grid = 1;
-        A.model_scratch = nullptr;
-        if (!A.model_in_smem) {
-            CK(h->model_scratch.reserve(sizeof(double) * (size_t)grid * nF * ss.max_nph));
-            A.model_scratch = h->model_scratch.as<double>();
-        }
+        prep_kernel<<<(unsigned)((njobs + 3) / 4), 128, 0, st>>>(A);
+        const long long per_job = ((G.n_wd_half + G.n_disc_half + G.n_bs + G.n_donor_q) + 31) & ~31;
+        positions_kernel<<<(unsigned)((njobs * per_job + 127) / 128), 128, 0, st>>>(A);
+        const size_t smem = flux_smem_bytes(h->Mc, mode ? 4 : 1);
         CK(cudaFuncSetAttribute(flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        flux_kernel<<<grid, kFluxThreads, smem, st>>>(A);
-        h->launches++;
+        flux_kernel<<<dim3((unsigned)njobs, (unsigned)ss.max_chunks), kFluxThreads, smem, st>>>(A);
+        h->launches += 3;
     } else if (record) {
         CK(cudaEventRecord(h->ev[ST_FLUX], st));
     }
     if (record) CK(cudaEventRecord(h->ev[ST_FINISH], st));
-    if (d_out) {
-        finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(what, L.n_ecl, n, h->ws.as<WalkerScal>(), d_chi, d_out);
+    if (d_out || d_chi) {
+        finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(what, L.n_ecl, n, ss.max_chunks,
+                                                                  ss.chunk_off.as<long long>(), h->ws.as<WalkerScal>(),
+                                                                  h->chi_part.as<double>(), d_chi, d_out);
         h->launches++;
     }
     if (record) {
@@ -408,13 +457,11 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
             G.quad_w[k] = cw / (3.0 * nint);
         }
     }
-    // samples per chunk of the flux kernel: as large as leaves room for two CTAs per SM
-    h->Mc = 512;
-    while (h->Mc > 256 && flux_smem_fixed(G, h->Mc, 1) > (size_t)96 * 1024) h->Mc -= 256;
-    if (flux_smem_fixed(G, h->Mc, 4) > (size_t)h->max_smem - 2048) {
-        g_create_error = "surface grid too dense for shared memory";
-        delete h;
-        return LFB_EINVAL;
+    // capacity of a flux-kernel chunk in samples (multiple of kFluxThreads); LFB_MC overrides for tuning
+    h->Mc = 2 * kFluxThreads;
+    if (const char* env = getenv("LFB_MC")) {
+        int v = atoi(env);
+        if (v >= kFluxThreads && v % kFluxThreads == 0 && flux_smem_bytes(v, 4) <= (size_t)h->max_smem - 2048) h->Mc = v;
     }
     *out = h;
     return LFB_OK;
@@ -428,7 +475,7 @@ void lfb_destroy(lfb_handle* h)
     DevBuf* bufs[] = {&h->gather, &h->consts, &h->psrc, &h->ptype, &h->pisvar, &h->pp1, &h->pp2, &h->pnorm,
                       &h->donor_off, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
                       &h->chisq, &h->ws, &h->js, &h->wd_io, &h->don, &h->disc_io, &h->bs_io, &h->bs_b,
-                      &h->model_scratch, &h->h_in, &h->h_out, &h->h_chisq};
+                      &h->jc, &h->wq, &h->ivp, &h->chi_part, &h->h_in, &h->h_out, &h->h_chisq};
     for (DevBuf* b : bufs) b->release();
     h->lc.release();
     h->cf_lc.release();
@@ -593,6 +640,7 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
         d_chi = h->chisq.as<double>();
     }
     if (what == LFB_LN_PRIOR && chisq_out) CK(cudaMemsetAsync(d_chi, 0xff, sizeof(double) * (size_t)njobs, st));
+    if (what == LFB_LN_PRIOR) CK(h->chi_part.reserve(8));
     DevLayout L = make_layout(h);
     // bounded batches of walkers keep the element buffers small (16 B x ~900 elements per job)
     long long per = std::max<long long>(1, h->max_jobs_per_batch / h->n_ecl);
