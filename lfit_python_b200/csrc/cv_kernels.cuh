@@ -682,13 +682,13 @@ __device__ __forceinline__ void put_event(unsigned long long* Darr, long long* b
 // streamed once from L2: events inside the range go to shared-memory event arrays (exact
 // fixed-point atomics), events before it into the start values; a block scan gives the
 // eclipsed / facing sums at every sample, then component mix, exposure quadrature, residuals.
-__global__ void __launch_bounds__(kFluxThreads) flux_kernel(const __grid_constant__ FluxArgs A)
+template <int Mc>
+__global__ void __launch_bounds__(kFluxThreads, Mc <= 768 ? 3 : 2) flux_kernel(const __grid_constant__ FluxArgs A)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     const GridCfg& G = A.G;
     constexpr int NW = kFluxThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int Mc = A.Mc;
     unsigned long long* D = (unsigned long long*)smraw;     // [kNumArr][Mc] events
     long long* part = (long long*)(D + kNumArr * Mc);       // [kNumArr][kFluxThreads] scan partials
     double* Fs = (double*)(part + kNumArr * kFluxThreads);  // [nF][Mc] flux per sample
@@ -739,32 +739,44 @@ __global__ void __launch_bounds__(kFluxThreads) flux_kernel(const __grid_constan
 #pragma unroll
     for (int a = 0; a < kNumArr; ++a) base[a] = 0;
     const int n_tile_iv = G.n_wd + G.n_disc + G.n_bs;
-    for (int i = tid; i < n_tile_iv; i += kFluxThreads) {
-        const EventRec rec = ivp[i];
-        if (rec_irrelevant(rec, m0, m1)) continue;
-        int arr;
-        long long wq;
-        if (i < G.n_wd) {
-            int t = i >> 1;
-            int k = (int)sqrt(0.5 * (double)t);
-            while (2 * k * k > t) --k;
-            while (2 * (k + 1) * (k + 1) <= t) ++k;
-            wq = __ldg(wq_wd + k);
-            arr = 0;
-        } else if (i < G.n_wd + G.n_disc) {
-            wq = __ldg(wq_disc + ((i - G.n_wd) >> 1) / (G.n_disc_th / 2));
-            arr = 1;
-        } else {
-            wq = __ldg(wq_bs + (i - G.n_wd - G.n_disc));
-            arr = 2;
-        }
-        long long b0 = 0;
-        unsigned long long* Da = D + arr * Mc;
+    // records are fetched four at a time so that their L2 latencies overlap
+    for (int i0 = tid; i0 < n_tile_iv; i0 += 4 * kFluxThreads) {
+        EventRec recs[4];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) put_event(Da, &b0, dec_pos(k < 3 ? rec.x : rec.y, k % 3), m0, m1, (k & 1) ? -wq : wq);
-        base[0] += arr == 0 ? b0 : 0;
-        base[1] += arr == 1 ? b0 : 0;
-        base[2] += arr == 2 ? b0 : 0;
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kFluxThreads;
+            recs[u] = i < n_tile_iv ? ivp[i] : no_events();
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kFluxThreads;
+            const EventRec rec = recs[u];
+            if (rec_irrelevant(rec, m0, m1)) continue;
+            int arr;
+            long long wq;
+            if (i < G.n_wd) {
+                int t = i >> 1;
+                int k = (int)sqrt(0.5 * (double)t);
+                while (2 * k * k > t) --k;
+                while (2 * (k + 1) * (k + 1) <= t) ++k;
+                wq = __ldg(wq_wd + k);
+                arr = 0;
+            } else if (i < G.n_wd + G.n_disc) {
+                wq = __ldg(wq_disc + ((i - G.n_wd) >> 1) / (G.n_disc_th / 2));
+                arr = 1;
+            } else {
+                wq = __ldg(wq_bs + (i - G.n_wd - G.n_disc));
+                arr = 2;
+            }
+            long long b0 = 0;
+            unsigned long long* Da = D + arr * Mc;
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                put_event(Da, &b0, dec_pos(k < 3 ? rec.x : rec.y, k % 3), m0, m1, (k & 1) ? -wq : wq);
+            base[0] += arr == 0 ? b0 : 0;
+            base[1] += arr == 1 ? b0 : 0;
+            base[2] += arr == 2 ? b0 : 0;
+        }
     }
     if (!(A.flags & LFB_FLAG_SKIP_DONOR)) {
         const double4* don = A.don + w * G.n_donor_q;
@@ -796,10 +808,11 @@ __global__ void __launch_bounds__(kFluxThreads) flux_kernel(const __grid_constan
     __syncthreads();  // also: all events are in D
 
     // ---- block scan: thread t owns samples m0 + t*R .. +R-1; warp a scans the partials of array a ----
-    const int R = Mc / kFluxThreads;
+    constexpr int R = Mc / kFluxThreads;
 #pragma unroll
     for (int a = 0; a < kNumArr; ++a) {
         long long v = 0;
+#pragma unroll
         for (int r = 0; r < R; ++r) v += (long long)D[a * Mc + tid * R + r];
         part[a * kFluxThreads + tid] = v;
     }
@@ -831,6 +844,7 @@ __global__ void __launch_bounds__(kFluxThreads) flux_kernel(const __grid_constan
     // ---- per-sample flux ----
     const double* cosS = A.smp.cosS + lc0 * K;
     const double* sinS = A.smp.sinS + lc0 * K;
+#pragma unroll
     for (int r = 0; r < R; ++r) {
         const int ml = tid * R + r, m = m0 + ml;
 #pragma unroll

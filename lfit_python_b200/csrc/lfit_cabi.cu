@@ -357,8 +357,21 @@ static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleS
         const long long per_job = ((G.n_wd_half + G.n_disc_half + G.n_bs + G.n_donor_q) + 31) & ~31;
         positions_kernel<<<(unsigned)((njobs * per_job + 127) / 128), 128, 0, st>>>(A);
         const size_t smem = flux_smem_bytes(h->Mc, mode ? 4 : 1);
-        CK(cudaFuncSetAttribute(flux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        flux_kernel<<<dim3((unsigned)njobs, (unsigned)ss.max_chunks), kFluxThreads, smem, st>>>(A);
+        const dim3 fgrid((unsigned)njobs, (unsigned)ss.max_chunks);
+#define LFB_LAUNCH_FLUX(MC)                                                                                     \
+    do {                                                                                                        \
+        CK(cudaFuncSetAttribute(flux_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        flux_kernel<MC><<<fgrid, kFluxThreads, smem, st>>>(A);                                                  \
+    } while (0)
+        switch (h->Mc) {
+        case 256: LFB_LAUNCH_FLUX(256); break;
+        case 512: LFB_LAUNCH_FLUX(512); break;
+        case 768: LFB_LAUNCH_FLUX(768); break;
+        case 1024: LFB_LAUNCH_FLUX(1024); break;
+        case 2048: LFB_LAUNCH_FLUX(2048); break;
+        default: return fail(h, LFB_EINVAL, "unsupported chunk capacity");
+        }
+#undef LFB_LAUNCH_FLUX
         h->launches += 3;
     } else if (record) {
         CK(cudaEventRecord(h->ev[ST_FLUX], st));
@@ -458,10 +471,10 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
         }
     }
     // capacity of a flux-kernel chunk in samples (multiple of kFluxThreads); LFB_MC overrides for tuning
-    h->Mc = 2 * kFluxThreads;
+    h->Mc = 768;
     if (const char* env = getenv("LFB_MC")) {
         int v = atoi(env);
-        if (v >= kFluxThreads && v % kFluxThreads == 0 && flux_smem_bytes(v, 4) <= (size_t)h->max_smem - 2048) h->Mc = v;
+        if (v == 256 || v == 512 || v == 768 || v == 1024 || v == 2048) h->Mc = v;
     }
     *out = h;
     return LFB_OK;

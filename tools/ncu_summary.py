@@ -77,6 +77,8 @@ def source(rep, top):
             continue
         if hdr is None or len(r) != len(hdr):
             continue
+        if r[0] in ("", "-"):
+            continue  # per-SASS rows repeat what the per-line rows already sum
         key = (func, fname, r[0], r[1].strip())
         a = agg.setdefault(key, [0.0, 0.0])
         a[0] += _num(r[isamp])
