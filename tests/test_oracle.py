@@ -1,0 +1,252 @@
+"""The CPU oracle against first-principles known answers, an independent brute-force model,
+its own robust solver, scipy's priors and the committed golden vectors.
+
+PARITY UNPINNED: no reference output exists for this path; these tests
+pin the oracle to physics, not to lfit.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_roche_known_answers():
+    # computed independently from the definitions with scipy
+    for q, ref in [(0.05, 0.768745415943), (0.1, 0.717512587115), (0.1037, 0.714609543404),
+                   (0.2, 0.658555678954), (0.5, 0.570751571519), (1.0, 0.5)]:
+        assert abs(O.xl1(q) - ref) < 1e-11
+    for q, ref in [(0.05, 0.0510864), (0.1, 0.0632761), (0.1037, 0.0639808), (0.2, 0.0779339),
+                   (0.5, 0.1014049), (1.0, 0.1222186)]:
+        assert abs(O.findphi(q, 90.0) - ref) < 2e-7
+    assert abs(O.findphi(0.1, 86.9) - 0.0607135) < 2e-7
+    assert abs(O.findi(0.1037, 0.0392) - 81.2221) < 2e-4
+    x = O.xl1(0.1037)
+    for frac, ref in [(0.2953, (0.097888, 0.186947)), (0.5214, (0.339469, 0.153589))]:
+        got = O.bspot(0.1037, frac * x)
+        assert abs(got[0] - ref[0]) < 2e-5 and abs(got[1] - ref[1]) < 2e-5
+        assert abs(np.hypot(got[0], got[1]) - frac * x) < 1e-12  # lands on the requested radius
+    assert 0.7 * x > 0.46  # the example's prior upper edge is beyond the 3:1 resonance cut
+
+
+def test_roche_failures():
+    with pytest.raises(O.RocheError):
+        O.xl1(-0.1)
+    with pytest.raises(O.RocheError):
+        O.findi(0.1, 0.2)      # wider than the edge-on eclipse
+    with pytest.raises(O.RocheError):
+        O.bspot(0.1037, 0.01)  # inside the stream's closest approach
+
+
+def test_findi_inverts_findphi():
+    for q, incs in ((0.05, (84.0, 87.0, 89.5)), (0.15, (80.0, 85.0, 89.0)), (0.6, (72.0, 80.0, 88.0))):
+        for inc in incs:
+            dphi = O.findphi(q, inc)
+            assert abs(O.findi(q, dphi) - inc) < 1e-7
+    with pytest.raises(O.RocheError):
+        O.findphi(0.05, 78.0)  # below the grazing inclination: the white-dwarf centre is never eclipsed
+
+
+def test_stream_conserves_jacobi_integral():
+    """0.5 v^2 + Phi is conserved along the ballistic stream that leaves L1 at rest."""
+    q = 0.2
+    mu = q / (1 + q)
+    xl = O.xl1(q)
+    pot = lambda x, y: -(1 - mu) / np.hypot(x, y) - mu / np.hypot(x - 1, y) - 0.5 * ((x - mu) ** 2 + y ** 2)
+    for frac in (0.7, 0.5, 0.3):
+        x, y, vx, vy = O.bspot(q, frac * xl)
+        assert abs(0.5 * (vx * vx + vy * vy) + pot(x, y) - pot(xl, 0.0)) < 1e-6  # fixed-step integrator, start 1e-5 off L1
+
+
+def test_newton_matches_robust_solver():
+    rng = np.random.default_rng(5)
+    n_ecl = 0
+    for _ in range(400):
+        q = rng.uniform(0.03, 1.0)
+        inc = rng.uniform(62.0, 90.0)
+        r, az = rng.uniform(0.02, 0.6) * O.xl1(q), rng.uniform(0, 2 * np.pi)
+        kind = rng.integers(3)
+        p0, xi, eta = (r * np.cos(az), r * np.sin(az), 0.0), 0.0, 0.0
+        if kind == 1:
+            p0, xi, eta = (0.0, 0.0, 0.0), 0.1 * r * np.cos(az), 0.1 * r * np.sin(az)
+        elif kind == 2:
+            p0 = (p0[0], p0[1], rng.uniform(-0.02, 0.02))
+        a = O.ingress_egress(q, inc, p0, xi, eta, solver=O.SOLVER_ROBUST)
+        b = O.ingress_egress(q, inc, p0, xi, eta, solver=O.SOLVER_NEWTON)
+        assert (a is None) == (b is None)
+        if a is not None:
+            n_ecl += 1
+            assert abs(a[0] - b[0]) < 1e-12 and abs(a[1] - b[1]) < 1e-12
+    assert n_ecl > 150
+
+
+def test_mirror_symmetry_of_eclipses():
+    """(x, -y, z) is eclipsed from -egress to -ingress of (x, y, z)."""
+    for p in ((0.2, 0.1, 0.0), (-0.1, 0.25, 0.01), (0.05, 0.3, 0.0)):
+        a = O.ingress_egress(0.15, 83.0, p, solver=O.SOLVER_ROBUST)
+        b = O.ingress_egress(0.15, 83.0, (p[0], -p[1], p[2]), solver=O.SOLVER_ROBUST)
+        assert abs(a[0] + b[1]) < 1e-12 and abs(a[1] + b[0]) < 1e-12
+
+
+def _blink(q, si, ci, pts, th, nlam=1500):
+    """Independent eclipse test: sample Phi densely along each LOS inside the bounding sphere."""
+    mu = q / (1 + q)
+    xl = O.xl1(q)
+    rs = 1 - xl
+    phic = -(1 - mu) / xl - mu / (1 - xl) - 0.5 * (xl - mu) ** 2
+    e = np.array([si * np.cos(th), -si * np.sin(th), ci])
+    lam = np.linspace(0.0, 2.0, nlam)
+    out = np.zeros(len(pts), dtype=bool)
+    for k, p in enumerate(pts):
+        x = p[None, :] + lam[:, None] * e[None, :]
+        inside = np.sum((x - [1, 0, 0]) ** 2, axis=1) < rs * rs
+        if not inside.any():
+            continue
+        xi = x[inside]
+        phi = (-(1 - mu) / np.linalg.norm(xi, axis=1) - mu / np.linalg.norm(xi - [1, 0, 0], axis=1)
+               - 0.5 * ((xi[:, 0] - mu) ** 2 + xi[:, 1] ** 2))
+        out[k] = phi.min() < phic
+    return out
+
+
+def test_disc_curve_against_brute_force_visibility():
+    """PyDisc-like curve from the oracle vs. a numpy model that never computes ingress/egress."""
+    q, inc, rin, rout, dexp = 0.12, 84.0, 0.02, 0.55, 0.4
+    cfg = O.config(n_disc_r=6, n_disc_th=16, solver=O.SOLVER_ROBUST)
+    phases = np.array([-0.09, -0.06, -0.035, -0.01, 0.0, 0.02, 0.045, 0.07, 0.1])
+    pars = [0, 1.0, 0, 0, q, inc, rout, 0.3, rin, 0.03, 120, 0.2, dexp, 0.0]
+    flags = O.FLAG_INCL | O.SKIP_WD | O.SKIP_BS | O.SKIP_DONOR
+    st, got = O.calc_flux(pars, phases, None, cfg=cfg, flags=flags)
+    assert st == 0
+    xl = O.xl1(q)
+    si, ci = np.sin(np.radians(inc)), np.cos(np.radians(inc))
+    pts, w = [], []
+    for m in range(6):
+        r = rin * xl + (m + 0.5) * (rout - rin) * xl / 6
+        for j in range(16):
+            az = (j + 0.5) * 2 * np.pi / 16
+            pts.append([r * np.cos(az), r * np.sin(az), 0.0])
+            w.append(r ** (1 - dexp))
+    pts, w = np.array(pts), np.array(w)
+    ref = np.array([w[~_blink(q, si, ci, pts, 2 * np.pi * ph)].sum() / w.sum() for ph in phases])
+    assert np.allclose(got, ref, atol=1e-12)
+    assert 0.0 < got.min() < 0.9 and abs(got.max() - 1.0) < 1e-14
+
+
+def test_components_are_unit_normalised_and_add_up():
+    """Out of eclipse each component is at its 'maximum light' scale and
+    flux = wdFlux*ywd + dFlux*yd + sFlux*ys + rsFlux*yrs (testCV.py:59-65)."""
+    p = [0.05, 0.07, 0.06, 0.013, 0.1037, 0.0392, 0.45, 0.284, 0.0187, 0.043, 120.0, 0.05, 0.5, 0.001,
+         1.5, 2.0, 80.0, 5.0]
+    ph = np.linspace(-0.45, 0.45, 61)
+    st, tot, comp = O.calc_flux(p, ph, 0.002, components=True)
+    assert st == 0
+    assert np.allclose(tot, sum(comp), rtol=1e-14)
+    assert abs(comp[0].max() - p[0]) < 1e-15 and comp[0].min() == 0.0      # white dwarf: total eclipse
+    assert abs(comp[1].max() - p[1]) < 1e-15 and 0 < comp[1].min() < p[1]  # disc: partial
+    assert comp[2].max() <= p[2] * (1 + 1e-12)
+    inc = O.findi(p[4], p[5])
+    st, q_flux = O.calc_flux(p, np.array([0.25 + p[13]]), None, flags=O.SKIP_WD | O.SKIP_DISC | O.SKIP_BS)
+    assert abs(q_flux[0] - p[3]) < 1e-15  # donor flux is normalised at quadrature
+    assert 75 < inc < 90
+
+
+def test_exposure_smearing_is_simpson():
+    p = [0.05, 0.07, 0.06, 0.013, 0.1037, 0.0392, 0.45, 0.284, 0.0187, 0.043, 120.0, 0.05, 0.5, 0.0]
+    ph, w = np.array([-0.0196, 0.01, 0.05]), 0.004
+    st, smeared = O.calc_flux(p, ph, w)
+    st, a = O.calc_flux(p, ph - w, None)
+    st, b = O.calc_flux(p, ph, None)
+    st, c = O.calc_flux(p, ph + w, None)
+    assert np.allclose(smeared, (a + 4 * b + c) / 6, rtol=1e-14)
+    st, k5 = O.calc_flux(p, ph, w, cfg=O.config(n_quad=5))
+    assert not np.allclose(k5, smeared, rtol=1e-6)
+
+
+def test_invalid_models_are_nan_and_inf():
+    base = [0.05, 0.07, 0.06, 0.013, 0.1037, 0.0392, 0.45, 0.284, 0.0187, 0.043, 120.0, 0.05, 0.5, 0.0]
+    ph = np.linspace(-0.1, 0.1, 11)
+    for idx, val in [(4, -1.0), (5, 0.3), (5, -0.01), (6, 0.005), (8, 0.0), (9, -0.1), (0, np.nan)]:
+        p = list(base)
+        p[idx] = val
+        st, f = O.calc_flux(p, ph, None)
+        assert st != 0 and np.isnan(f).all()
+        assert O.chisq(p, ph, np.zeros_like(ph), np.ones_like(ph), np.ones_like(ph)) == np.inf
+
+
+def test_priors_against_scipy_and_the_reference_quirk():
+    from scipy import integrate, stats
+    for val in (0.28, 0.2845, 0.3, 0.25):
+        assert abs(O.prior_ln_prob("gauss", 0.284, 0.001, 1.0, val) - stats.norm(0.284, 0.001).logpdf(val)) < 1e-9
+    assert O.prior_ln_prob("gauss", 0.284, 0.001, 1.0, 0.284 + 0.039) == -np.inf  # 39 sigma: pdf underflows
+    assert np.isfinite(O.prior_ln_prob("gauss", 0.284, 0.001, 1.0, 0.284 + 0.038))
+    assert O.prior_ln_prob("gaussPos", 1.0, 5.0, 1.0, -0.1) == -np.inf
+    assert abs(O.prior_ln_prob("uniform", 0.03, 0.5, 1.0, 0.1) + np.log(0.47)) < 1e-14
+    assert O.prior_ln_prob("uniform", 0.03, 0.5, 1.0, 0.5) == -np.inf  # strict inequalities
+    # log_uniform: normalised by |integral of ln(1/x)| (model.py:77-79), not by ln(p2/p1)
+    norm = abs(integrate.quad(lambda x: np.log(1.0 / x), 0.001, 0.2)[0])
+    assert abs(norm - 0.513979827) < 1e-8
+    from lfit_python_b200.workloads import prior_norm
+    assert abs(prior_norm("log_uniform", 0.001, 0.2) - norm) < 1e-12
+    assert abs(O.prior_ln_prob("log_uniform", 0.001, 0.2, norm, 0.043) - np.log(1 / norm / 0.043)) < 1e-14
+    assert abs(O.prior_ln_prob("mod_jeff", 0.01, 1.0, np.log(101.0), 0.2) - np.log(1 / np.log(101.0) / 0.21)) < 1e-14
+
+
+def test_golden_vectors():
+    g = np.load(os.path.join(GOLD, "calc_flux.npz"))
+    for k in range(g["pars"].shape[0]):
+        p = g["pars"][k]
+        p = p[~np.isnan(p)]
+        st, tot, comp = O.calc_flux(p, g["phase"], g["width"], components=True)  # fast Newton solver
+        assert st == 0
+        assert np.max(np.abs(tot - g["total"][k]) / g["total"][k]) < 1e-12
+        assert np.allclose(np.asarray(comp), g["comp"][k], rtol=0, atol=1e-13)
+    r = np.load(os.path.join(GOLD, "roche.npz"))
+    assert np.allclose([O.xl1(v) for v in r["q"]], r["xl1"], rtol=1e-14)
+    assert np.allclose([O.findphi(v, 90.0) for v in r["q"]], r["maxphi"], rtol=1e-13)
+    for row in r["ingress_egress"]:
+        got = O.ingress_egress(row[0], row[1], row[2:5])
+        if np.isnan(row[5]):
+            assert got is None
+        else:
+            assert abs(got[0] - row[5]) < 1e-12 and abs(got[1] - row[6]) < 1e-12
+
+
+def test_golden_log_prob():
+    from lfit_python_b200 import workloads
+    g = np.load(os.path.join(GOLD, "log_prob.npz"))
+    wl = workloads.config(2, n_bands=2, ecl_per_band=2, n_ph=90, phase_range=(-0.15, 0.2))
+    wl.lc_y = g["lc_y"]
+    lay = O.FlatLayout(wl.ndim, wl.npars, wl.gather, wl.consts, wl.prior_src, wl.prior_type, wl.prior_p1,
+                       wl.prior_p2, wl.prior_norm, wl.prior_isvar, wl.lc_off, wl.lc_phase, wl.lc_width, wl.lc_y,
+                       wl.lc_ye)
+    for what, name in ((0, "ln_prior"), (1, "ln_like"), (2, "ln_prob")):
+        v, chi = O.log_prob(lay, g["theta"], what=what, return_chisq=True)
+        assert np.array_equal(np.isfinite(v), np.isfinite(g[name]))
+        fin = np.isfinite(v)
+        assert np.allclose(v[fin], g[name][fin], rtol=1e-11)
+        assert np.array_equal(np.isnan(chi), np.isnan(g[name + "_chisq"]))
+    assert not np.isnan(g["ln_prob"]).any() and np.isfinite(g["ln_prob"]).sum() >= 5
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/test_data/mcmc_input.dat"), reason="reference tree not mounted")
+def test_real_data_sanity_pin(tmp_path):
+    """The reference's shipped starting parameters on its shipped data (useGP switched off):
+    all six eclipses pass the validity priors and five of six reach a reduced chi-squared below
+    2.5 -- the only (weak) contact with real lfit-fitted numbers that the tree offers."""
+    from lfit_python_b200.CVModel import construct_model
+    from lfit_python_b200.flatten import FlatLayout
+    txt = open("/root/reference/test_data/mcmc_input.dat").read().replace("useGP = 1", "useGP = 0")
+    (tmp_path / "in.dat").write_text(txt)
+    os.symlink("/root/reference/test_data/lightcurves", tmp_path / "lightcurves")
+    L = FlatLayout(construct_model(str(tmp_path / "in.dat")))
+    assert L.ndim == 84 and [e.lc.n_data for e in L.eclipses] == [247, 170, 299, 228, 166, 303]
+    lay = O.FlatLayout(L.ndim, L.npars, L.gather, L.consts, L.prior_src, L.prior_type, L.prior_p1, L.prior_p2,
+                       L.prior_norm, L.prior_isvar, L.lc_off, L.lc_phase, L.lc_width, L.lc_y, L.lc_ye)
+    assert np.isfinite(O.log_prob(lay, L.p0, what=0)[0])
+    chi = O.log_prob(lay, L.p0, what=1, return_chisq=True)[1][0]
+    red = chi / np.array([e.lc.n_data for e in L.eclipses])
+    assert (red < 2.5).sum() >= 5 and red.max() < 20
