@@ -40,6 +40,7 @@ constexpr int kElemThreads = 128;
 constexpr int kMaxDonorRings = 128;
 constexpr int kMaxQuad = 15;
 constexpr int kNumArr = 8;  // event arrays: white dwarf, disc, bright spot, 5 donor moments
+constexpr int kNoEventPos = 0x7fffffff;
 constexpr double kFix = 72057594037927936.0;         // 2^56: fixed-point scale of normalised weights
 constexpr double kInvFix = 1.0 / 72057594037927936.0;
 
@@ -84,6 +85,7 @@ struct JobScal {
     double xs, ys;             // stream impact point
     double smax, smaxp, shi;   // bright-spot strip: profile peak, peak^exp2, strip length (scale units)
     int status;                // 0 ok, 1 walker invalid, 2 stream misses disc, 3 bad parameter, 4 not needed
+    int ev_lo, ev_hi;          // sample positions spanned by the eclipse events of the job's tiles
 };
 
 __device__ __forceinline__ double fetch(const DevLayout& L, const double* th, int src)
@@ -139,9 +141,10 @@ __global__ void walker_kernel(DevLayout L, int what, int flags, long long n, con
     ws[w] = W;
 }
 
-// ---------------------------------------------------------------- stream_kernel
-__global__ void stream_kernel(DevLayout L, int what, int flags, long long njobs, const double* __restrict__ theta,
-                              WalkerScal* ws, JobScal* __restrict__ js)
+// ---------------------------------------------------------------- jobcheck_kernel / stream_kernel
+// jobcheck: which jobs are worth evaluating, and the bright-spot strip constants.
+__global__ void jobcheck_kernel(DevLayout L, int what, int flags, long long njobs, const double* __restrict__ theta,
+                                const WalkerScal* __restrict__ ws, JobScal* __restrict__ js)
 {
     long long job = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (job >= njobs) return;
@@ -151,57 +154,68 @@ __global__ void stream_kernel(DevLayout L, int what, int flags, long long njobs,
     J.xs = J.ys = 0.0;
     J.smax = J.smaxp = J.shi = 1.0;
     J.status = 0;
-    const WalkerScal W = ws[w];
+    J.ev_lo = kNoEventPos;
+    J.ev_hi = -2;
+    const WalkerScal& W = ws[w];
     if (W.status != 0) {
         J.status = 1;
-        js[job] = J;
-        return;
-    }
-    if (what != LFB_LN_LIKE && !(W.lnprior > -INFINITY)) {
+    } else if (what != LFB_LN_LIKE && !(W.lnprior > -INFINITY)) {
         J.status = 4;  // the prior already vetoed this walker: nothing downstream is evaluated
-        js[job] = J;
-        return;
-    }
-    const double* th = theta + w * L.ndim;
-    const int* g = L.gather + e * LFB_NPAR;
-    const bool do_wd = !(flags & LFB_FLAG_SKIP_WD), do_disc = !(flags & LFB_FLAG_SKIP_DISC);
-    const bool do_bs = !(flags & LFB_FLAG_SKIP_BS);
-    bool finite_all = true;
-    for (int k = 0; k < L.npars; ++k) finite_all = finite_all && isfinite(fetch(L, th, g[k]));
-    double rwd = fetch(L, th, g[P_RWD]), rdisc = fetch(L, th, g[P_RDISC]);
-    double exp1 = L.npars > P_EXP1 ? fetch(L, th, g[P_EXP1]) : 2.0;
-    double exp2 = L.npars > P_EXP2 ? fetch(L, th, g[P_EXP2]) : 1.0;
-    double scale = fetch(L, th, g[P_SCALE]);
-    if (!finite_all || ((do_wd || do_disc) && !(rwd > 0.0)) || (do_disc && !(rdisc > rwd)) ||
-        (do_bs && (!(scale > 0.0) || !(exp1 > 0.0) || !(exp2 > 0.0)))) {
-        J.status = 3;
-        js[job] = J;
-        return;
-    }
-    if (do_bs) {
-        double rdisc_a = rdisc * W.R.xl1;
-        double imp[4];
-        if (!bspot(W.R, rdisc_a, imp)) {
-            J.status = 2;  // the stream misses the disc (roche.bspot raises, CVModel.py:309-316)
-            if (what != LFB_LN_LIKE) ws[w].lnprior = -INFINITY;
-        } else {
-            J.xs = imp[0];
-            J.ys = imp[1];
+    } else {
+        const double* th = theta + w * L.ndim;
+        const int* g = L.gather + e * LFB_NPAR;
+        const bool do_wd = !(flags & LFB_FLAG_SKIP_WD), do_disc = !(flags & LFB_FLAG_SKIP_DISC);
+        const bool do_bs = !(flags & LFB_FLAG_SKIP_BS);
+        bool finite_all = true;
+        for (int k = 0; k < L.npars; ++k) finite_all = finite_all && isfinite(fetch(L, th, g[k]));
+        double rwd = fetch(L, th, g[P_RWD]), rdisc = fetch(L, th, g[P_RDISC]);
+        double exp1 = L.npars > P_EXP1 ? fetch(L, th, g[P_EXP1]) : 2.0;
+        double exp2 = L.npars > P_EXP2 ? fetch(L, th, g[P_EXP2]) : 1.0;
+        double scale = fetch(L, th, g[P_SCALE]);
+        if (!finite_all || ((do_wd || do_disc) && !(rwd > 0.0)) || (do_disc && !(rdisc > rwd)) ||
+            (do_bs && (!(scale > 0.0) || !(exp1 > 0.0) || !(exp2 > 0.0)))) {
+            J.status = 3;
+        } else if (do_bs) {
             J.smax = pow(exp1 / exp2, 1.0 / exp2);
             J.smaxp = pow(J.smax, exp2);
             J.shi = fmin(20.0 + J.smax, pow(J.smaxp + 30.0, 1.0 / exp2));
-            if (what != LFB_LN_LIKE) {
-                // azimuth window about the disc tangent at the impact point (CVModel.py:282-307)
-                double az = fetch(L, th, g[P_AZ]);
-                double alpha = atan2(imp[1], imp[0]) / kDeg;
-                if (alpha < 0.0) alpha = 90.0 - alpha;
-                double tangent = alpha + 90.0;
-                double minaz = fmax(0.0, tangent - 80.0), maxaz = fmin(178.0, tangent + 80.0);
-                if (!(az >= minaz) || !(az <= maxaz)) ws[w].lnprior = -INFINITY;
-            }
         }
     }
     js[job] = J;
+}
+
+// stream: ballistic stream from L1 to the disc edge -> bright-spot impact point; the azimuth rule
+// of SimpleEclipse.ln_prior.  A serial ODE per job: launched on a side stream so that it overlaps
+// the element solves that do not need it.
+__global__ void stream_kernel(DevLayout L, int what, int flags, long long njobs, const double* __restrict__ theta,
+                              WalkerScal* ws, JobScal* js)
+{
+    long long job = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (job >= njobs || (flags & LFB_FLAG_SKIP_BS)) return;
+    if (js[job].status != 0) return;
+    long long w = job / L.n_ecl;
+    int e = (int)(job - w * L.n_ecl);
+    const Roche R = ws[w].R;
+    const double* th = theta + w * L.ndim;
+    const int* g = L.gather + e * LFB_NPAR;
+    double rdisc_a = fetch(L, th, g[P_RDISC]) * R.xl1;
+    double imp[4];
+    if (!bspot(R, rdisc_a, imp)) {
+        js[job].status = 2;  // the stream misses the disc (roche.bspot raises, CVModel.py:309-316)
+        if (what != LFB_LN_LIKE) ws[w].lnprior = -INFINITY;
+        return;
+    }
+    js[job].xs = imp[0];
+    js[job].ys = imp[1];
+    if (what != LFB_LN_LIKE) {
+        // azimuth window about the disc tangent at the impact point (CVModel.py:282-307)
+        double az = fetch(L, th, g[P_AZ]);
+        double alpha = atan2(imp[1], imp[0]) / kDeg;
+        if (alpha < 0.0) alpha = 90.0 - alpha;
+        double tangent = alpha + 90.0;
+        double minaz = fmax(0.0, tangent - 80.0), maxaz = fmin(178.0, tangent + 80.0);
+        if (!(az >= minaz) || !(az <= maxaz)) ws[w].lnprior = -INFINITY;
+    }
 }
 
 // ---------------------------------------------------------------- elements_kernel
@@ -344,7 +358,7 @@ __device__ __forceinline__ double block_sum(double v, double* red)
     return t;
 }
 
-constexpr int kNoEvent = 0x7fffffff;  // event position: never happens
+constexpr int kNoEvent = kNoEventPos;  // event position: never happens
 constexpr int kAtStart = -1;          // event position: before the first sample
 
 // Per-job constants of the flux stage (written by prep_kernel)
@@ -366,7 +380,7 @@ struct FluxArgs {
     long long njobs;
     const double* theta;
     const WalkerScal* ws;
-    const JobScal* js;
+    JobScal* js;
     const double2* wd_io;
     const double4* don;
     const double2* disc_io;
@@ -579,72 +593,97 @@ __device__ __forceinline__ EventRec interval_pieces(const SampleAxis& X, double 
                            enc_pos(ev[3]) | (enc_pos(ev[4]) << 21) | (enc_pos(ev[5]) << 42));
 }
 
+// position of the last closing event of a record (kNoEvent if it stays open to the end; -2 if empty)
+__device__ __forceinline__ int rec_last_close(const EventRec& rec)
+{
+    if (dec_pos(rec.x, 0) == kNoEvent) return -2;
+    const int o1 = dec_pos(rec.x, 2), o2 = dec_pos(rec.y, 1);
+    return o2 != kNoEvent ? dec_pos(rec.y, 2) : (o1 != kNoEvent ? dec_pos(rec.y, 0) : dec_pos(rec.x, 1));
+}
+
 // positions_kernel: one thread per solved element (or donor quarter tile) of a job: where on the
 // job's sorted sample axis its eclipse (facing) intervals open and close.
 __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ FluxArgs A)
 {
     const GridCfg& G = A.G;
     const int per_job = G.n_wd_half + G.n_disc_half + G.n_bs + G.n_donor_q;
-    const int padded = (per_job + 31) & ~31;
+    const int padded = (per_job + 31) & ~31;  // a warp never straddles two jobs
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long job = gid / padded;
     const int t = (int)(gid - job * padded);
-    if (job >= A.njobs || t >= per_job) return;
+    if (job >= A.njobs) return;  // warp-uniform
     const long long w = job / A.L.n_ecl;
     const int egather = (int)(job - w * A.L.n_ecl);
     const int e = A.mode ? 0 : egather;
     const WalkerScal& W = A.ws[w];
-    if (!job_live(A, W, A.js[job])) return;
-    const SampleAxis X = sample_axis(A.smp, e, G.n_quad);
-    const JobConst& C = A.jc[job];
-    const double phi0w = C.phi0w;
-    EventRec* ivp = A.ivp + job * A.ni_total;
-    const int n_half = G.n_wd_half + G.n_disc_half;
-    const EventRec none = no_events();
-    if (t < n_half + G.n_bs) {
-        double2 io;
-        int i0;
-        bool on, mirror = t < n_half;
-        if (t < G.n_wd_half) {
-            on = !(A.flags & LFB_FLAG_SKIP_WD);
-            io = on ? A.wd_io[w * G.n_wd_half + t] : make_double2(kBig, -kBig);
-            i0 = 2 * t;
-        } else if (t < n_half) {
-            int h = t - G.n_wd_half;
-            on = !(A.flags & LFB_FLAG_SKIP_DISC);
-            io = on ? A.disc_io[job * G.n_disc_half + h] : make_double2(kBig, -kBig);
-            i0 = G.n_wd + 2 * h;
+    if (!job_live(A, W, A.js[job])) return;  // warp-uniform
+    int lo = kNoEvent, hi = -2;  // span of this thread's eclipse events on the sample axis
+    if (t < per_job) {
+        const SampleAxis X = sample_axis(A.smp, e, G.n_quad);
+        const double phi0w = A.jc[job].phi0w;
+        EventRec* ivp = A.ivp + job * A.ni_total;
+        const int n_half = G.n_wd_half + G.n_disc_half;
+        const EventRec none = no_events();
+        if (t < n_half + G.n_bs) {
+            double2 io;
+            int i0;
+            bool on, mirror = t < n_half;
+            if (t < G.n_wd_half) {
+                on = !(A.flags & LFB_FLAG_SKIP_WD);
+                io = on ? A.wd_io[w * G.n_wd_half + t] : make_double2(kBig, -kBig);
+                i0 = 2 * t;
+            } else if (t < n_half) {
+                int h = t - G.n_wd_half;
+                on = !(A.flags & LFB_FLAG_SKIP_DISC);
+                io = on ? A.disc_io[job * G.n_disc_half + h] : make_double2(kBig, -kBig);
+                i0 = G.n_wd + 2 * h;
+            } else {
+                int h = t - n_half;
+                on = !(A.flags & LFB_FLAG_SKIP_BS);
+                io = on ? A.bs_io[job * G.n_bs + h] : make_double2(kBig, -kBig);
+                i0 = G.n_wd + G.n_disc + h;
+            }
+            const bool ecl = io.y > io.x;
+            const EventRec r0 = ecl ? interval_pieces(X, io.x + phi0w, io.y + phi0w) : none;
+            ivp[i0] = r0;
+            lo = dec_pos(r0.x, 0);
+            hi = rec_last_close(r0);
+            // the y -> -y image is eclipsed from -egress to -ingress
+            if (mirror) {
+                const EventRec r1 = ecl ? interval_pieces(X, -io.y + phi0w, -io.x + phi0w) : none;
+                ivp[i0 + 1] = r1;
+                lo = min(lo, dec_pos(r1.x, 0));
+                hi = max(hi, rec_last_close(r1));
+            }
         } else {
-            int h = t - n_half;
-            on = !(A.flags & LFB_FLAG_SKIP_BS);
-            io = on ? A.bs_io[job * G.n_bs + h] : make_double2(kBig, -kBig);
-            i0 = G.n_wd + G.n_disc + h;
-        }
-        const bool ecl = io.y > io.x;
-        ivp[i0] = ecl ? interval_pieces(X, io.x + phi0w, io.y + phi0w) : none;
-        // the y -> -y image is eclipsed from -egress to -ingress
-        if (mirror) ivp[i0 + 1] = ecl ? interval_pieces(X, -io.y + phi0w, -io.x + phi0w) : none;
-    } else {
-        // donor: every tile image faces the observer for |phase - centre| < half width
-        const int h = t - n_half - G.n_bs;
-        const bool on = !(A.flags & LFB_FLAG_SKIP_DONOR);
-        double4 q = on ? A.don[w * G.n_donor_q + h] : make_double4(1.0, 0.0, 0.0, 0.0);
-        double Aq = W.si * q.x, Bq = -W.si * q.y, Dq = W.ci * q.z;
-        double rho = sqrt(Aq * Aq + Bq * Bq);
-        double psi = atan2(Bq, Aq) * (1.0 / kTwoPi);
-        double ratio = rho > 0.0 ? Dq / rho : (Dq > 0.0 ? 2.0 : -2.0);
-        // image with +D faces the observer iff cos(th - psi) > -D/rho
-        double hp = ratio >= 1.0 ? 0.5 : (ratio <= -1.0 ? -1.0 : acos(-ratio) * (1.0 / kTwoPi));
-        double hm = ratio <= -1.0 ? 0.5 : (ratio >= 1.0 ? -1.0 : acos(ratio) * (1.0 / kTwoPi));
-        EventRec* dnp = ivp + G.n_wd + G.n_disc + G.n_bs + 4 * h;
+            // donor: every tile image faces the observer for |phase - centre| < half width
+            const int h = t - n_half - G.n_bs;
+            const bool on = !(A.flags & LFB_FLAG_SKIP_DONOR);
+            double4 q = on ? A.don[w * G.n_donor_q + h] : make_double4(1.0, 0.0, 0.0, 0.0);
+            double Aq = W.si * q.x, Bq = -W.si * q.y, Dq = W.ci * q.z;
+            double rho = sqrt(Aq * Aq + Bq * Bq);
+            double psi = atan2(Bq, Aq) * (1.0 / kTwoPi);
+            double ratio = rho > 0.0 ? Dq / rho : (Dq > 0.0 ? 2.0 : -2.0);
+            // image with +D faces the observer iff cos(th - psi) > -D/rho
+            double hp = ratio >= 1.0 ? 0.5 : (ratio <= -1.0 ? -1.0 : acos(-ratio) * (1.0 / kTwoPi));
+            double hm = ratio <= -1.0 ? 0.5 : (ratio >= 1.0 ? -1.0 : acos(ratio) * (1.0 / kTwoPi));
+            EventRec* dnp = ivp + G.n_wd + G.n_disc + G.n_bs + 4 * h;
 #pragma unroll
-        for (int im = 0; im < 4; ++im) {
-            double cen = ((im & 1) ? -psi : psi) + phi0w, hw = (im & 2) ? hm : hp;
-            EventRec p = none;
-            if (on && hw >= 0.5) p.x = (p.x & ~(unsigned long long)kFieldNone) | enc_pos(kAtStart);  // always faces the observer
-            else if (on && hw >= 0.0) p = interval_pieces(X, cen - hw, cen + hw);
-            dnp[im] = p;
+            for (int im = 0; im < 4; ++im) {
+                double cen = ((im & 1) ? -psi : psi) + phi0w, hw = (im & 2) ? hm : hp;
+                EventRec p = none;
+                if (on && hw >= 0.5) p.x = (p.x & ~(unsigned long long)kFieldNone) | enc_pos(kAtStart);  // always faces the observer
+                else if (on && hw >= 0.0) p = interval_pieces(X, cen - hw, cen + hw);
+                dnp[im] = p;
+            }
         }
+    }
+    // span of the job's eclipse events (lets chunks far from the eclipse skip the tile records)
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0 && lo != kNoEvent) {
+        atomicMin(&A.js[job].ev_lo, lo);
+        atomicMax(&A.js[job].ev_hi, hi);
     }
 }
 
@@ -739,8 +778,10 @@ __global__ void __launch_bounds__(kFluxThreads, Mc <= 768 ? 3 : 2) flux_kernel(c
 #pragma unroll
     for (int a = 0; a < kNumArr; ++a) base[a] = 0;
     const int n_tile_iv = G.n_wd + G.n_disc + G.n_bs;
-    // records are fetched four at a time so that their L2 latencies overlap
-    for (int i0 = tid; i0 < n_tile_iv; i0 += 4 * kFluxThreads) {
+    // records are fetched four at a time so that their L2 latencies overlap; chunks that lie wholly
+    // before the first or after the last eclipse event of the job have nothing to do here
+    const bool tiles_matter = J.ev_lo < m1 && J.ev_hi >= m0;
+    for (int i0 = tid; tiles_matter && i0 < n_tile_iv; i0 += 4 * kFluxThreads) {
         EventRec recs[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {

@@ -79,7 +79,8 @@ struct lfb_handle {
     int device = 0;
     lfb_config cfg{};
     GridCfg grid{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr;  // side: the serial stream ODE, overlapped with the element solves
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     cudaEvent_t ev[ST_COUNT + 1] = {};
     bool ev_valid = false;
     std::string err;
@@ -282,9 +283,15 @@ static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleS
     if (record) CK(cudaEventRecord(h->ev[ST_WALKER], st));
     walker_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, what, flags, n, d_theta, h->ws.as<WalkerScal>());
     if (record) CK(cudaEventRecord(h->ev[ST_STREAM], st));
-    stream_kernel<<<(unsigned)((njobs + 63) / 64), 64, 0, st>>>(L, what, flags, njobs, d_theta, h->ws.as<WalkerScal>(),
-                                                                 h->js.as<JobScal>());
-    h->launches += 2;
+    jobcheck_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, st>>>(L, what, flags, njobs, d_theta, h->ws.as<WalkerScal>(),
+                                                                      h->js.as<JobScal>());
+    // fork: the ballistic-stream ODE (one serial integration per job) runs beside the element solves
+    CK(cudaEventRecord(h->fork_ev, st));
+    CK(cudaStreamWaitEvent(h->side, h->fork_ev, 0));
+    stream_kernel<<<(unsigned)((njobs + 63) / 64), 64, 0, h->side>>>(L, what, flags, njobs, d_theta, h->ws.as<WalkerScal>(),
+                                                                      h->js.as<JobScal>());
+    CK(cudaEventRecord(h->join_ev, h->side));
+    h->launches += 3;
     if (record) CK(cudaEventRecord(h->ev[ST_ELEMENTS], st));
     if (what != LFB_LN_PRIOR) {
         ElemArgs E;
@@ -310,16 +317,17 @@ static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleS
             elements_kernel<1><<<blocks(njobs, G.n_disc_half), kElemThreads, 0, st>>>(E);
             h->launches++;
         }
-        if (!(flags & LFB_FLAG_SKIP_BS)) {
-            elements_kernel<2><<<blocks(njobs, G.n_bs), kElemThreads, 0, st>>>(E);
-            h->launches++;
-        }
         if (!(flags & LFB_FLAG_SKIP_WD)) {
             elements_kernel<0><<<blocks(n, G.n_wd_half), kElemThreads, 0, st>>>(E);
             h->launches++;
         }
         if (!(flags & LFB_FLAG_SKIP_DONOR)) {
             elements_kernel<3><<<blocks(n, G.n_donor_q), kElemThreads, 0, st>>>(E);
+            h->launches++;
+        }
+        CK(cudaStreamWaitEvent(st, h->join_ev, 0));  // join: the strip needs the impact point
+        if (!(flags & LFB_FLAG_SKIP_BS)) {
+            elements_kernel<2><<<blocks(njobs, G.n_bs), kElemThreads, 0, st>>>(E);
             h->launches++;
         }
         if (record) CK(cudaEventRecord(h->ev[ST_FLUX], st));
@@ -336,7 +344,7 @@ static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleS
         A.njobs = njobs;
         A.theta = d_theta;
         A.ws = E.ws;
-        A.js = E.js;
+        A.js = h->js.as<JobScal>();
         A.wd_io = E.wd_io;
         A.don = E.don;
         A.disc_io = E.disc_io;
@@ -373,8 +381,9 @@ static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleS
         }
 #undef LFB_LAUNCH_FLUX
         h->launches += 3;
-    } else if (record) {
-        CK(cudaEventRecord(h->ev[ST_FLUX], st));
+    } else {
+        CK(cudaStreamWaitEvent(st, h->join_ev, 0));
+        if (record) CK(cudaEventRecord(h->ev[ST_FLUX], st));
     }
     if (record) CK(cudaEventRecord(h->ev[ST_FINISH], st));
     if (d_out || d_chi) {
@@ -434,6 +443,9 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (int i = 0; i <= ST_COUNT; ++i)
         if ((e = cudaEventCreate(&h->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -494,6 +506,9 @@ void lfb_destroy(lfb_handle* h)
     h->cf_lc.release();
     for (int i = 0; i <= ST_COUNT; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+    if (h->join_ev) cudaEventDestroy(h->join_ev);
+    if (h->side) cudaStreamDestroy(h->side);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

@@ -158,11 +158,10 @@ LFB_HD bool findi(const Roche& R, double dphi, double maxphi, double& sini)
     return true;
 }
 
-// Potential and its derivatives over the (th, lam) family of LOS of one element.
-LFB_HD void ray_eval(const Roche& R, double si, double ci, const Point& T, double th, double lam, Derivs& D)
+// Potential and its derivatives over the (th, lam) family of LOS of one element, at the
+// orbital angle whose cosine and sine are (c, s).
+LFB_HD void ray_eval(const Roche& R, double si, double ci, const Point& T, double c, double s, double lam, Derivs& D)
 {
-    double s, c;
-    sincos_(th, &s, &c);
     double ex = si * c, ey = -si * s;
     double dx = fma(lam, ex, -T.xi * s - T.eta * ci * c);
     double dy = fma(lam, ey, -T.xi * c + T.eta * ci * s);
@@ -185,6 +184,34 @@ LFB_HD void ray_eval(const Roche& R, double si, double ci, const Point& T, doubl
     D.Sll = a12 - b1 * x_e * x_e - b2 * d_e * d_e - e_xy;
     D.Stt = (a12 - 1.0) * t_t - b1 * x_t * x_t - b2 * d_t * d_t - (gx * dx + gy * dy);
     D.Stl = (a12 - 1.0) * e_t - b1 * x_e * x_t - b2 * d_e * d_t + (gx * ey - gy * ex);
+}
+
+// (c, s) <- rotation by d radians, |d| <= 0.25: Taylor to d^13 (below 1e-17), no range reduction
+LFB_HD void rotate_cs(double& c, double& s, double d)
+{
+    double d2 = d * d;
+    double sd = d * fma(d2, fma(d2, fma(d2, fma(d2, fma(d2, fma(d2, 1.0 / 6227020800.0, -1.0 / 39916800.0), 1.0 / 362880.0),
+                                                    -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
+    double cd = fma(d2, fma(d2, fma(d2, fma(d2, fma(d2, fma(d2, 1.0 / 479001600.0, -1.0 / 3628800.0), 1.0 / 40320.0),
+                                            -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
+    double cn = c * cd - s * sd;
+    s = s * cd + c * sd;
+    c = cn;
+}
+
+// reciprocal good to ~1e-11 relative: enough for a Newton step (the residual, not the step,
+// decides where the iteration converges to)
+LFB_HD double fast_rcp(double x)
+{
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = r * fma(-x, r, 2.0);
+    r = r * fma(-x, r, 2.0);
+    return r;
+#else
+    return 1.0 / x;
+#endif
 }
 
 // min over the chord of the LOS inside the bounding sphere of Phi - Phi_c (robust path only)
@@ -291,16 +318,19 @@ constexpr int kMinIters = 12;   // deepest-LOS Newton (shallow elements only), e
 constexpr int kRootIters = 16;  // grazing-LOS Newton, early exit
 
 // Ingress/egress phases (cycles) of one element; 0 if it is never eclipsed.
-// Fast path: 2-D Newton on (th, lam) for the two LOS that graze the critical
-// surface (Phi = Phi_c, dPhi/dlam = 0), started from the tangents to a sphere
-// inscribed in the lobe (deep elements) or from the osculating parabola at the
-// deepest LOS (shallow elements); every root is verified, anything unverified
-// goes to ingress_egress_robust.
+// Fast path: 2-D Newton on (th, lam) for the two LOS that graze the critical surface
+// (Phi = Phi_c, dPhi/dlam = 0), started from the tangents to a sphere inscribed in the lobe
+// (deep elements) or from the osculating parabola at the deepest LOS (shallow elements).  The
+// orbital angle is carried as (cos, sin) and advanced by small rotations, so the loop has no
+// trigonometric calls; one atan2 per root at the end.  Every root is verified; anything
+// unverified goes to ingress_egress_robust.
 LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, double* ph_in, double* ph_out)
 {
-    double psi = atan2(T.y - T.xi, 1.0 - T.x + T.eta * ci);
-    double th = psi, s, c;
-    sincos_(th, &s, &c);
+    // conjunction: the LOS passes closest to the donor's centre
+    const double X = 1.0 - T.x + T.eta * ci, Y = T.y - T.xi;
+    const double ih = rsqrt(X * X + Y * Y);
+    const double cpsi = X * ih, spsi = Y * ih;
+    double c = cpsi, s = spsi;
     double ex = si * c, ey = -si * s;
     double wx = 1.0 - (T.x - T.xi * s - T.eta * ci * c);
     double wy = -(T.y - T.xi * c + T.eta * ci * s);
@@ -312,21 +342,25 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
     double tang = sqrt(w2 - R.rin * R.rin);
     double cosd = (tang - wz * ci) / rxy;
     Derivs D;
-    double th0, th1, lam0, lam1, thm = psi;
+    double c0, s0, c1, s1, lam0, lam1, cm = cpsi, sm = spsi;
     if (cosd < 0.995) {
-        double del = acos(cosd > -1.0 ? cosd : -1.0);
-        th0 = psi - del;
-        th1 = psi + del;
+        // the conjunction LOS passes well inside the inscribed sphere: start at its tangents
+        cosd = cosd > -1.0 ? cosd : -1.0;
+        double sind = sqrt(1.0 - cosd * cosd);
+        c0 = cpsi * cosd + spsi * sind;  // psi - del
+        s0 = spsi * cosd - cpsi * sind;
+        c1 = cpsi * cosd - spsi * sind;  // psi + del
+        s1 = spsi * cosd + cpsi * sind;
         lam0 = lam1 = tang;
     } else {
         for (int it = 0; it < 5; ++it) {
-            ray_eval(R, si, ci, T, th, lam, D);
+            ray_eval(R, si, ci, T, c, s, lam, D);
             if (!(D.Sll > 0.0)) return 0;  // no potential minimum along the closest LOS: out of reach
             lam += clampd(-D.Sl / D.Sll, 0.1);
         }
         bool conv = false;
         for (int it = 0; it < kMinIters; ++it) {
-            ray_eval(R, si, ci, T, th, lam, D);
+            ray_eval(R, si, ci, T, c, s, lam, D);
             double det = D.Stt * D.Sll - D.Stl * D.Stl;
             if (!(D.Sll > 0.0) || !(det > 0.0)) {
                 if (D.S >= R.phic) return 0;
@@ -334,54 +368,60 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
             }
             double dth = clampd(-(D.St * D.Sll - D.Sl * D.Stl) / det, 0.1);
             double dl = clampd(-(D.Sl * D.Stt - D.St * D.Stl) / det, 0.1);
-            th += dth;
+            rotate_cs(c, s, dth);
             lam += dl;
             if (fabs(dth) < 1e-7 && fabs(dl) < 1e-7) { conv = true; break; }
         }
         if (!conv) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
-        ray_eval(R, si, ci, T, th, lam, D);
+        ray_eval(R, si, ci, T, c, s, lam, D);
         double g0 = D.S - R.phic;
         if (!(g0 < 0.0)) return 0;  // the deepest LOS clears the lobe
         double kappa = D.Stt - D.Stl * D.Stl / D.Sll;
         if (!(D.Sll > 0.0) || !(kappa > 0.0)) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
         double del = sqrt(-2.0 * g0 / kappa), slope = -D.Stl / D.Sll;
-        thm = th;
-        th0 = th - del;
-        th1 = th + del;
+        if (!(del < 0.25)) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
+        cm = c;
+        sm = s;
+        c0 = c1 = c;
+        s0 = s1 = s;
+        rotate_cs(c0, s0, -del);
+        rotate_cs(c1, s1, del);
         lam0 = lam - slope * del;
         lam1 = lam + slope * del;
     }
     double res[2];
 #pragma unroll 1
     for (int side = 0; side < 2; ++side) {
-        double sg = side ? 1.0 : -1.0;
-        th = side ? th1 : th0;
+        const double sg = side ? 1.0 : -1.0;
+        c = side ? c1 : c0;
+        s = side ? s1 : s0;
         lam = side ? lam1 : lam0;
         bool conv = false;
         for (int it = 0; it < kRootIters; ++it) {
-            ray_eval(R, si, ci, T, th, lam, D);
+            ray_eval(R, si, ci, T, c, s, lam, D);
             double F1 = D.S - R.phic, F2 = D.Sl;
-            double idet = 1.0 / (D.St * D.Sll - D.Sl * D.Stl);
+            double idet = fast_rcp(D.St * D.Sll - D.Sl * D.Stl);
             double dth = clampd((-F1 * D.Sll + F2 * D.Sl) * idet, 0.2);
             double dl = clampd((-D.St * F2 + D.Stl * F1) * idet, 0.2);
-            if (sg * (th + dth - thm) <= 0.0) {  // stay on this side of the deepest LOS
-                dth = 0.5 * (thm - th);
+            // stay on this side of the deepest LOS: sin(th + dth - thm) must keep the sign of sg
+            double cross = s * cm - c * sm;  // sin(th - thm)
+            if (!(sg * (cross + dth * (c * cm + s * sm)) > 0.0)) {
+                dth = -0.5 * asin(cross > 1.0 ? 1.0 : (cross < -1.0 ? -1.0 : cross));
                 dl *= 0.5;
             }
-            th += dth;
+            rotate_cs(c, s, dth);
             lam += dl;
-            if (fabs(dth) < 1e-13 && fabs(dl) < 1e-10) { conv = true; break; }
+            // quadratic convergence: a step below 1e-9 leaves an error far below 1e-15
+            if (fabs(dth) < 1e-9 && fabs(dl) < 1e-7) { conv = true; break; }
         }
-        // accept only a converged grazing LOS of the right kind
-        ray_eval(R, si, ci, T, th, lam, D);
-        sincos_(th, &s, &c);
+        // accept only a converged grazing LOS of the right kind (D is one tiny step old)
         double xx = T.x - T.xi * s - T.eta * ci * c + lam * si * c - 1.0;
         double yy = T.y - T.xi * c + T.eta * ci * s - lam * si * s;
         double zz = T.z + T.eta * si + lam * ci;
         bool ok = conv && D.Sll > 0.0 && lam > 0.0 && xx * xx + yy * yy + zz * zz <= R.rs * R.rs &&
-                  (side ? D.St > 0.0 : D.St < 0.0) && fabs(th - psi) < 0.5 * kPi;
+                  (side ? D.St > 0.0 : D.St < 0.0) && c * cpsi + s * spsi > 0.0;
         if (!ok) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
-        res[side] = th;
+        res[side] = atan2(s, c);
     }
     if (!(res[0] < res[1])) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
     *ph_in = res[0] * (1.0 / kTwoPi);
