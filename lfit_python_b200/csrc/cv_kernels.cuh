@@ -71,6 +71,8 @@ struct GridCfg {
     int n_wd_half, n_disc_half;  // elements solved (the other half follows by the y -> -y mirror)
     double donor_ulimb, donor_gdexp;
     const int* donor_ring_off;  // [n_donor_th + 1] offsets of each ring's quarter tiles
+    const int* disc_order;      // [n_disc_half] disc elements ordered along the line of centres, so that the
+                                // threads of a warp solve elements of the same kind (deep / shallow / never eclipsed)
     double quad_off[kMaxQuad], quad_w[kMaxQuad];
 };
 
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(kElemThreads) elements_kernel(const __grid_con
 
     Point T = {0.0, 0.0, 0.0, 0.0, 0.0};
     double wt = 0.0;
+    int tile = t;  // where the result goes
     if (COMP == 0) {
         // white dwarf: limb-darkened disc on the sky, ring k, tiles with cos(alpha) > 0
         const double rwd_a = fetch(A.L, th, g[P_RWD]) * R.xl1;
@@ -306,7 +309,8 @@ __global__ void __launch_bounds__(kElemThreads) elements_kernel(const __grid_con
             // disc: ring m, sector j on the y > 0 side
             const double rwd_a = fetch(A.L, th, g[P_RWD]) * R.xl1, rdisc_a = fetch(A.L, th, g[P_RDISC]) * R.xl1;
             int hth = G.n_disc_th / 2;
-            int m = t / hth, j = t - m * hth;
+            tile = G.disc_order[t];
+            int m = tile / hth, j = tile - m * hth;
             double r = rwd_a + (m + 0.5) * (rdisc_a - rwd_a) / G.n_disc_r;
             double sa, ca;
             sincos_((j + 0.5) * kTwoPi / G.n_disc_th, &sa, &ca);
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(kElemThreads) elements_kernel(const __grid_con
     double pin, pout;
     if (!ingress_egress(R, si, ci, T, &pin, &pout)) { pin = kBig; pout = -kBig; }
     if (COMP == 0) A.wd_io[unit * G.n_wd_half + t] = make_double2(pin, pout);
-    else if (COMP == 1) A.disc_io[unit * G.n_disc_half + t] = make_double2(pin, pout);
+    else if (COMP == 1) A.disc_io[unit * G.n_disc_half + tile] = make_double2(pin, pout);
     else {
         A.bs_io[unit * G.n_bs + t] = make_double2(pin, pout);
         A.bs_b[unit * G.n_bs + t] = wt;

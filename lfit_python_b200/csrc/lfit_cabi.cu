@@ -73,31 +73,66 @@ struct SampleSet {
 
 enum { ST_WALKER = 0, ST_STREAM, ST_ELEMENTS, ST_FLUX, ST_FINISH, ST_COUNT };
 
+// A lane runs one batch of walkers through the whole pipeline on its own streams and buffers.
+// Two lanes work on alternate batches so that one batch's FP64-bound element solves overlap
+// the other's shared-memory-bound flux stage.
+struct Lane {
+    cudaStream_t st = nullptr, side = nullptr;  // side: the serial stream ODE beside the element solves
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, done_ev = nullptr;
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    DevBuf ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, ivp, chi_part;
+    cudaError_t create()
+    {
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        for (int i = 0; i <= ST_COUNT; ++i)
+            if ((e = cudaEventCreate(&ev[i])) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    void destroy()
+    {
+        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &ivp, &chi_part};
+        for (DevBuf* x : b) x->release();
+        for (int i = 0; i <= ST_COUNT; ++i)
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        if (fork_ev) cudaEventDestroy(fork_ev);
+        if (join_ev) cudaEventDestroy(join_ev);
+        if (done_ev) cudaEventDestroy(done_ev);
+        if (side) cudaStreamDestroy(side);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+constexpr int kLanes = 2;
+
 }  // namespace
 
 struct lfb_handle {
     int device = 0;
     lfb_config cfg{};
     GridCfg grid{};
-    cudaStream_t stream = nullptr, side = nullptr;  // side: the serial stream ODE, overlapped with the element solves
-    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
-    cudaEvent_t ev[ST_COUNT + 1] = {};
+    cudaStream_t stream = nullptr;
+    Lane lanes[kLanes];
+    cudaEvent_t enter_ev = nullptr, t0_ev = nullptr, t1_ev = nullptr;
     bool ev_valid = false;
     std::string err;
     long long launches = 0;
     int sm_count = 148;
     int max_smem = 0;
     int Mc = 512;
-    long long max_jobs_per_batch = 262144;
+    long long max_jobs_per_batch = 131072;
     // layout
     bool have_layout = false, have_lc = false;
     int ndim = 0, n_ecl = 0, npars = 0, n_prior = 0;
-    DevBuf gather, consts, psrc, ptype, pisvar, pp1, pp2, pnorm, donor_off;
+    DevBuf gather, consts, psrc, ptype, pisvar, pp1, pp2, pnorm, donor_off, disc_order;
     SampleSet lc, cf_lc;
     // calc_flux scratch
     DevBuf cf_gather, cf_pars, cf_tot, cf_comp;
     // work
-    DevBuf theta, out, chisq, ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, ivp, chi_part;
+    DevBuf theta, out, chisq;
     DevBuf h_in, h_out, h_chisq;
     lfb_handle() { h_in.pinned_host = h_out.pinned_host = h_chisq.pinned_host = true; }
 };
@@ -267,32 +302,33 @@ static size_t flux_smem_bytes(int Mc, int nF)
 }
 
 // One pass of the pipeline over walkers [0, n) (device pointers, one batch).
-static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleSet& ss, int what, int flags, int mode,
+static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss, int what, int flags, int mode,
                      long long n, const double* d_theta, double* d_out, double* d_chi, double* d_tot, double* d_comp,
                      bool record)
 {
     const GridCfg& G = h->grid;
     const long long njobs = n * L.n_ecl;
-    CK(h->ws.reserve(sizeof(WalkerScal) * (size_t)n));
-    CK(h->js.reserve(sizeof(JobScal) * (size_t)njobs));
-    CK(h->wd_io.reserve(sizeof(double2) * (size_t)n * G.n_wd_half));
-    CK(h->don.reserve(sizeof(double4) * (size_t)n * G.n_donor_q));
-    CK(h->disc_io.reserve(sizeof(double2) * (size_t)njobs * G.n_disc_half));
-    CK(h->bs_io.reserve(sizeof(double2) * (size_t)njobs * G.n_bs));
-    CK(h->bs_b.reserve(sizeof(double) * (size_t)njobs * G.n_bs));
-    if (record) CK(cudaEventRecord(h->ev[ST_WALKER], st));
-    walker_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, what, flags, n, d_theta, h->ws.as<WalkerScal>());
-    if (record) CK(cudaEventRecord(h->ev[ST_STREAM], st));
-    jobcheck_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, st>>>(L, what, flags, njobs, d_theta, h->ws.as<WalkerScal>(),
-                                                                      h->js.as<JobScal>());
+    cudaStream_t st = ln.st;
+    CK(ln.ws.reserve(sizeof(WalkerScal) * (size_t)n));
+    CK(ln.js.reserve(sizeof(JobScal) * (size_t)njobs));
+    CK(ln.wd_io.reserve(sizeof(double2) * (size_t)n * G.n_wd_half));
+    CK(ln.don.reserve(sizeof(double4) * (size_t)n * G.n_donor_q));
+    CK(ln.disc_io.reserve(sizeof(double2) * (size_t)njobs * G.n_disc_half));
+    CK(ln.bs_io.reserve(sizeof(double2) * (size_t)njobs * G.n_bs));
+    CK(ln.bs_b.reserve(sizeof(double) * (size_t)njobs * G.n_bs));
+    if (record) CK(cudaEventRecord(ln.ev[ST_WALKER], st));
+    walker_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, what, flags, n, d_theta, ln.ws.as<WalkerScal>());
+    if (record) CK(cudaEventRecord(ln.ev[ST_STREAM], st));
+    jobcheck_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, st>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
+                                                                      ln.js.as<JobScal>());
     // fork: the ballistic-stream ODE (one serial integration per job) runs beside the element solves
-    CK(cudaEventRecord(h->fork_ev, st));
-    CK(cudaStreamWaitEvent(h->side, h->fork_ev, 0));
-    stream_kernel<<<(unsigned)((njobs + 63) / 64), 64, 0, h->side>>>(L, what, flags, njobs, d_theta, h->ws.as<WalkerScal>(),
-                                                                      h->js.as<JobScal>());
-    CK(cudaEventRecord(h->join_ev, h->side));
+    CK(cudaEventRecord(ln.fork_ev, st));
+    CK(cudaStreamWaitEvent(ln.side, ln.fork_ev, 0));
+    stream_kernel<<<(unsigned)((njobs + 63) / 64), 64, 0, ln.side>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
+                                                                      ln.js.as<JobScal>());
+    CK(cudaEventRecord(ln.join_ev, ln.side));
     h->launches += 3;
-    if (record) CK(cudaEventRecord(h->ev[ST_ELEMENTS], st));
+    if (record) CK(cudaEventRecord(ln.ev[ST_ELEMENTS], st));
     if (what != LFB_LN_PRIOR) {
         ElemArgs E;
         E.L = L;
@@ -302,13 +338,13 @@ static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleS
         E.n = n;
         E.njobs = njobs;
         E.theta = d_theta;
-        E.ws = h->ws.as<WalkerScal>();
-        E.js = h->js.as<JobScal>();
-        E.wd_io = h->wd_io.as<double2>();
-        E.don = h->don.as<double4>();
-        E.disc_io = h->disc_io.as<double2>();
-        E.bs_io = h->bs_io.as<double2>();
-        E.bs_b = h->bs_b.as<double>();
+        E.ws = ln.ws.as<WalkerScal>();
+        E.js = ln.js.as<JobScal>();
+        E.wd_io = ln.wd_io.as<double2>();
+        E.don = ln.don.as<double4>();
+        E.disc_io = ln.disc_io.as<double2>();
+        E.bs_io = ln.bs_io.as<double2>();
+        E.bs_b = ln.bs_b.as<double>();
         auto blocks = [&](long long units, int per_unit) {
             long long padded = (per_unit + 31) & ~31;
             return (unsigned)((units * padded + kElemThreads - 1) / kElemThreads);
@@ -325,12 +361,12 @@ static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleS
             elements_kernel<3><<<blocks(n, G.n_donor_q), kElemThreads, 0, st>>>(E);
             h->launches++;
         }
-        CK(cudaStreamWaitEvent(st, h->join_ev, 0));  // join: the strip needs the impact point
+        CK(cudaStreamWaitEvent(st, ln.join_ev, 0));  // join: the strip needs the impact point
         if (!(flags & LFB_FLAG_SKIP_BS)) {
             elements_kernel<2><<<blocks(njobs, G.n_bs), kElemThreads, 0, st>>>(E);
             h->launches++;
         }
-        if (record) CK(cudaEventRecord(h->ev[ST_FLUX], st));
+        if (record) CK(cudaEventRecord(ln.ev[ST_FLUX], st));
         FluxArgs A;
         A.L = L;
         A.G = G;
@@ -344,21 +380,21 @@ static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleS
         A.njobs = njobs;
         A.theta = d_theta;
         A.ws = E.ws;
-        A.js = h->js.as<JobScal>();
+        A.js = ln.js.as<JobScal>();
         A.wd_io = E.wd_io;
         A.don = E.don;
         A.disc_io = E.disc_io;
         A.bs_io = E.bs_io;
         A.bs_b = E.bs_b;
         const size_t nwq = (size_t)G.n_wd_rings + G.n_disc_r + G.n_bs;
-        CK(h->jc.reserve(sizeof(JobConst) * (size_t)njobs));
-        CK(h->wq.reserve(sizeof(long long) * (size_t)njobs * nwq));
-        CK(h->ivp.reserve(sizeof(EventRec) * (size_t)njobs * A.ni_total));
-        CK(h->chi_part.reserve(sizeof(double) * (size_t)njobs * ss.max_chunks));
-        A.jc = h->jc.as<JobConst>();
-        A.wq = h->wq.as<long long>();
-        A.ivp = h->ivp.as<EventRec>();
-        A.chi_part = h->chi_part.as<double>();
+        CK(ln.jc.reserve(sizeof(JobConst) * (size_t)njobs));
+        CK(ln.wq.reserve(sizeof(long long) * (size_t)njobs * nwq));
+        CK(ln.ivp.reserve(sizeof(EventRec) * (size_t)njobs * A.ni_total));
+        CK(ln.chi_part.reserve(sizeof(double) * (size_t)njobs * ss.max_chunks));
+        A.jc = ln.jc.as<JobConst>();
+        A.wq = ln.wq.as<long long>();
+        A.ivp = ln.ivp.as<EventRec>();
+        A.chi_part = ln.chi_part.as<double>();
         A.flux_tot = d_tot;
         A.flux_comp = d_comp;
         prep_kernel<<<(unsigned)((njobs + 3) / 4), 128, 0, st>>>(A);
@@ -382,19 +418,18 @@ static int run_batch(lfb_handle* h, cudaStream_t st, const DevLayout& L, SampleS
 #undef LFB_LAUNCH_FLUX
         h->launches += 3;
     } else {
-        CK(cudaStreamWaitEvent(st, h->join_ev, 0));
-        if (record) CK(cudaEventRecord(h->ev[ST_FLUX], st));
+        CK(cudaStreamWaitEvent(st, ln.join_ev, 0));
+        if (record) CK(cudaEventRecord(ln.ev[ST_FLUX], st));
     }
-    if (record) CK(cudaEventRecord(h->ev[ST_FINISH], st));
+    if (record) CK(cudaEventRecord(ln.ev[ST_FINISH], st));
     if (d_out || d_chi) {
         finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(what, L.n_ecl, n, ss.max_chunks,
-                                                                  ss.chunk_off.as<long long>(), h->ws.as<WalkerScal>(),
-                                                                  h->chi_part.as<double>(), d_chi, d_out);
+                                                                  ss.chunk_off.as<long long>(), ln.ws.as<WalkerScal>(),
+                                                                  ln.chi_part.as<double>(), d_chi, d_out);
         h->launches++;
     }
     if (record) {
-        CK(cudaEventRecord(h->ev[ST_COUNT], st));
-        h->ev_valid = true;
+        CK(cudaEventRecord(ln.ev[ST_COUNT], st));
     }
     CK(cudaGetLastError());
     return LFB_OK;
@@ -443,11 +478,11 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    if ((e = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-    for (int i = 0; i <= ST_COUNT; ++i)
-        if ((e = cudaEventCreate(&h->ev[i])) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int i = 0; i < kLanes; ++i)
+        if ((e = h->lanes[i].create()) != cudaSuccess) return bail("lane streams/events", e);
+    if ((e = cudaEventCreateWithFlags(&h->enter_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->t0_ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->t1_ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     GridCfg& G = h->grid;
@@ -470,6 +505,23 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
         cudaMemcpy(h->donor_off.p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
         return bail("donor ring table", cudaGetLastError());
     G.donor_ring_off = h->donor_off.as<int>();
+    // disc elements in order of their position along the line of centres, (m + 1/2) cos(az): elements
+    // next to each other in this order are eclipsed in the same way (deeply / barely / never), which
+    // keeps the 32 threads of a warp on the same branch of the solver
+    {
+        const int hth = c.n_disc_th / 2;
+        std::vector<int> order(G.n_disc_half);
+        std::iota(order.begin(), order.end(), 0);
+        auto key = [&](int tile) {
+            int m = tile / hth, j = tile % hth;
+            return (m + 0.5) * cos((j + 0.5) * kTwoPi / c.n_disc_th);
+        };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) > key(b); });
+        if (h->disc_order.reserve(order.size() * sizeof(int)) != cudaSuccess ||
+            cudaMemcpy(h->disc_order.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail("disc order table", cudaGetLastError());
+        G.disc_order = h->disc_order.as<int>();
+    }
     // composite Simpson nodes on [-1, 1] (exposure = phase +- width, CVModel.py:64)
     if (c.n_quad == 1) {
         G.quad_off[0] = 0.0;
@@ -498,17 +550,18 @@ void lfb_destroy(lfb_handle* h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->gather, &h->consts, &h->psrc, &h->ptype, &h->pisvar, &h->pp1, &h->pp2, &h->pnorm,
-                      &h->donor_off, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
-                      &h->chisq, &h->ws, &h->js, &h->wd_io, &h->don, &h->disc_io, &h->bs_io, &h->bs_b,
-                      &h->jc, &h->wq, &h->ivp, &h->chi_part, &h->h_in, &h->h_out, &h->h_chisq};
+                      &h->donor_off, &h->disc_order, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
+                      &h->chisq, &h->h_in, &h->h_out, &h->h_chisq};
     for (DevBuf* b : bufs) b->release();
     h->lc.release();
     h->cf_lc.release();
-    for (int i = 0; i <= ST_COUNT; ++i)
-        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
-    if (h->join_ev) cudaEventDestroy(h->join_ev);
-    if (h->side) cudaStreamDestroy(h->side);
+    for (int i = 0; i < kLanes; ++i) {
+        if (h->lanes[i].st) cudaStreamSynchronize(h->lanes[i].st);
+        h->lanes[i].destroy();
+    }
+    if (h->enter_ev) cudaEventDestroy(h->enter_ev);
+    if (h->t0_ev) cudaEventDestroy(h->t0_ev);
+    if (h->t1_ev) cudaEventDestroy(h->t1_ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -529,12 +582,18 @@ int lfb_last_stage_ms(lfb_handle* h, float out[6])
     if (!h || !out) return LFB_EINVAL;
     for (int i = 0; i < 6; ++i) out[i] = -1.0f;
     if (!h->ev_valid) return LFB_ESTATE;
+    // stages of the last batch that ran on lane 0 (they overlap the other lane's work);
+    // total = the whole call on the caller's stream
+    Lane& ln = h->lanes[0];
     for (int i = 0; i < ST_COUNT; ++i)
-        if (cudaEventElapsedTime(&out[i], h->ev[i], h->ev[i + 1]) != cudaSuccess) {
+        if (cudaEventElapsedTime(&out[i], ln.ev[i], ln.ev[i + 1]) != cudaSuccess) {
             cudaGetLastError();
             return fail(h, LFB_ECUDA, "stage events not complete: synchronise the stream first");
         }
-    cudaEventElapsedTime(&out[5], h->ev[0], h->ev[ST_COUNT]);
+    if (cudaEventElapsedTime(&out[5], h->t0_ev, h->t1_ev) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, LFB_ECUDA, "stage events not complete: synchronise the stream first");
+    }
     return LFB_OK;
 }
 
@@ -542,7 +601,7 @@ float lfb_last_kernel_ms(lfb_handle* h)
 {
     float t[6];
     if (lfb_last_stage_ms(h, t) != LFB_OK) return -1.0f;
-    return t[ST_ELEMENTS] + t[ST_FLUX];
+    return t[5];
 }
 
 int lfb_set_layout(lfb_handle* h, int ndim, int n_ecl, int npars, const int* gather, int n_consts,
@@ -668,16 +727,39 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
         d_chi = h->chisq.as<double>();
     }
     if (what == LFB_LN_PRIOR && chisq_out) CK(cudaMemsetAsync(d_chi, 0xff, sizeof(double) * (size_t)njobs, st));
-    if (what == LFB_LN_PRIOR) CK(h->chi_part.reserve(8));
+    if (what == LFB_LN_PRIOR)
+        for (int i = 0; i < kLanes; ++i) CK(h->lanes[i].chi_part.reserve(8));
     DevLayout L = make_layout(h);
-    // bounded batches of walkers keep the element buffers small (16 B x ~900 elements per job)
-    long long per = std::max<long long>(1, h->max_jobs_per_batch / h->n_ecl);
-    for (long long w0 = 0; w0 < n; w0 += per) {
-        long long nb = std::min(per, n - w0);
-        int rc = run_batch(h, st, L, h->lc, what, 0, 0, nb, d_theta + w0 * h->ndim, d_out + w0, d_chi + w0 * h->n_ecl,
-                           nullptr, nullptr, w0 + per >= n);
+    // Batches of walkers alternate between two lanes (own streams and buffers): one batch's
+    // FP64-bound element solves overlap the other's flux stage, and the element / event buffers
+    // stay bounded (~60 KB per job in flight).
+    CK(cudaEventRecord(h->enter_ev, st));
+    CK(cudaEventRecord(h->t0_ev, st));
+    const long long njobs_all = n * h->n_ecl;
+    long long nbatch = (njobs_all + h->max_jobs_per_batch - 1) / h->max_jobs_per_batch;
+    if (nbatch < kLanes && njobs_all >= 1024) nbatch = kLanes;
+    if (nbatch > 1 && (nbatch & 1)) ++nbatch;
+    const long long per = (n + nbatch - 1) / nbatch;
+    int used = 0;
+    long long b = 0;
+    for (long long w0 = 0; w0 < n; w0 += per, ++b) {
+        Lane& ln = h->lanes[b % kLanes];
+        if (b < kLanes) {
+            CK(cudaStreamWaitEvent(ln.st, h->enter_ev, 0));
+            used = (int)b + 1;
+        }
+        const long long nb = std::min(per, n - w0);
+        const bool last_on_lane0 = (b % kLanes) == 0 && w0 + (long long)kLanes * per >= n;
+        int rc = run_batch(h, ln, L, h->lc, what, 0, 0, nb, d_theta + w0 * h->ndim, d_out + w0, d_chi + w0 * h->n_ecl,
+                           nullptr, nullptr, last_on_lane0);
         if (rc) return rc;
     }
+    for (int i = 0; i < used; ++i) {
+        CK(cudaEventRecord(h->lanes[i].done_ev, h->lanes[i].st));
+        CK(cudaStreamWaitEvent(st, h->lanes[i].done_ev, 0));
+    }
+    CK(cudaEventRecord(h->t1_ev, st));
+    h->ev_valid = true;
     if (!out_dev || (chisq_out && !chi_dev)) {
         CK(h->h_out.reserve(sizeof(double) * (size_t)n));
         if (!out_dev) CK(cudaMemcpyAsync(h->h_out.p, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -736,8 +818,13 @@ int lfb_calc_flux(lfb_handle* h, long long n_sets, const double* pars, int npars
     L.npars = npars;
     L.n_prior = 0;
     L.gather = h->cf_gather.as<int>();
-    rc = run_batch(h, st, L, h->cf_lc, LFB_LN_LIKE, flags, 1, n_sets, d_pars, nullptr, nullptr, d_tot, d_comp, false);
+    Lane& ln = h->lanes[0];
+    CK(cudaEventRecord(h->enter_ev, st));
+    CK(cudaStreamWaitEvent(ln.st, h->enter_ev, 0));
+    rc = run_batch(h, ln, L, h->cf_lc, LFB_LN_LIKE, flags, 1, n_sets, d_pars, nullptr, nullptr, d_tot, d_comp, false);
     if (rc) return rc;
+    CK(cudaEventRecord(ln.done_ev, ln.st));
+    CK(cudaStreamWaitEvent(st, ln.done_ev, 0));
     if (!tot_dev) CK(cudaMemcpyAsync(out_total, d_tot, cur, cudaMemcpyDeviceToHost, st));
     if (out_comp && !comp_dev) CK(cudaMemcpyAsync(out_comp, d_comp, 4 * cur, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -158,6 +158,37 @@ LFB_HD bool findi(const Roche& R, double dphi, double maxphi, double& sini)
     return true;
 }
 
+// 1/sqrt(x) for the well-scaled squared distances met here (no zero / denormal / inf handling):
+// hardware seed + two Newton steps, a few ulp.
+LFB_HD double fast_rsqrt(double x)
+{
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    return y;
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// reciprocal good to ~1e-11 relative: enough for a Newton step (the residual, not the step,
+// decides where the iteration converges to)
+LFB_HD double fast_rcp(double x)
+{
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = r * fma(-x, r, 2.0);
+    r = r * fma(-x, r, 2.0);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
 // Potential and its derivatives over the (th, lam) family of LOS of one element, at the
 // orbital angle whose cosine and sine are (c, s).
 LFB_HD void ray_eval(const Roche& R, double si, double ci, const Point& T, double c, double s, double lam, Derivs& D)
@@ -170,7 +201,7 @@ LFB_HD void ray_eval(const Roche& R, double si, double ci, const Point& T, doubl
     double tx = dy, ty = -dx;  // d/dth of the part that turns with the observer
     double x2 = x - 1.0;
     double yz = y * y + z * z;
-    double ir1 = rsqrt(x * x + yz), ir2 = rsqrt(x2 * x2 + yz);
+    double ir1 = fast_rsqrt(x * x + yz), ir2 = fast_rsqrt(x2 * x2 + yz);
     double a1 = R.omu * ir1 * ir1 * ir1, a2 = R.mu * ir2 * ir2 * ir2;
     double b1 = 3.0 * a1 * ir1 * ir1, b2 = 3.0 * a2 * ir2 * ir2;
     double a12 = a1 + a2, xc = x - R.mu;
@@ -197,21 +228,6 @@ LFB_HD void rotate_cs(double& c, double& s, double d)
     double cn = c * cd - s * sd;
     s = s * cd + c * sd;
     c = cn;
-}
-
-// reciprocal good to ~1e-11 relative: enough for a Newton step (the residual, not the step,
-// decides where the iteration converges to)
-LFB_HD double fast_rcp(double x)
-{
-#ifdef __CUDA_ARCH__
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = r * fma(-x, r, 2.0);
-    r = r * fma(-x, r, 2.0);
-    return r;
-#else
-    return 1.0 / x;
-#endif
 }
 
 // min over the chord of the LOS inside the bounding sphere of Phi - Phi_c (robust path only)
