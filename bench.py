@@ -33,10 +33,15 @@ if ROOT not in sys.path:
 METRIC = "lightcurve_evals_per_s"
 UNIT = "lightcurve evals/s"
 
-# FP64 operations one lightcurve evaluation of the bench workload executes (FMA = 2;
-# add/mul/compare-select = 1), from the ncu instruction counters of the same command
-# (profiles/): see DESIGN.md "Roofline accounting".  Keyed by kernel revision.
-FLOPS_PER_LIGHTCURVE = {"r1-direct": None, "r1-events": None}
+# FP64 operations per light-curve evaluation of the bench workload (FMA = 2, add = mul = 1,
+# compares / conversions 0), from the ncu instruction counters of this very command
+# (smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on, profiles/r01_launches.csv,
+# tabulated by tools/launch_table.py); see DESIGN.md "Roofline accounting".  Keyed by kernel
+# revision: "elements" = the four elements_kernel launches (stage 1, the FP64-bound kernels),
+# "all" = every kernel of a log-probability pass.
+FLOPS_PER_LIGHTCURVE = {
+    "r1": {"elements": 2.458e6, "all": 2.962e6, "source": "profiles/r01_launches.csv"},
+}
 
 
 def env_int(name, default):
@@ -244,31 +249,55 @@ def run_gpu(args, rank, local_rank, world):
     e2e_s = float(e2e_s.item())
     assert np.array_equal(np.isfinite(lnp_h), np.isfinite(lnp_d.cpu().numpy()))
 
+    # clean per-stage device times for the roofline: the same pass with the two batch lanes
+    # serialised (LFB_LANES=1), so that the element solves are timed alone, by CUDA events
+    # recorded on the stream they run on
+    os.environ["LFB_LANES"] = "1"
+    eng1 = _cabi.Engine(local_rank, **wl.grid)
+    os.environ.pop("LFB_LANES")
+    wl.apply(eng1)
+    serial_stage = []
+    for i in range(3 + args.steps):
+        flush.fill_(float(i))
+        eng1.log_prob_device(theta_d.data_ptr(), n, lnp_d.data_ptr(), what=_cabi.LN_PROB, stream=stream)
+        torch.cuda.synchronize()
+        if i >= 3:
+            serial_stage.append(eng1.last_stage_ms())
+    eng1.close()
+
     if rank == 0:
         evals_per_step = world * n * wl.n_ecl
         value = evals_per_step * args.steps / (total_ms * 1e-3)
         k_ms = float(np.mean(kernel_ms))
-        flops_lc = FLOPS_PER_LIGHTCURVE.get(args.kernel_rev)
+        fl = FLOPS_PER_LIGHTCURVE.get(args.kernel_rev)
         stages = {k: float(np.mean([d[k] for d in stage_ms])) for k in stage_ms[0]}
-        roof = {"bound": "fp64", "kernel": "elements_kernel + flux_kernel", "kernel_ms": k_ms, "stage_ms": stages,
-                "kernel_share_of_step": k_ms / (total_ms / args.steps),
-                "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "DFMA probe on this device, this run",
-                "traffic": None, "flops_per_lightcurve": flops_lc}
-        if flops_lc:
-            roof["achieved"] = flops_lc * n * wl.n_ecl / (k_ms * 1e-3) * 1e-12
+        serial = {k: float(np.mean([d[k] for d in serial_stage])) for k in serial_stage[0]}
+        el_ms = serial["elements"]
+        roof = {"bound": "fp64", "kernel": "elements_kernel<wd,disc,spot,donor> (stage 1: Roche ingress/egress solves)",
+                "kernel_ms": el_ms, "kernel_share_of_step": el_ms / serial["total"],
+                "stage_ms_serial": serial, "stage_ms_overlapped": stages, "pipeline_ms": k_ms,
+                "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "DFMA probe on this device, this run "
+                "(MEASURED_PEAKS.json has no FP64 vector figure)", "traffic": None}
+        if fl and wl.name.startswith("C2") and not args.n_ph and not wl.grid:
+            per_rank = n * wl.n_ecl
+            roof["flops_per_lightcurve"] = fl
+            roof["achieved"] = fl["elements"] * per_rank / (el_ms * 1e-3) * 1e-12
             roof["frac"] = roof["achieved"] / fp64_peak
+            roof["whole_pass"] = {"achieved": fl["all"] * per_rank / (k_ms * 1e-3) * 1e-12,
+                                  "frac": fl["all"] * per_rank / (k_ms * 1e-3) * 1e-12 / fp64_peak}
         else:
             roof["achieved"] = None
             roof["frac"] = None
         # HBM side of the same kernel, for the record: theta in, chi-squared out, light curve re-read per CTA
-        alg_bytes = n * wl.n_ecl * (18 * 8 + 8 + 4 * 8 * wl.n_ph)
+        alg_bytes = n * wl.n_ecl * (18 * 8 + 8 + 2 * (16 * 903 + 8 * 200 + 32 * 103) + 2 * 16 * 2012)
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "measured"
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback"
         roof["hbm"] = {"achieved": alg_bytes / (k_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                       "frac": alg_bytes / (k_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src}
+                       "frac": alg_bytes / (k_ms * 1e-3) * 1e-9 / hbm_peak, "peak_source": hbm_src,
+                       "note": "algorithmic bytes of the whole pass: theta in, chi-squared out, element and event records written and read once"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -277,7 +306,7 @@ def run_gpu(args, rank, local_rank, world):
                        "ndim": wl.ndim, "grid": eng.config, "l2": "flushed between timed iterations (256 MB fill)",
                        "parallelism": "walkers sharded, %d rank(s)" % world,
                        "collective": "nccl all_gather of ln_prob + positions" if world > 1 else "none"},
-            "emcee_steps_per_s": args.steps / (total_ms * 1e-3),
+            "ensemble_passes_per_s": args.steps / (total_ms * 1e-3),
             "e2e": {"value": evals_per_step * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(n * wl.ndim * 8), "d2h_bytes_per_step": int(n * 8)},
             "gpu_launches": int(launches),
@@ -305,7 +334,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0, help="reference arm: walkers per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--kernel-rev", default="r1-events")
+    ap.add_argument("--kernel-rev", default="r1")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":

@@ -124,6 +124,7 @@ struct lfb_handle {
     int max_smem = 0;
     int Mc = 512;
     long long max_jobs_per_batch = 131072;
+    int n_lanes = kLanes;  // LFB_LANES=1 serialises the batches (clean per-stage timings for profiling)
     // layout
     bool have_layout = false, have_lc = false;
     int ndim = 0, n_ecl = 0, npars = 0, n_prior = 0;
@@ -536,6 +537,10 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
     }
     // capacity of a flux-kernel chunk in samples (multiple of kFluxThreads); LFB_MC overrides for tuning
     h->Mc = 768;
+    if (const char* env = getenv("LFB_LANES")) {
+        int v = atoi(env);
+        if (v >= 1 && v <= kLanes) h->n_lanes = v;
+    }
     if (const char* env = getenv("LFB_MC")) {
         int v = atoi(env);
         if (v == 256 || v == 512 || v == 768 || v == 1024 || v == 2048) h->Mc = v;
@@ -737,19 +742,19 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
     CK(cudaEventRecord(h->t0_ev, st));
     const long long njobs_all = n * h->n_ecl;
     long long nbatch = (njobs_all + h->max_jobs_per_batch - 1) / h->max_jobs_per_batch;
-    if (nbatch < kLanes && njobs_all >= 1024) nbatch = kLanes;
-    if (nbatch > 1 && (nbatch & 1)) ++nbatch;
+    if (nbatch < h->n_lanes && njobs_all >= 1024) nbatch = h->n_lanes;
+    if (h->n_lanes > 1 && nbatch > 1 && (nbatch & 1)) ++nbatch;
     const long long per = (n + nbatch - 1) / nbatch;
     int used = 0;
     long long b = 0;
     for (long long w0 = 0; w0 < n; w0 += per, ++b) {
-        Lane& ln = h->lanes[b % kLanes];
-        if (b < kLanes) {
+        Lane& ln = h->lanes[b % h->n_lanes];
+        if (b < h->n_lanes) {
             CK(cudaStreamWaitEvent(ln.st, h->enter_ev, 0));
             used = (int)b + 1;
         }
         const long long nb = std::min(per, n - w0);
-        const bool last_on_lane0 = (b % kLanes) == 0 && w0 + (long long)kLanes * per >= n;
+        const bool last_on_lane0 = (b % h->n_lanes) == 0 && w0 + (long long)h->n_lanes * per >= n;
         int rc = run_batch(h, ln, L, h->lc, what, 0, 0, nb, d_theta + w0 * h->ndim, d_out + w0, d_chi + w0 * h->n_ecl,
                            nullptr, nullptr, last_on_lane0);
         if (rc) return rc;
