@@ -249,6 +249,23 @@ def run_gpu(args, rank, local_rank, world):
     e2e_s = float(e2e_s.item())
     assert np.array_equal(np.isfinite(lnp_h), np.isfinite(lnp_d.cpu().numpy()))
 
+    # emcee steps/s: the stretch move of mcmc_utils.EnsembleSampler (host side, emcee's algebra) driving the
+    # vectorised CUDA log-probability -- one step = two half-steps = n log-probability evaluations per GPU
+    from lfit_python_b200 import mcmc_utils
+    sampler = mcmc_utils.EnsembleSampler(n, wl.ndim, lambda t: eng.log_prob(t, what=_cabi.LN_PROB), vectorize=True,
+                                         rng=np.random.default_rng(99 + rank))
+    state = sampler.run_mcmc(theta_h, 2, store=False)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    n_mc = max(5, args.steps)
+    sampler.run_mcmc(state[0], n_mc, log_prob0=state[1], store=False)
+    mc_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(mc_s, op=dist.ReduceOp.MAX)
+    mc_steps_per_s = n_mc / float(mc_s.item())
+    acc_frac = float(sampler.acceptance_fraction.mean())
+
     # clean per-stage device times for the roofline: the same pass with the two batch lanes
     # serialised (LFB_LANES=1), so that the element solves are timed alone, by CUDA events
     # recorded on the stream they run on
@@ -307,6 +324,9 @@ def run_gpu(args, rank, local_rank, world):
                        "parallelism": "walkers sharded, %d rank(s)" % world,
                        "collective": "nccl all_gather of ln_prob + positions" if world > 1 else "none"},
             "ensemble_passes_per_s": args.steps / (total_ms * 1e-3),
+            "emcee_steps_per_s": mc_steps_per_s,
+            "emcee": {"walkers_per_gpu": n, "steps_timed": n_mc, "acceptance_fraction": acc_frac,
+                      "note": "host stretch move (numpy) + one CUDA ln_prob call per half-step, host buffers"},
             "e2e": {"value": evals_per_step * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(n * wl.ndim * 8), "d2h_bytes_per_step": int(n * 8)},
             "gpu_launches": int(launches),
