@@ -221,6 +221,15 @@ LFB_HD void ray_eval(const Roche& R, double si, double ci, const Point& T, doubl
 LFB_HD void rotate_cs(double& c, double& s, double d)
 {
     double d2 = d * d;
+    if (d2 < 1e-6) {
+        // late Newton steps: d^7 terms are below 1e-21
+        double sd = d * fma(d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+        double cd = fma(d2, fma(d2, fma(d2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+        double cn = c * cd - s * sd;
+        s = s * cd + c * sd;
+        c = cn;
+        return;
+    }
     double sd = d * fma(d2, fma(d2, fma(d2, fma(d2, fma(d2, fma(d2, 1.0 / 6227020800.0, -1.0 / 39916800.0), 1.0 / 362880.0),
                                                     -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
     double cd = fma(d2, fma(d2, fma(d2, fma(d2, fma(d2, fma(d2, 1.0 / 479001600.0, -1.0 / 3628800.0), 1.0 / 40320.0),
@@ -372,7 +381,9 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         for (int it = 0; it < 5; ++it) {
             ray_eval(R, si, ci, T, c, s, lam, D);
             if (!(D.Sll > 0.0)) return 0;  // no potential minimum along the closest LOS: out of reach
-            lam += clampd(-D.Sl / D.Sll, 0.1);
+            double dl = clampd(-D.Sl * fast_rcp(D.Sll), 0.1);
+            lam += dl;
+            if (fabs(dl) < 1e-6) break;  // the 2-D Newton below finishes the job
         }
         bool conv = false;
         for (int it = 0; it < kMinIters; ++it) {
