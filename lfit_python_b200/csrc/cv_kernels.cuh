@@ -71,6 +71,7 @@ struct GridCfg {
     int n_wd_half, n_disc_half;  // elements solved (the other half follows by the y -> -y mirror)
     double donor_ulimb, donor_gdexp;
     const int* donor_ring_off;  // [n_donor_th + 1] offsets of each ring's quarter tiles
+    const unsigned short* rec_widx;  // [n_wd + n_disc + n_bs] index of each tile record's weight in the job's weight table
     const int* disc_order;      // [n_disc_half] disc elements ordered along the line of centres, so that the
                                 // threads of a warp solve elements of the same kind (deep / shallow / never eclipsed)
     double quad_off[kMaxQuad], quad_w[kMaxQuad];
@@ -392,6 +393,7 @@ struct FluxArgs {
     const double* bs_b;
     JobConst* jc;           // [njobs]
     long long* wq;          // [njobs][n_wd_rings + n_disc_r + n_bs] fixed-point element weights
+    long long* qmom;        // [njobs][n_donor_q][8] fixed-point donor moment parts of each quarter tile
     ulonglong2* ivp;        // [njobs][ni_total] event records (EventRec) of every eclipse / facing interval
     double* chi_part;       // [njobs][max_chunks]
     double* flux_tot;       // mode 1: [njobs][n_ph]
@@ -671,6 +673,21 @@ __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ 
             // image with +D faces the observer iff cos(th - psi) > -D/rho
             double hp = ratio >= 1.0 ? 0.5 : (ratio <= -1.0 ? -1.0 : acos(-ratio) * (1.0 / kTwoPi));
             double hm = ratio <= -1.0 ? 0.5 : (ratio >= 1.0 ? -1.0 : acos(ratio) * (1.0 / kTwoPi));
+            // W m (1 - u + u m), m = A c + B s + D, as moments of (1, c, s, c^2, c s): the four mirror
+            // images differ by the signs of B and D, so eight integers serve all of them
+            {
+                const double ud = G.donor_ulimb, sc = on ? q.w * A.jc[job].don_sc : 0.0;
+                const double Bp = W.si * q.y;
+                long long* m = A.qmom + (job * G.n_donor_q + h) * 8;
+                m[0] = llrint(sc * ud * (Dq * Dq + Bp * Bp));
+                m[1] = llrint(sc * (1.0 - ud) * Dq);
+                m[2] = llrint(sc * (1.0 - ud) * Aq);
+                m[3] = llrint(sc * 2.0 * ud * Aq * Dq);
+                m[4] = llrint(sc * (1.0 - ud) * Bp);
+                m[5] = llrint(sc * 2.0 * ud * Bp * Dq);
+                m[6] = llrint(sc * ud * (Aq * Aq - Bp * Bp));
+                m[7] = llrint(sc * 2.0 * ud * Aq * Bp);
+            }
             EventRec* dnp = ivp + G.n_wd + G.n_disc + G.n_bs + 4 * h;
 #pragma unroll
             for (int im = 0; im < 4; ++im) {
@@ -700,24 +717,6 @@ __device__ __forceinline__ bool rec_irrelevant(const EventRec& rec, int m0, int 
     const int o1 = dec_pos(rec.x, 2), o2 = dec_pos(rec.y, 1);
     const int last_close = o2 != kNoEvent ? dec_pos(rec.y, 2) : (o1 != kNoEvent ? dec_pos(rec.y, 0) : dec_pos(rec.x, 1));
     return last_close < m0;
-}
-
-// five moments (1, c, s, c^2, c s) of W m (1 - u + u m), m = A c + B s + D, in 2^-56 fixed point
-__device__ __forceinline__ void donor_moments(double sc, double ud, double Aq, double Bi, double Di, long long mo[5])
-{
-    mo[0] = llrint(sc * ((1.0 - ud) * Di + ud * (Di * Di + Bi * Bi)));
-    mo[1] = llrint(sc * ((1.0 - ud) * Aq + 2.0 * ud * Aq * Di));
-    mo[2] = llrint(sc * ((1.0 - ud) * Bi + 2.0 * ud * Bi * Di));
-    mo[3] = llrint(sc * (ud * (Aq * Aq - Bi * Bi)));
-    mo[4] = llrint(sc * (2.0 * ud * Aq * Bi));
-}
-
-// An event of weight w at sample position p, seen from the chunk [m0, m1): before the chunk it
-// belongs to the chunk's start value, inside it goes to the chunk's event array.
-__device__ __forceinline__ void put_event(unsigned long long* Darr, long long* base, int p, int m0, int m1, long long w)
-{
-    if (p < m0) *base += w;
-    else if (p < m1) atomicAdd(Darr + (p - m0), (unsigned long long)w);
 }
 
 // flux_kernel: one CTA per (job, chunk of consecutive data points).  The chunk's samples are a
@@ -769,10 +768,7 @@ __global__ void __launch_bounds__(kFluxThreads, Mc <= 768 ? 3 : 2) flux_kernel(c
     }
     const JobConst C = A.jc[job];
     const long long* wq_wd = A.wq + job * (G.n_wd_rings + G.n_disc_r + G.n_bs);
-    const long long* wq_disc = wq_wd + G.n_wd_rings;
-    const long long* wq_bs = wq_disc + G.n_disc_r;
     const EventRec* ivp = A.ivp + job * A.ni_total;
-    const double ud = G.donor_ulimb;
 
     for (int i = tid; i < kNumArr * Mc; i += kFluxThreads) D[i] = 0ull;
     __syncthreads();
@@ -797,48 +793,54 @@ __global__ void __launch_bounds__(kFluxThreads, Mc <= 768 ? 3 : 2) flux_kernel(c
             const int i = i0 + u * kFluxThreads;
             const EventRec rec = recs[u];
             if (rec_irrelevant(rec, m0, m1)) continue;
-            int arr;
-            long long wq;
-            if (i < G.n_wd) {
-                int t = i >> 1;
-                int k = (int)sqrt(0.5 * (double)t);
-                while (2 * k * k > t) --k;
-                while (2 * (k + 1) * (k + 1) <= t) ++k;
-                wq = __ldg(wq_wd + k);
-                arr = 0;
-            } else if (i < G.n_wd + G.n_disc) {
-                wq = __ldg(wq_disc + ((i - G.n_wd) >> 1) / (G.n_disc_th / 2));
-                arr = 1;
-            } else {
-                wq = __ldg(wq_bs + (i - G.n_wd - G.n_disc));
-                arr = 2;
-            }
-            long long b0 = 0;
+            const int widx = __ldg(G.rec_widx + i);
+            const long long wq = __ldg(wq_wd + widx);  // the job's weight table is contiguous: rings, rings, strip
+            const int arr = (widx >= G.n_wd_rings) + (widx >= G.n_wd_rings + G.n_disc_r);
             unsigned long long* Da = D + arr * Mc;
+            int net = 0;  // intervals of this record that are open when the chunk starts
 #pragma unroll
-            for (int k = 0; k < 6; ++k)
-                put_event(Da, &b0, dec_pos(k < 3 ? rec.x : rec.y, k % 3), m0, m1, (k & 1) ? -wq : wq);
+            for (int k = 0; k < 6; ++k) {
+                const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
+                if (p < m0) net += (k & 1) ? -1 : 1;
+                else if (p < m1) atomicAdd(Da + (p - m0), (unsigned long long)((k & 1) ? -wq : wq));
+            }
+            const long long b0 = net ? wq : 0;
             base[0] += arr == 0 ? b0 : 0;
             base[1] += arr == 1 ? b0 : 0;
             base[2] += arr == 2 ? b0 : 0;
         }
     }
     if (!(A.flags & LFB_FLAG_SKIP_DONOR)) {
-        const double4* don = A.don + w * G.n_donor_q;
         const EventRec* dnp = ivp + n_tile_iv;
+        const long long* qm = A.qmom + job * G.n_donor_q * 8;
         for (int i = tid; i < 4 * G.n_donor_q; i += kFluxThreads) {
             const EventRec rec = dnp[i];
             if (rec_irrelevant(rec, m0, m1)) continue;
-            const double4 q = don[i >> 2];
+            // image i & 1: B = +si ny (else -si ny); i & 2: D = -ci nz (else +ci nz)
+            const longlong2* m8 = (const longlong2*)(qm + 8 * (i >> 2));
+            const longlong2 m01 = __ldg(m8), m23 = __ldg(m8 + 1), m45 = __ldg(m8 + 2), m67 = __ldg(m8 + 3);
+            const bool pb = i & 1, nd = i & 2;
             long long mo[5];
-            donor_moments(q.w * C.don_sc, ud, W.si * q.x, (i & 1) ? W.si * q.y : -W.si * q.y,
-                          (i & 2) ? -W.ci * q.z : W.ci * q.z, mo);
+            mo[0] = m01.x + (nd ? -m01.y : m01.y);
+            mo[1] = m23.x + (nd ? -m23.y : m23.y);
+            mo[2] = m45.x + (nd ? -m45.y : m45.y);
+            mo[2] = pb ? mo[2] : -mo[2];
+            mo[3] = m67.x;
+            mo[4] = pb ? m67.y : -m67.y;
+            int net = 0;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
-                if (p >= m1) break;
+                if (p < m0) net += (k & 1) ? -1 : 1;
+                else if (p < m1) {
 #pragma unroll
-                for (int j = 0; j < 5; ++j) put_event(D + (3 + j) * Mc, &base[3 + j], p, m0, m1, (k & 1) ? -mo[j] : mo[j]);
+                    for (int j = 0; j < 5; ++j)
+                        atomicAdd(D + (3 + j) * Mc + (p - m0), (unsigned long long)((k & 1) ? -mo[j] : mo[j]));
+                }
+            }
+            if (net) {
+#pragma unroll
+                for (int j = 0; j < 5; ++j) base[3 + j] += mo[j];
             }
         }
     }

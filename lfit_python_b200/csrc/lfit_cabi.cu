@@ -80,7 +80,7 @@ struct Lane {
     cudaStream_t st = nullptr, side = nullptr;  // side: the serial stream ODE beside the element solves
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr, done_ev = nullptr;
     cudaEvent_t ev[ST_COUNT + 1] = {};
-    DevBuf ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, ivp, chi_part;
+    DevBuf ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, qmom, ivp, chi_part;
     cudaError_t create()
     {
         cudaError_t e;
@@ -95,7 +95,7 @@ struct Lane {
     }
     void destroy()
     {
-        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &ivp, &chi_part};
+        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &qmom, &ivp, &chi_part};
         for (DevBuf* x : b) x->release();
         for (int i = 0; i <= ST_COUNT; ++i)
             if (ev[i]) cudaEventDestroy(ev[i]);
@@ -128,7 +128,7 @@ struct lfb_handle {
     // layout
     bool have_layout = false, have_lc = false;
     int ndim = 0, n_ecl = 0, npars = 0, n_prior = 0;
-    DevBuf gather, consts, psrc, ptype, pisvar, pp1, pp2, pnorm, donor_off, disc_order;
+    DevBuf gather, consts, psrc, ptype, pisvar, pp1, pp2, pnorm, donor_off, disc_order, rec_widx;
     SampleSet lc, cf_lc;
     // calc_flux scratch
     DevBuf cf_gather, cf_pars, cf_tot, cf_comp;
@@ -390,10 +390,12 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         const size_t nwq = (size_t)G.n_wd_rings + G.n_disc_r + G.n_bs;
         CK(ln.jc.reserve(sizeof(JobConst) * (size_t)njobs));
         CK(ln.wq.reserve(sizeof(long long) * (size_t)njobs * nwq));
+        CK(ln.qmom.reserve(sizeof(long long) * (size_t)njobs * G.n_donor_q * 8));
         CK(ln.ivp.reserve(sizeof(EventRec) * (size_t)njobs * A.ni_total));
         CK(ln.chi_part.reserve(sizeof(double) * (size_t)njobs * ss.max_chunks));
         A.jc = ln.jc.as<JobConst>();
         A.wq = ln.wq.as<long long>();
+        A.qmom = ln.qmom.as<long long>();
         A.ivp = ln.ivp.as<EventRec>();
         A.chi_part = ln.chi_part.as<double>();
         A.flux_tot = d_tot;
@@ -523,6 +525,28 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
             return bail("disc order table", cudaGetLastError());
         G.disc_order = h->disc_order.as<int>();
     }
+    // where each tile record (mirrors included) finds its weight in a job's weight table
+    // [white-dwarf rings | disc rings | strip elements]
+    {
+        std::vector<unsigned short> widx((size_t)G.n_wd + G.n_disc + G.n_bs);
+        for (int i = 0; i < G.n_wd; ++i) {
+            int t = i >> 1, k = (int)sqrt(0.5 * (double)t);
+            while (2 * k * k > t) --k;
+            while (2 * (k + 1) * (k + 1) <= t) ++k;
+            widx[i] = (unsigned short)k;
+        }
+        for (int i = 0; i < G.n_disc; ++i) widx[G.n_wd + i] = (unsigned short)(G.n_wd_rings + (i >> 1) / (G.n_disc_th / 2));
+        for (int i = 0; i < G.n_bs; ++i) widx[G.n_wd + G.n_disc + i] = (unsigned short)(G.n_wd_rings + G.n_disc_r + i);
+        if (G.n_wd_rings + G.n_disc_r + G.n_bs > 65535) {
+            g_create_error = "surface grid too dense (weight table index)";
+            delete h;
+            return LFB_EINVAL;
+        }
+        if (h->rec_widx.reserve(widx.size() * sizeof(unsigned short)) != cudaSuccess ||
+            cudaMemcpy(h->rec_widx.p, widx.data(), widx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail("record weight index table", cudaGetLastError());
+        G.rec_widx = h->rec_widx.as<unsigned short>();
+    }
     // composite Simpson nodes on [-1, 1] (exposure = phase +- width, CVModel.py:64)
     if (c.n_quad == 1) {
         G.quad_off[0] = 0.0;
@@ -555,7 +579,7 @@ void lfb_destroy(lfb_handle* h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->gather, &h->consts, &h->psrc, &h->ptype, &h->pisvar, &h->pp1, &h->pp2, &h->pnorm,
-                      &h->donor_off, &h->disc_order, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
+                      &h->donor_off, &h->disc_order, &h->rec_widx, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
                       &h->chisq, &h->h_in, &h->h_out, &h->h_chisq};
     for (DevBuf* b : bufs) b->release();
     h->lc.release();
