@@ -266,6 +266,20 @@ def run_gpu(args, rank, local_rank, world):
     mc_steps_per_s = n_mc / float(mc_s.item())
     acc_frac = float(sampler.acceptance_fraction.mean())
 
+    # the same move with the ensemble resident in HBM (no PCIe traffic per step)
+    class _Vec:
+        engine, ndim = eng, wl.ndim
+    dsampler = mcmc_utils.DeviceEnsembleSampler(n, _Vec, seed=7 + rank)
+    dsampler.run_mcmc(theta_h, 2)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    dsampler.run_mcmc(None, n_mc)
+    dmc_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dmc_s, op=dist.ReduceOp.MAX)
+    dmc_steps_per_s = n_mc / float(dmc_s.item())
+
     # clean per-stage device times for the roofline: the same pass with the two batch lanes
     # serialised (LFB_LANES=1), so that the element solves are timed alone, by CUDA events
     # recorded on the stream they run on
@@ -326,7 +340,8 @@ def run_gpu(args, rank, local_rank, world):
             "ensemble_passes_per_s": args.steps / (total_ms * 1e-3),
             "emcee_steps_per_s": mc_steps_per_s,
             "emcee": {"walkers_per_gpu": n, "steps_timed": n_mc, "acceptance_fraction": acc_frac,
-                      "note": "host stretch move (numpy) + one CUDA ln_prob call per half-step, host buffers"},
+                      "note": "host stretch move (numpy) + one CUDA ln_prob call per half-step, host buffers",
+                      "device_resident_steps_per_s": dmc_steps_per_s},
             "e2e": {"value": evals_per_step * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(n * wl.ndim * 8), "d2h_bytes_per_step": int(n * 8)},
             "gpu_launches": int(launches),

@@ -182,3 +182,69 @@ def readchain(file, nskip=0, thin=1):
     npars = data.shape[1] - 1
     chain = data[:nprod * nwalkers, 1:].reshape((nprod, nwalkers, npars))
     return np.swapaxes(chain, 0, 1)[:, nskip::thin, :]
+
+
+class DeviceEnsembleSampler:
+    """The same stretch move with the ensemble resident in GPU memory.
+
+    Positions, log-probabilities, proposals and the accept/reject step live in torch CUDA tensors
+    (plumbing only); the log-probability is the CUDA engine called through raw device pointers, so
+    a step moves nothing across PCIe.  `vec` is a flatten.VectorModel (or anything with `.engine`
+    and `.ndim`)."""
+
+    def __init__(self, nwalkers, vec, a=2.0, seed=None, what=2):
+        import torch
+        if nwalkers % 2 or nwalkers < 2 * vec.ndim:
+            raise ValueError("need an even number of walkers, at least twice the number of dimensions")
+        self.torch = torch
+        self.engine, self.ndim, self.nwalkers, self.a, self.what = vec.engine, vec.ndim, nwalkers, float(a), what
+        self.device = torch.device("cuda", self.engine.device)
+        self.gen = torch.Generator(device=self.device)
+        if seed is not None:
+            self.gen.manual_seed(int(seed))
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.pos = self.lnp = None
+        self.naccepted = torch.zeros(nwalkers, dtype=torch.int64, device=self.device)
+        self.iterations = 0
+
+    def _log_prob(self, theta):
+        torch = self.torch
+        theta = theta.contiguous()
+        out = torch.empty(theta.shape[0], dtype=torch.float64, device=self.device)
+        self.engine.log_prob_device(theta.data_ptr(), theta.shape[0], out.data_ptr(), what=self.what,
+                                    stream=self.stream.cuda_stream)
+        return out
+
+    def run_mcmc(self, initial_state, nsteps):
+        """Advance nsteps; returns (positions, log-probabilities) as host arrays."""
+        torch = self.torch
+        half = self.nwalkers // 2
+        with torch.cuda.stream(self.stream):
+            if initial_state is not None:
+                self.pos = torch.as_tensor(np.asarray(initial_state, dtype=np.float64)).to(self.device)
+                self.lnp = self._log_prob(self.pos)
+            pos, lnp = self.pos, self.lnp
+            for _ in range(nsteps):
+                perm = torch.randperm(self.nwalkers, device=self.device, generator=self.gen)
+                for first, second in ((perm[:half], perm[half:]), (perm[half:], perm[:half])):
+                    s, c = pos[first], pos[second]
+                    u = torch.rand(half, dtype=torch.float64, device=self.device, generator=self.gen)
+                    zz = ((self.a - 1.0) * u + 1.0) ** 2 / self.a
+                    partner = c[torch.randint(half, (half,), device=self.device, generator=self.gen)]
+                    prop = partner - (partner - s) * zz[:, None]
+                    new_lnp = self._log_prob(prop)
+                    lnpdiff = (self.ndim - 1.0) * torch.log(zz) + new_lnp - lnp[first]
+                    accept = lnpdiff > torch.log(torch.rand(half, dtype=torch.float64, device=self.device,
+                                                            generator=self.gen))
+                    idx = first[accept]
+                    pos[idx] = prop[accept]
+                    lnp[idx] = new_lnp[accept]
+                    self.naccepted[idx] += 1
+                self.iterations += 1
+            self.pos, self.lnp = pos, lnp
+        self.stream.synchronize()
+        return pos.cpu().numpy(), lnp.cpu().numpy()
+
+    @property
+    def acceptance_fraction(self):
+        return self.naccepted.cpu().numpy() / max(self.iterations, 1)
