@@ -287,13 +287,15 @@ def run_gpu(args, rank, local_rank, world):
     eng1 = _cabi.Engine(local_rank, **wl.grid)
     os.environ.pop("LFB_LANES")
     wl.apply(eng1)
-    serial_stage = []
+    eng1.set_trace(True)
+    serial_stage, serial_trace = [], []
     for i in range(3 + args.steps):
         flush.fill_(float(i))
         eng1.log_prob_device(theta_d.data_ptr(), n, lnp_d.data_ptr(), what=_cabi.LN_PROB, stream=stream)
         torch.cuda.synchronize()
         if i >= 3:
             serial_stage.append(eng1.last_stage_ms())
+            serial_trace.append(eng1.last_trace_ms())
     eng1.close()
 
     if rank == 0:
@@ -303,10 +305,11 @@ def run_gpu(args, rank, local_rank, world):
         fl = FLOPS_PER_LIGHTCURVE.get(args.kernel_rev)
         stages = {k: float(np.mean([d[k] for d in stage_ms])) for k in stage_ms[0]}
         serial = {k: float(np.mean([d[k] for d in serial_stage])) for k in serial_stage[0]}
+        trace = {k: float(np.mean([d[k] for d in serial_trace])) for k in serial_trace[0]}
         el_ms = serial["elements"]
         roof = {"bound": "fp64", "kernel": "elements_kernel<wd,disc,spot,donor> (stage 1: Roche ingress/egress solves)",
                 "kernel_ms": el_ms, "kernel_share_of_step": el_ms / serial["total"],
-                "stage_ms_serial": serial, "stage_ms_overlapped": stages, "pipeline_ms": k_ms,
+                "stage_ms_serial": serial, "kernel_ms_serial": trace, "stage_ms_overlapped": stages, "pipeline_ms": k_ms,
                 "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "DFMA probe on this device, this run "
                 "(MEASURED_PEAKS.json has no FP64 vector figure)", "traffic": None}
         if fl and wl.name.startswith("C2") and not args.n_ph and not wl.grid:

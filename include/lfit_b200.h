@@ -121,6 +121,26 @@ long long lfb_launch_count(const lfb_handle *h);
 int lfb_last_stage_ms(lfb_handle *h, float out[6]);
 /* elements + flux of the same call, <0 if none */
 float lfb_last_kernel_ms(lfb_handle *h);
+/* Per-kernel trace (measurement aid, no reference counterpart).  lfb_set_trace(h, 1) brackets
+ * every kernel of the last batch on lane 0 with CUDA events; lfb_last_trace_ms returns the
+ * device time of each in LFB_K_* order (-1 where the kernel did not run) and, in the last
+ * slot, the ballistic-stream kernel on its side stream.  Off by default: the extra event
+ * records cost a few microseconds per batch. */
+enum {
+    LFB_K_WALKER = 0,  /* walker_kernel */
+    LFB_K_JOBCHECK,    /* jobcheck_kernel */
+    LFB_K_ELEM_DISC,   /* elements_kernel<1> */
+    LFB_K_ELEM_WD,     /* elements_kernel<0> */
+    LFB_K_ELEM_DONOR,  /* elements_kernel<3> */
+    LFB_K_ELEM_BS,     /* elements_kernel<2>, with any wait for the stream ODE */
+    LFB_K_PREP,        /* prep_kernel */
+    LFB_K_POSITIONS,   /* positions_kernel */
+    LFB_K_FLUX,        /* flux_kernel */
+    LFB_K_FINISH,      /* finish_kernel */
+    LFB_K_COUNT        /* last_trace_ms slot of stream_kernel (side stream) */
+};
+int lfb_set_trace(lfb_handle *h, int on);
+int lfb_last_trace_ms(lfb_handle *h, float out[LFB_K_COUNT + 1]);
 
 /* Measurement aid (no reference counterpart): sustained FP64 FMA rate of the device in
  * TFLOP/s (FMA = 2), the roofline denominator bench.py reports against. */

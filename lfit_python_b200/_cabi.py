@@ -22,7 +22,11 @@ EXPORTS = (
     "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_get_config", "lfb_set_layout",
     "lfb_set_priors", "lfb_set_lightcurves", "lfb_log_prob", "lfb_calc_flux", "lfb_roche",
     "lfb_launch_count", "lfb_last_kernel_ms", "lfb_last_stage_ms", "lfb_measure_fp64_peak",
+    "lfb_set_trace", "lfb_last_trace_ms",
 )
+TRACE_KERNELS = ("walker_kernel", "jobcheck_kernel", "elements_kernel<1> disc", "elements_kernel<0> white dwarf",
+                 "elements_kernel<3> donor", "elements_kernel<2> strip", "prep_kernel", "positions_kernel",
+                 "flux_kernel", "finish_kernel", "stream_kernel (side stream)")
 
 
 class EngineError(RuntimeError):
@@ -73,6 +77,8 @@ def load():
     lib.lfb_last_kernel_ms.restype = C.c_float
     lib.lfb_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
     lib.lfb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.lfb_set_trace.argtypes = [vp, C.c_int]
+    lib.lfb_last_trace_ms.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = lib
     return lib
 
@@ -144,6 +150,16 @@ class Engine:
         out = (C.c_float * 6)()
         self._check(self._lib.lfb_last_stage_ms(self._h, out), "lfb_last_stage_ms")
         return dict(zip(("walker", "stream", "elements", "flux", "finish", "total"), [float(x) for x in out]))
+
+    def set_trace(self, on=True):
+        """Bracket every kernel of the last batch with CUDA events (see last_trace_ms)."""
+        self._check(self._lib.lfb_set_trace(self._h, int(bool(on))), "lfb_set_trace")
+
+    def last_trace_ms(self):
+        """Device ms of every kernel of the last log_prob batch on lane 0 (needs set_trace)."""
+        out = (C.c_float * len(TRACE_KERNELS))()
+        self._check(self._lib.lfb_last_trace_ms(self._h, out), "lfb_last_trace_ms")
+        return {k: float(x) for k, x in zip(TRACE_KERNELS, out) if x >= 0.0}
 
     def measure_fp64_peak(self, iters=20000):
         """Sustained DFMA rate of this device in TFLOP/s (roofline denominator)."""

@@ -62,8 +62,11 @@ struct DevSamples {
     const int* bins;             // [K * total + n_ecl] per eclipse M + 1 entries (see SampleAxis)
     const int* pos;              // [total * K] sorted position of each (point, node); points in phase order
     const int* pt_index;         // [total] original index of each phase-ordered point
+    const int* dp;               // [K * total] sorted sample -> point * K + node
+    const int2* prange;          // [total] per point: suffix minimum (within its segment) of the first sample of
+                                 // this and all later points, and its own last sample
     const long long* chunk_off;  // [n_ecl + 1] offsets into chunks
-    const int4* chunks;          // per chunk: first point, one past last point, first sample, last sample
+    const int4* chunks;          // per segment: first point, one past last point, first sample, last sample
 };
 
 struct GridCfg {
@@ -379,8 +382,8 @@ struct FluxArgs {
     GridCfg G;
     DevSamples smp;
     int what, flags, mode;  // mode 0: chi-squared, 1: flux curves
-    int Mc;                 // capacity of a chunk in samples
-    int max_chunks;         // chunks of the longest light curve (stride of chi_part)
+    int Ms;                 // capacity of a segment of the sample axis in samples
+    int max_nph;            // points of the longest light curve (stride of the per-point sums)
     int ni_total;           // event records per job: n_wd + n_disc + n_bs + 4 n_donor_q
     long long njobs;
     const double* theta;
@@ -395,7 +398,7 @@ struct FluxArgs {
     long long* wq;          // [njobs][n_wd_rings + n_disc_r + n_bs] fixed-point element weights
     long long* qmom;        // [njobs][n_donor_q][8] fixed-point donor moment parts of each quarter tile
     ulonglong2* ivp;        // [njobs][ni_total] event records (EventRec) of every eclipse / facing interval
-    double* chi_part;       // [njobs][max_chunks]
+    double* chisq_job;      // [njobs] chi-squared of each job (NaN: not evaluated)
     double* flux_tot;       // mode 1: [njobs][n_ph]
     double* flux_comp;      // mode 1 (optional): [4][njobs][n_ph]
 };
@@ -708,45 +711,51 @@ __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ 
     }
 }
 
-// A record matters to the chunk [m0, m1) unless all its events come after the chunk (positions
-// ascend, so the first one decides) or every piece has closed before it (then +w and -w cancel
-// in the chunk's start value).
-__device__ __forceinline__ bool rec_irrelevant(const EventRec& rec, int m0, int m1)
-{
-    if (dec_pos(rec.x, 0) >= m1) return true;
-    const int o1 = dec_pos(rec.x, 2), o2 = dec_pos(rec.y, 1);
-    const int last_close = o2 != kNoEvent ? dec_pos(rec.y, 2) : (o1 != kNoEvent ? dec_pos(rec.y, 0) : dec_pos(rec.x, 1));
-    return last_close < m0;
-}
-
-// flux_kernel: one CTA per (job, chunk of consecutive data points).  The chunk's samples are a
-// contiguous range [m0, m1) of the sorted sample axis.  All interval records of the job are
-// streamed once from L2: events inside the range go to shared-memory event arrays (exact
-// fixed-point atomics), events before it into the start values; a block scan gives the
-// eclipsed / facing sums at every sample, then component mix, exposure quadrature, residuals.
-template <int Mc>
-__global__ void __launch_bounds__(kFluxThreads, Mc <= 768 ? 3 : 2) flux_kernel(const __grid_constant__ FluxArgs A)
+// flux_kernel: one CTA per job -- stages (2)-(4) of the model, one pass over the job's sorted
+// exposure-sample axis in segments of at most Ms samples.
+//
+// Every eclipse / facing interval is a few events (+w where it opens, -w where it closes) on the
+// axis and the component curves are running sums of those events (2^-56 fixed point, so sums do
+// not depend on the order the events arrive in).  Per segment:
+//   * white-dwarf, disc and strip events are dense around the eclipse: shared-memory atomics add
+//     them into three per-sample delta arrays, a block scan turns the deltas into running sums;
+//   * donor events are sparse (one per ~5 samples): they are counting-sorted by sample, their
+//     moment contributions block-scanned in event order, and the running sums kept per event;
+//   * every sample then reads its three tile sums and the donor sums of the last event at or
+//     before it, evaluates the four components, and the exposure quadrature, residuals and a
+//     warp-shuffle + shared-memory chi-squared reduction follow.
+template <int Ms>
+__global__ void __launch_bounds__(kFluxThreads, (Ms <= 2048 ? 2 : 1)) flux_kernel(const __grid_constant__ FluxArgs A)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     const GridCfg& G = A.G;
     constexpr int NW = kFluxThreads / 32;
+    constexpr int RP = Ms / kFluxThreads;  // samples per thread in the block scans
+    constexpr int EC = Ms / 2;             // donor events whose running sums fit at once
+    constexpr int EP = EC / kFluxThreads;  // ... per thread
+    constexpr int ND = kNumArr - 3;        // donor moment arrays
+    static_assert(Ms % (2 * kFluxThreads) == 0, "segment capacity: a multiple of twice the block size");
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    unsigned long long* D = (unsigned long long*)smraw;     // [kNumArr][Mc] events
-    long long* part = (long long*)(D + kNumArr * Mc);       // [kNumArr][kFluxThreads] scan partials
-    double* Fs = (double*)(part + kNumArr * kFluxThreads);  // [nF][Mc] flux per sample
+    const int nF = A.mode ? 4 : 1;
+    const int NDQ = G.n_donor_q;
+    long long* qmom = (long long*)smraw;                              // [NDQ][8] donor moment parts of a quarter tile
+    unsigned long long* Dt = (unsigned long long*)(qmom + 8 * NDQ);  // [3][Ms] tile deltas, then running sums (f64)
+    double* Dsum = (double*)Dt;
+    double* Fs = (double*)(Dt + 3 * Ms);                              // [nF][Ms] flux per sample of the segment
+    double* P = Fs + (size_t)nF * Ms;                                 // [ND][EC] donor running sums after each event
+    int* S = (int*)(P + ND * EC);                                     // [Ms + 1] donor events per sample -> bucket ends
+    unsigned short* ev = (unsigned short*)(S + Ms + 1);               // [6 * 4 NDQ] donor events sorted by sample
     __shared__ double red[NW];
     __shared__ long long wtot[kNumArr][NW];
+    __shared__ long long s_carry[kNumArr], s_next[kNumArr];
+    __shared__ int s_itot[NW];
 
     const long long job = blockIdx.x;
-    const int c = blockIdx.y;
     const long long w = job / A.L.n_ecl;
     const int egather = (int)(job - w * A.L.n_ecl);
     const int e = A.mode ? 0 : egather;
     const long long ch0 = A.smp.chunk_off[e];
-    const int n_chunks = (int)(A.smp.chunk_off[e + 1] - ch0);
-    if (c >= n_chunks) return;
-    const int4 ch = __ldg(A.smp.chunks + ch0 + c);  // first point, one past last point, first sample, last sample
-    const int j0 = ch.x, j1 = ch.y, m0 = ch.z, m1 = ch.w + 1;
+    const int n_seg = (int)(A.smp.chunk_off[e + 1] - ch0);
     const long long lc0 = A.smp.lc_off[e];
     const int n_ph = (int)(A.smp.lc_off[e + 1] - lc0);
     const int K = G.n_quad;
@@ -755,207 +764,309 @@ __global__ void __launch_bounds__(kFluxThreads, Mc <= 768 ? 3 : 2) flux_kernel(c
     if (!job_live(A, W, J)) {
         const bool skipped = J.status == 4 || J.status == 0;
         if (A.mode == 0) {
-            if (tid == 0) A.chi_part[job * A.max_chunks + c] = skipped ? NAN : INFINITY;
+            if (tid == 0) A.chisq_job[job] = skipped ? NAN : INFINITY;
         } else {
-            for (int j = j0 + tid; j < j1; j += kFluxThreads) {
-                const int jo = __ldg(A.smp.pt_index + lc0 + j);
-                A.flux_tot[job * n_ph + jo] = NAN;
+            for (int j = tid; j < n_ph; j += kFluxThreads) {
+                A.flux_tot[job * n_ph + j] = NAN;
                 if (A.flux_comp)
-                    for (int cidx = 0; cidx < 4; ++cidx) A.flux_comp[((long long)cidx * A.njobs + job) * n_ph + jo] = NAN;
+                    for (int cidx = 0; cidx < 4; ++cidx) A.flux_comp[((long long)cidx * A.njobs + job) * n_ph + j] = NAN;
             }
         }
         return;
     }
     const JobConst C = A.jc[job];
-    const long long* wq_wd = A.wq + job * (G.n_wd_rings + G.n_disc_r + G.n_bs);
+    const long long* wq_tab = A.wq + job * (G.n_wd_rings + G.n_disc_r + G.n_bs);
     const EventRec* ivp = A.ivp + job * A.ni_total;
-
-    for (int i = tid; i < kNumArr * Mc; i += kFluxThreads) D[i] = 0ull;
-    __syncthreads();
-
-    // ---- events: stream the job's interval records ----
-    long long base[kNumArr];
-#pragma unroll
-    for (int a = 0; a < kNumArr; ++a) base[a] = 0;
     const int n_tile_iv = G.n_wd + G.n_disc + G.n_bs;
-    // records are fetched four at a time so that their L2 latencies overlap; chunks that lie wholly
-    // before the first or after the last eclipse event of the job have nothing to do here
-    const bool tiles_matter = J.ev_lo < m1 && J.ev_hi >= m0;
-    for (int i0 = tid; tiles_matter && i0 < n_tile_iv; i0 += 4 * kFluxThreads) {
-        EventRec recs[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kFluxThreads;
-            recs[u] = i < n_tile_iv ? ivp[i] : no_events();
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kFluxThreads;
-            const EventRec rec = recs[u];
-            if (rec_irrelevant(rec, m0, m1)) continue;
-            const int widx = __ldg(G.rec_widx + i);
-            const long long wq = __ldg(wq_wd + widx);  // the job's weight table is contiguous: rings, rings, strip
-            const int arr = (widx >= G.n_wd_rings) + (widx >= G.n_wd_rings + G.n_disc_r);
-            unsigned long long* Da = D + arr * Mc;
-            int net = 0;  // intervals of this record that are open when the chunk starts
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
-                if (p < m0) net += (k & 1) ? -1 : 1;
-                else if (p < m1) atomicAdd(Da + (p - m0), (unsigned long long)((k & 1) ? -wq : wq));
-            }
-            const long long b0 = net ? wq : 0;
-            base[0] += arr == 0 ? b0 : 0;
-            base[1] += arr == 1 ? b0 : 0;
-            base[2] += arr == 2 ? b0 : 0;
-        }
-    }
-    if (!(A.flags & LFB_FLAG_SKIP_DONOR)) {
-        const EventRec* dnp = ivp + n_tile_iv;
-        const long long* qm = A.qmom + job * G.n_donor_q * 8;
-        for (int i = tid; i < 4 * G.n_donor_q; i += kFluxThreads) {
-            const EventRec rec = dnp[i];
-            if (rec_irrelevant(rec, m0, m1)) continue;
-            // image i & 1: B = +si ny (else -si ny); i & 2: D = -ci nz (else +ci nz)
-            const longlong2* m8 = (const longlong2*)(qm + 8 * (i >> 2));
-            const longlong2 m01 = __ldg(m8), m23 = __ldg(m8 + 1), m45 = __ldg(m8 + 2), m67 = __ldg(m8 + 3);
-            const bool pb = i & 1, nd = i & 2;
-            long long mo[5];
-            mo[0] = m01.x + (nd ? -m01.y : m01.y);
-            mo[1] = m23.x + (nd ? -m23.y : m23.y);
-            mo[2] = m45.x + (nd ? -m45.y : m45.y);
-            mo[2] = pb ? mo[2] : -mo[2];
-            mo[3] = m67.x;
-            mo[4] = pb ? m67.y : -m67.y;
-            int net = 0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
-                if (p < m0) net += (k & 1) ? -1 : 1;
-                else if (p < m1) {
-#pragma unroll
-                    for (int j = 0; j < 5; ++j)
-                        atomicAdd(D + (3 + j) * Mc + (p - m0), (unsigned long long)((k & 1) ? -mo[j] : mo[j]));
-                }
-            }
-            if (net) {
-#pragma unroll
-                for (int j = 0; j < 5; ++j) base[3 + j] += mo[j];
-            }
-        }
-    }
-    // start values of the running sums: exact integer reduction over the CTA
-#pragma unroll
-    for (int a = 0; a < kNumArr; ++a) {
-        long long v = base[a];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) wtot[a][wid] = v;
-    }
-    __syncthreads();  // also: all events are in D
+    const EventRec* dnp = ivp + n_tile_iv;
+    const bool do_don = !(A.flags & LFB_FLAG_SKIP_DONOR);
+    const int n_img = do_don ? 4 * NDQ : 0;
 
-    // ---- block scan: thread t owns samples m0 + t*R .. +R-1; warp a scans the partials of array a ----
-    constexpr int R = Mc / kFluxThreads;
-#pragma unroll
-    for (int a = 0; a < kNumArr; ++a) {
-        long long v = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) v += (long long)D[a * Mc + tid * R + r];
-        part[a * kFluxThreads + tid] = v;
+    if (do_don) {
+        const longlong2* src = (const longlong2*)(A.qmom + job * NDQ * 8);
+        for (int i = tid; i < 4 * NDQ; i += kFluxThreads) ((longlong2*)qmom)[i] = __ldg(src + i);
     }
-    __syncthreads();
-    for (int a = wid; a < kNumArr; a += NW) {
-        long long* pa = part + a * kFluxThreads + lane * NW;
-        long long loc[NW], t = 0;
-#pragma unroll
-        for (int j = 0; j < NW; ++j) { loc[j] = t; t += pa[j]; }
-        long long inc = t;
+    // moments (1, c, s, c^2, c s) of donor tile image im: the mirror images of a quarter tile differ by the
+    // signs of B (bit 0 set: +) and D (bit 1 set: -)
+    auto add_image = [&](int im, long long sgn, long long* acc) {
+        const long long* m = qmom + 8 * (im >> 2);
+        const long long sb = (im & 1) ? sgn : -sgn, sd = (im & 2) ? -1 : 1;
+        acc[0] += sgn * (m[0] + sd * m[1]);
+        acc[1] += sgn * (m[2] + sd * m[3]);
+        acc[2] += sb * (m[4] + sd * m[5]);
+        acc[3] += sgn * m[6];
+        acc[4] += sb * m[7];
+    };
+    // inclusive warp scan of a 64-bit value
+    auto warp_incl = [&](long long v) {
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            long long u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
+            const long long u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
         }
-        long long exc = inc - t;
-#pragma unroll
-        for (int j = 0; j < NW; ++j) pa[j] = exc + loc[j];
-    }
-    __syncthreads();
-    long long pre[kNumArr];
-#pragma unroll
-    for (int a = 0; a < kNumArr; ++a) {
-        long long v = part[a * kFluxThreads + tid];
-#pragma unroll
-        for (int i = 0; i < NW; ++i) v += wtot[a][i];
-        pre[a] = v;
-    }
-    // ---- per-sample flux ----
-    const double* cosS = A.smp.cosS + lc0 * K;
-    const double* sinS = A.smp.sinS + lc0 * K;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int ml = tid * R + r, m = m0 + ml;
-#pragma unroll
-        for (int a = 0; a < kNumArr; ++a) pre[a] += (long long)D[a * Mc + ml];
-        if (m >= m1) break;
-        const double c0 = __ldg(cosS + m), s0 = __ldg(sinS + m);
-        const double cc = c0 * C.cphi + s0 * C.sphi, ss = s0 * C.cphi - c0 * C.sphi;
-        const double v_wd = 1.0 - (double)pre[0] * kInvFix;
-        const double v_d = 1.0 - (double)pre[1] * kInvFix;
-        const double v_s = 1.0 - (double)pre[2] * kInvFix;
-        const double bm = C.beam_a * cc + C.beam_b * ss + C.beam_d;
-        const double beam = C.fis + (1.0 - C.fis) * (bm > 0.0 ? bm : 0.0);
-        const double dn = (double)pre[3] + (double)pre[4] * cc + (double)pre[5] * ss + (double)pre[6] * (cc * cc) +
-                          (double)pre[7] * (cc * ss);
-        const double fwd = C.f_wd * v_wd, fd = C.f_d * v_d, fs = C.f_s * beam * v_s, frs = C.f_rs * dn;
-        if (A.mode == 0) {
-            Fs[ml] = fwd + fd + fs + frs;
-        } else {
-            Fs[ml] = fwd;
-            Fs[Mc + ml] = fd;
-            Fs[2 * Mc + ml] = fs;
-            Fs[3 * Mc + ml] = frs;
-        }
-    }
+        return v;
+    };
+    double chi = 0.0;
     __syncthreads();
 
-    // ---- exposure quadrature (Simpson over phase +- width), residuals / output ----
-    const int* pos = A.smp.pos + lc0 * K;
-    double chi = 0.0;
-    for (int j = j0 + tid; j < j1; j += kFluxThreads) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int k = 0; k < K; ++k) {
-            const int p = __ldg(pos + j * K + k) - m0;
-            const double qw = G.quad_w[k];
-            acc[0] += qw * Fs[p];
-            if (A.mode) {
-                acc[1] += qw * Fs[Mc + p];
-                acc[2] += qw * Fs[2 * Mc + p];
-                acc[3] += qw * Fs[3 * Mc + p];
+    for (int seg = 0; seg < n_seg; ++seg) {
+        const int4 ch = __ldg(A.smp.chunks + ch0 + seg);  // first point, one past last point, first sample, last sample
+        const int j0 = ch.x, j1 = ch.y, m0 = ch.z, m1 = ch.w + 1, len = m1 - m0;
+        const bool tiles_matter = J.ev_lo < m1 && J.ev_hi >= m0;
+        // the next segment starts at sample m0n of this one (segments may overlap, they leave no gap:
+        // 1 <= m0n <= len); its running sums start from those after sample m0n - 1
+        const int m0n = seg + 1 < n_seg ? __ldg(&A.smp.chunks[ch0 + seg + 1].z) - m0 : -1;
+
+        // ---- 1. events of the segment: tile deltas, donor counts, sums already open at sample 0 ----
+        if (tiles_matter)
+            for (int q = tid; q < 3 * Ms; q += kFluxThreads) Dt[q] = 0ull;
+        for (int q = tid; q < Ms + 1; q += kFluxThreads) S[q] = 0;
+        __syncthreads();
+        long long base[kNumArr];
+#pragma unroll
+        for (int a = 0; a < kNumArr; ++a) base[a] = 0;
+        if (tiles_matter || seg == 0)
+            for (int i0 = tid; i0 < n_tile_iv; i0 += 4 * kFluxThreads) {
+                EventRec recs[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kFluxThreads;
+                    recs[u] = i < n_tile_iv ? ivp[i] : no_events();
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * kFluxThreads;
+                    const EventRec rec = recs[u];
+                    const int first = dec_pos(rec.x, 0);
+                    if (first == kNoEvent || first >= m1) continue;
+                    const int widx = __ldg(G.rec_widx + i);
+                    const long long wq = __ldg(wq_tab + widx);  // the job's weight table: WD rings, disc rings, strip
+                    const int arr = (widx >= G.n_wd_rings) + (widx >= G.n_wd_rings + G.n_disc_r);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
+                        if (p == kAtStart) {
+                            if (seg == 0) base[arr] += wq;
+                        } else if (p >= m0 && p < m1) {
+                            atomicAdd(Dt + arr * Ms + (p - m0), (unsigned long long)((k & 1) ? -wq : wq));
+                        }
+                    }
+                }
+            }
+        for (int i = tid; i < n_img; i += kFluxThreads) {
+            const EventRec rec = dnp[i];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
+                if (p == kNoEvent) break;  // positions ascend, empty fields come last
+                if (p == kAtStart) {
+                    if (seg == 0) add_image(i, 1, base + 3);
+                } else if (p >= m0 && p < m1) {
+                    atomicAdd(&S[p - m0 + 1], 1);
+                }
             }
         }
-        if (A.mode == 0) {
-            const double r = (__ldg(A.smp.y + lc0 + j) - acc[0]) / __ldg(A.smp.ye + lc0 + j);
-            chi += r * r;
-        } else {
-            const int jo = __ldg(A.smp.pt_index + lc0 + j);
-            A.flux_tot[job * n_ph + jo] = acc[0] + acc[1] + acc[2] + acc[3];
-            if (A.flux_comp)
-                for (int cidx = 0; cidx < 4; ++cidx)
-                    A.flux_comp[((long long)cidx * A.njobs + job) * n_ph + jo] = acc[cidx];
+        if (seg == 0) {
+#pragma unroll
+            for (int a = 0; a < kNumArr; ++a) {
+                long long v = base[a];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) wtot[a][wid] = v;
+            }
         }
+        __syncthreads();
+        if (seg == 0 && tid < kNumArr) {
+            long long v = 0;
+            for (int i = 0; i < NW; ++i) v += wtot[tid][i];
+            s_carry[tid] = v;  // running sums just before sample 0
+        }
+        // ---- 2. donor bucket offsets: exclusive scan of the counts (S[x + 1] = events before sample x) ----
+        {
+            int cnt[RP], tot = 0;
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+                cnt[r] = S[1 + tid * RP + r];
+                tot += cnt[r];
+            }
+            int inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            if (lane == 31) s_itot[wid] = inc;
+            __syncthreads();
+            int run = inc - tot;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) run += i < wid ? s_itot[i] : 0;
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+                const int c2 = cnt[r];
+                S[1 + tid * RP + r] = run;  // start of sample (tid*RP + r)'s bucket, used as fill cursor
+                run += c2;
+            }
+        }
+        __syncthreads();
+        // ---- 3. fill the donor buckets; afterwards S[x + 1] = number of events at or before sample x ----
+        for (int i = tid; i < n_img; i += kFluxThreads) {
+            const EventRec rec = dnp[i];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
+                if (p == kNoEvent) break;
+                if (p >= m0 && p < m1) ev[atomicAdd(&S[p - m0 + 1], 1)] = (unsigned short)((i << 1) | (k & 1));
+            }
+        }
+        // ---- 4. tile deltas -> running sums after every sample (block scan, in place, as f64) ----
+        if (tiles_matter) {
+            long long loc[3][RP], tot[3], inc[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                long long t = 0;
+#pragma unroll
+                for (int r = 0; r < RP; ++r) {
+                    t += (long long)Dt[a * Ms + tid * RP + r];
+                    loc[a][r] = t;
+                }
+                tot[a] = t;
+                inc[a] = warp_incl(t);
+                if (lane == 31) wtot[a][wid] = inc[a];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                long long before = s_carry[a] + inc[a] - tot[a];
+#pragma unroll
+                for (int i = 0; i < NW - 1; ++i) before += i < wid ? wtot[a][i] : 0;
+#pragma unroll
+                for (int r = 0; r < RP; ++r) {
+                    const long long v = before + loc[a][r];
+                    if (tid * RP + r == m0n - 1) s_next[a] = v;
+                    Dsum[a * Ms + tid * RP + r] = (double)v;
+                }
+            }
+        } else if (tid < 3) {
+            s_next[tid] = s_carry[tid];
+        }
+        __syncthreads();
+        // ---- 5. donor events -> running sums after every event, EC events at a time; 6. the samples ----
+        const int n_ev = S[len];
+        const int ev_next = m0n > 0 ? S[m0n] : 0;  // events at or before sample m0n - 1
+        if (tid < ND && ev_next == 0) s_next[3 + tid] = s_carry[3 + tid];
+        long long dcar[ND];  // donor sums before the first event of the round
+#pragma unroll
+        for (int a = 0; a < ND; ++a) dcar[a] = s_carry[3 + a];
+        for (int r0 = 0; r0 == 0 || r0 < n_ev; r0 += EC) {
+            if (r0 < n_ev) {
+                long long loc[ND][EP], tot[ND], inc[ND];
+#pragma unroll
+                for (int a = 0; a < ND; ++a) tot[a] = 0;
+#pragma unroll
+                for (int q = 0; q < EP; ++q) {
+                    const int x = r0 + tid * EP + q;
+                    if (x < n_ev) {
+                        const int word = ev[x];
+                        add_image(word >> 1, (word & 1) ? -1 : 1, tot);
+                    }
+#pragma unroll
+                    for (int a = 0; a < ND; ++a) loc[a][q] = tot[a];
+                }
+#pragma unroll
+                for (int a = 0; a < ND; ++a) {
+                    inc[a] = warp_incl(tot[a]);
+                    if (lane == 31) wtot[3 + a][wid] = inc[a];
+                }
+                __syncthreads();
+#pragma unroll
+                for (int a = 0; a < ND; ++a) {
+                    long long before = dcar[a] + inc[a] - tot[a], all = dcar[a];
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) {
+                        const long long t = wtot[3 + a][i];
+                        before += i < wid ? t : 0;
+                        all += t;
+                    }
+#pragma unroll
+                    for (int q = 0; q < EP; ++q) {
+                        const int x = r0 + tid * EP + q;
+                        const long long v = before + loc[a][q];
+                        if (x < n_ev) {
+                            P[a * EC + tid * EP + q] = (double)v;
+                            if (x == ev_next - 1) s_next[3 + a] = v;
+                        }
+                    }
+                    dcar[a] = all;
+                }
+                __syncthreads();
+            }
+            // ---- 6. components at every sample whose last event lies in this round ----
+            for (int p = tid; p < len; p += kFluxThreads) {
+                const int idx = S[p + 1];
+                if (!((idx > r0 && idx <= r0 + EC) || (idx == 0 && r0 == 0))) continue;
+                double t3[3], dm[ND];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) t3[a] = tiles_matter ? Dsum[a * Ms + p] : (double)s_carry[a];
+#pragma unroll
+                for (int a = 0; a < ND; ++a) dm[a] = idx == 0 ? (double)s_carry[3 + a] : P[a * EC + idx - r0 - 1];
+                const int m = m0 + p;
+                const double c0 = __ldg(A.smp.cosS + lc0 * K + m), s0 = __ldg(A.smp.sinS + lc0 * K + m);
+                const double cc = c0 * C.cphi + s0 * C.sphi, ss = s0 * C.cphi - c0 * C.sphi;
+                const double bm = C.beam_a * cc + C.beam_b * ss + C.beam_d;
+                const double beam = C.fis + (1.0 - C.fis) * (bm > 0.0 ? bm : 0.0);
+                const double dn = dm[0] + dm[1] * cc + dm[2] * ss + dm[3] * (cc * cc) + dm[4] * (cc * ss);
+                const double f0 = C.f_wd * (1.0 - t3[0] * kInvFix);
+                const double f1 = C.f_d * (1.0 - t3[1] * kInvFix);
+                const double f2 = C.f_s * beam * (1.0 - t3[2] * kInvFix);
+                const double f3 = C.f_rs * dn;
+                if (A.mode == 0) {
+                    Fs[p] = f0 + f1 + f2 + f3;
+                } else {
+                    Fs[p] = f0;
+                    Fs[Ms + p] = f1;
+                    Fs[2 * Ms + p] = f2;
+                    Fs[3 * Ms + p] = f3;
+                }
+            }
+            __syncthreads();
+        }
+        if (tid < kNumArr && seg + 1 < n_seg) s_carry[tid] = s_next[tid];
+        // ---- 7. exposure quadrature (Simpson over phase +- width), residuals / output ----
+        for (int j = j0 + tid; j < j1; j += kFluxThreads) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int k = 0; k < K; ++k) {
+                const int q = __ldg(A.smp.pos + (lc0 + j) * K + k) - m0;
+                const double qw = G.quad_w[k];
+                acc[0] += qw * Fs[q];
+                if (A.mode) {
+                    acc[1] += qw * Fs[Ms + q];
+                    acc[2] += qw * Fs[2 * Ms + q];
+                    acc[3] += qw * Fs[3 * Ms + q];
+                }
+            }
+            if (A.mode == 0) {
+                const double r = (__ldg(A.smp.y + lc0 + j) - acc[0]) / __ldg(A.smp.ye + lc0 + j);
+                chi += r * r;
+            } else {
+                const int jo = __ldg(A.smp.pt_index + lc0 + j);
+                A.flux_tot[job * n_ph + jo] = acc[0] + acc[1] + acc[2] + acc[3];
+                if (A.flux_comp)
+                    for (int cidx = 0; cidx < 4; ++cidx)
+                        A.flux_comp[((long long)cidx * A.njobs + job) * n_ph + jo] = acc[cidx];
+            }
+        }
+        __syncthreads();
     }
     if (A.mode == 0) {
         chi = block_sum<kFluxThreads>(chi, red);
-        if (tid == 0) A.chi_part[job * A.max_chunks + c] = chi;
+        if (tid == 0) A.chisq_job[job] = chi;
     }
 }
 
 // ---------------------------------------------------------------- finish_kernel
-// chi^2 of every job from its chunks (fixed order: deterministic), then
 // Node.ln_prob = ln_prior + sum of -chi^2/2 with the -inf rules (model.py:476-498)
-__global__ void finish_kernel(int what, int n_ecl, long long n, int max_chunks, const long long* __restrict__ chunk_off,
-                              const WalkerScal* __restrict__ ws, const double* __restrict__ chi_part,
-                              double* __restrict__ chisq, double* __restrict__ out)
+__global__ void finish_kernel(int what, int n_ecl, long long n, const WalkerScal* __restrict__ ws,
+                              const double* __restrict__ chisq_job, double* __restrict__ chisq, double* __restrict__ out)
 {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n) return;
@@ -963,9 +1074,7 @@ __global__ void finish_kernel(int what, int n_ecl, long long n, int max_chunks, 
     double like = 0.0;
     if (what != LFB_LN_PRIOR) {
         for (int e = 0; e < n_ecl; ++e) {
-            const int nc = (int)(chunk_off[e + 1] - chunk_off[e]);
-            double chi = 0.0;
-            for (int c = 0; c < nc; ++c) chi += chi_part[(w * n_ecl + e) * max_chunks + c];
+            double chi = chisq_job[w * n_ecl + e];
             // NaN marks "not evaluated" (prior veto); a NaN model is +inf (CVModel.py:163-171)
             const bool skipped = what == LFB_LN_PROB && !(lnp > -INFINITY);
             if (isnan(chi) && !skipped) chi = INFINITY;

@@ -44,13 +44,13 @@ struct DevBuf {
 
 // Sorted exposure samples of a set of light curves (device copies)
 struct SampleSet {
-    DevBuf lc_off, y, ye, S, cosS, sinS, bins, pos, pt_index, chunk_off, chunks;
+    DevBuf lc_off, y, ye, S, cosS, sinS, bins, pos, pt_index, dp, prange, chunk_off, chunks;
     int max_chunks = 1;
     int max_nph = 0;
     long long total = 0;
     void release()
     {
-        DevBuf* b[] = {&lc_off, &y, &ye, &S, &cosS, &sinS, &bins, &pos, &pt_index, &chunk_off, &chunks};
+        DevBuf* b[] = {&lc_off, &y, &ye, &S, &cosS, &sinS, &bins, &pos, &pt_index, &dp, &prange, &chunk_off, &chunks};
         for (DevBuf* x : b) x->release();
     }
     DevSamples view()
@@ -65,6 +65,8 @@ struct SampleSet {
         v.bins = bins.as<int>();
         v.pos = pos.as<int>();
         v.pt_index = pt_index.as<int>();
+        v.dp = dp.as<int>();
+        v.prange = prange.as<int2>();
         v.chunk_off = chunk_off.as<long long>();
         v.chunks = chunks.as<int4>();
         return v;
@@ -80,6 +82,8 @@ struct Lane {
     cudaStream_t st = nullptr, side = nullptr;  // side: the serial stream ODE beside the element solves
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr, done_ev = nullptr;
     cudaEvent_t ev[ST_COUNT + 1] = {};
+    cudaEvent_t kev[LFB_K_COUNT + 1] = {}, sev[2] = {};  // per-kernel trace (lfb_set_trace), side-stream pair
+    bool kev_set[LFB_K_COUNT + 1] = {};
     DevBuf ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, qmom, ivp, chi_part;
     cudaError_t create()
     {
@@ -91,6 +95,10 @@ struct Lane {
         if ((e = cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
         for (int i = 0; i <= ST_COUNT; ++i)
             if ((e = cudaEventCreate(&ev[i])) != cudaSuccess) return e;
+        for (int i = 0; i <= LFB_K_COUNT; ++i)
+            if ((e = cudaEventCreate(&kev[i])) != cudaSuccess) return e;
+        for (int i = 0; i < 2; ++i)
+            if ((e = cudaEventCreate(&sev[i])) != cudaSuccess) return e;
         return cudaSuccess;
     }
     void destroy()
@@ -99,6 +107,10 @@ struct Lane {
         for (DevBuf* x : b) x->release();
         for (int i = 0; i <= ST_COUNT; ++i)
             if (ev[i]) cudaEventDestroy(ev[i]);
+        for (int i = 0; i <= LFB_K_COUNT; ++i)
+            if (kev[i]) cudaEventDestroy(kev[i]);
+        for (int i = 0; i < 2; ++i)
+            if (sev[i]) cudaEventDestroy(sev[i]);
         if (fork_ev) cudaEventDestroy(fork_ev);
         if (join_ev) cudaEventDestroy(join_ev);
         if (done_ev) cudaEventDestroy(done_ev);
@@ -118,11 +130,12 @@ struct lfb_handle {
     Lane lanes[kLanes];
     cudaEvent_t enter_ev = nullptr, t0_ev = nullptr, t1_ev = nullptr;
     bool ev_valid = false;
+    bool trace = false;  // lfb_set_trace
     std::string err;
     long long launches = 0;
     int sm_count = 148;
     int max_smem = 0;
-    int Mc = 512;
+    int Mc = 3072, Mc_flux = 2048;  // segment capacity of the flux kernel: chi-squared mode / flux-curve mode
     long long max_jobs_per_batch = 131072;
     int n_lanes = kLanes;  // LFB_LANES=1 serialises the batches (clean per-stage timings for profiling)
     // layout
@@ -182,15 +195,16 @@ static int donor_ring_count(int nth, int k)
 // by all walkers: order the points in (wrapped) phase, merge their K exposure samples, wrap to
 // [-0.5, 0.5], sort, record where each (point, node) landed, build the bin table of the sorted
 // axis, and cut the points into chunks whose samples span at most Mc consecutive sorted samples.
-static int build_samples(lfb_handle* h, SampleSet& ss, int n_ecl, const long long* off, const double* phase,
+static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const long long* off, const double* phase,
                          const double* width, const double* y, const double* ye)
 {
     const GridCfg& G = h->grid;
-    const int K = G.n_quad, Mc = h->Mc;
+    const int K = G.n_quad;
     const long long total = off[n_ecl];
     std::vector<double> S((size_t)total * K), cS((size_t)total * K), sS((size_t)total * K);
     std::vector<double> ys((size_t)total), yes((size_t)total);
-    std::vector<int> pos((size_t)total * K), bins((size_t)total * K + n_ecl, 0), pt_index((size_t)total);
+    std::vector<int> pos((size_t)total * K), bins((size_t)total * K + n_ecl, 0), pt_index((size_t)total), dp((size_t)total * K);
+    std::vector<int2> prange((size_t)total);
     std::vector<long long> chunk_off(n_ecl + 1, 0);
     std::vector<int4> chunks;
     int max_nph = 0, max_chunks = 1;
@@ -233,6 +247,7 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int n_ecl, const long lon
             cS[o * K + r] = cos(kTwoPi * raw[src]);
             sS[o * K + r] = sin(kTwoPi * raw[src]);
             pos[o * K + src] = r;
+            dp[o * K + r] = src;  // = point * K + node
         }
         // bin table: first sample at or after the start of each of M equal phase bins
         if (M > 0) {
@@ -274,6 +289,31 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int n_ecl, const long lon
             ++nch;
             j0 = j1;
         }
+        // the flux kernel carries running sums from one segment to the next: the sample ranges must
+        // start at sample 0 and leave no gap (they may overlap by a few samples)
+        for (int k = 0; k < nch; ++k) {
+            int4& cur = chunks[chunks.size() - nch + k];
+            const int want = k == 0 ? 0 : chunks[chunks.size() - nch + k - 1].w + 1;
+            if (cur.z > want) cur.z = want;
+            if (cur.w - cur.z + 1 > Mc) {
+                h->err = "set_lightcurves: exposures overlap too irregularly for the segmented sample axis";
+                return LFB_EINVAL;
+            }
+        }
+        // per point: last sample, and the suffix minimum of the first samples inside its segment
+        for (int k = 0; k < nch; ++k) {
+            const int4 cur = chunks[chunks.size() - nch + k];
+            int sfx = cur.w + 1;
+            for (int j = cur.y - 1; j >= cur.x; --j) {
+                int lo = M, hi = -1;
+                for (int q = 0; q < K; ++q) {
+                    lo = std::min(lo, pos[o * K + j * K + q]);
+                    hi = std::max(hi, pos[o * K + j * K + q]);
+                }
+                sfx = std::min(sfx, lo);
+                prange[o + j] = make_int2(sfx, hi);
+            }
+        }
         chunk_off[e + 1] = chunk_off[e] + nch;
         max_chunks = std::max(max_chunks, nch);
     }
@@ -288,6 +328,8 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int n_ecl, const long lon
     if ((rc = upload(h, ss.bins, bins.data(), sizeof(int) * bins.size()))) return rc;
     if ((rc = upload(h, ss.pos, pos.data(), sizeof(int) * pos.size()))) return rc;
     if ((rc = upload(h, ss.pt_index, pt_index.data(), sizeof(int) * pt_index.size()))) return rc;
+    if ((rc = upload(h, ss.dp, dp.data(), sizeof(int) * dp.size()))) return rc;
+    if ((rc = upload(h, ss.prange, prange.data(), sizeof(int2) * prange.size()))) return rc;
     if ((rc = upload(h, ss.chunk_off, chunk_off.data(), sizeof(long long) * chunk_off.size()))) return rc;
     if ((rc = upload(h, ss.chunks, chunks.data(), sizeof(int4) * chunks.size()))) return rc;
     CK(cudaStreamSynchronize(h->stream));  // the host vectors die here
@@ -297,9 +339,14 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int n_ecl, const long lon
     return LFB_OK;
 }
 
-static size_t flux_smem_bytes(int Mc, int nF)
+// shared memory of flux_kernel<Ms>: donor moment parts, three tile delta arrays, flux per sample,
+// donor bucket offsets and sorted donor events (worst case 6 per image)
+static size_t flux_smem_bytes(const GridCfg& G, int Ms, int nF)
 {
-    return 8 * ((size_t)kNumArr * Mc + (size_t)kNumArr * kFluxThreads + (size_t)nF * Mc);
+    const size_t ndq = (size_t)G.n_donor_q;
+    size_t b = 64 * ndq + 24 * (size_t)Ms + 8 * (size_t)nF * Ms + 8 * 5 * ((size_t)Ms / 2) + 4 * ((size_t)Ms + 1) +
+               2 * 6 * 4 * ndq;
+    return (b + 15) & ~(size_t)15;
 }
 
 // One pass of the pipeline over walkers [0, n) (device pointers, one batch).
@@ -317,16 +364,30 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
     CK(ln.disc_io.reserve(sizeof(double2) * (size_t)njobs * G.n_disc_half));
     CK(ln.bs_io.reserve(sizeof(double2) * (size_t)njobs * G.n_bs));
     CK(ln.bs_b.reserve(sizeof(double) * (size_t)njobs * G.n_bs));
+    const bool trace = record && h->trace;
+    if (trace)
+        for (int i = 0; i <= LFB_K_COUNT; ++i) ln.kev_set[i] = false;
+#define KREC(i)                                      \
+    do {                                             \
+        if (trace) {                                 \
+            CK(cudaEventRecord(ln.kev[i], st));      \
+            ln.kev_set[i] = true;                    \
+        }                                            \
+    } while (0)
     if (record) CK(cudaEventRecord(ln.ev[ST_WALKER], st));
+    KREC(LFB_K_WALKER);
     walker_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, what, flags, n, d_theta, ln.ws.as<WalkerScal>());
     if (record) CK(cudaEventRecord(ln.ev[ST_STREAM], st));
+    KREC(LFB_K_JOBCHECK);
     jobcheck_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, st>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
                                                                       ln.js.as<JobScal>());
     // fork: the ballistic-stream ODE (one serial integration per job) runs beside the element solves
     CK(cudaEventRecord(ln.fork_ev, st));
     CK(cudaStreamWaitEvent(ln.side, ln.fork_ev, 0));
+    if (trace) CK(cudaEventRecord(ln.sev[0], ln.side));
     stream_kernel<<<(unsigned)((njobs + 63) / 64), 64, 0, ln.side>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
                                                                       ln.js.as<JobScal>());
+    if (trace) CK(cudaEventRecord(ln.sev[1], ln.side));
     CK(cudaEventRecord(ln.join_ev, ln.side));
     h->launches += 3;
     if (record) CK(cudaEventRecord(ln.ev[ST_ELEMENTS], st));
@@ -351,18 +412,22 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
             return (unsigned)((units * padded + kElemThreads - 1) / kElemThreads);
         };
         if (!(flags & LFB_FLAG_SKIP_DISC)) {
+            KREC(LFB_K_ELEM_DISC);
             elements_kernel<1><<<blocks(njobs, G.n_disc_half), kElemThreads, 0, st>>>(E);
             h->launches++;
         }
         if (!(flags & LFB_FLAG_SKIP_WD)) {
+            KREC(LFB_K_ELEM_WD);
             elements_kernel<0><<<blocks(n, G.n_wd_half), kElemThreads, 0, st>>>(E);
             h->launches++;
         }
         if (!(flags & LFB_FLAG_SKIP_DONOR)) {
+            KREC(LFB_K_ELEM_DONOR);
             elements_kernel<3><<<blocks(n, G.n_donor_q), kElemThreads, 0, st>>>(E);
             h->launches++;
         }
         CK(cudaStreamWaitEvent(st, ln.join_ev, 0));  // join: the strip needs the impact point
+        KREC(LFB_K_ELEM_BS);  // includes any wait for the stream ODE on the side stream
         if (!(flags & LFB_FLAG_SKIP_BS)) {
             elements_kernel<2><<<blocks(njobs, G.n_bs), kElemThreads, 0, st>>>(E);
             h->launches++;
@@ -375,8 +440,9 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         A.what = what;
         A.flags = flags;
         A.mode = mode;
-        A.Mc = h->Mc;
-        A.max_chunks = ss.max_chunks;
+        const int Ms = mode ? h->Mc_flux : h->Mc;
+        A.Ms = Ms;
+        A.max_nph = ss.max_nph;
         A.ni_total = G.n_wd + G.n_disc + G.n_bs + 4 * G.n_donor_q;
         A.njobs = njobs;
         A.theta = d_theta;
@@ -392,31 +458,36 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         CK(ln.wq.reserve(sizeof(long long) * (size_t)njobs * nwq));
         CK(ln.qmom.reserve(sizeof(long long) * (size_t)njobs * G.n_donor_q * 8));
         CK(ln.ivp.reserve(sizeof(EventRec) * (size_t)njobs * A.ni_total));
-        CK(ln.chi_part.reserve(sizeof(double) * (size_t)njobs * ss.max_chunks));
+        CK(ln.chi_part.reserve(sizeof(double) * (size_t)njobs));
         A.jc = ln.jc.as<JobConst>();
         A.wq = ln.wq.as<long long>();
         A.qmom = ln.qmom.as<long long>();
         A.ivp = ln.ivp.as<EventRec>();
-        A.chi_part = ln.chi_part.as<double>();
+        A.chisq_job = ln.chi_part.as<double>();
         A.flux_tot = d_tot;
         A.flux_comp = d_comp;
+        KREC(LFB_K_PREP);
         prep_kernel<<<(unsigned)((njobs + 3) / 4), 128, 0, st>>>(A);
         const long long per_job = ((G.n_wd_half + G.n_disc_half + G.n_bs + G.n_donor_q) + 31) & ~31;
+        KREC(LFB_K_POSITIONS);
         positions_kernel<<<(unsigned)((njobs * per_job + 127) / 128), 128, 0, st>>>(A);
-        const size_t smem = flux_smem_bytes(h->Mc, mode ? 4 : 1);
-        const dim3 fgrid((unsigned)njobs, (unsigned)ss.max_chunks);
-#define LFB_LAUNCH_FLUX(MC)                                                                                     \
+        const size_t smem = flux_smem_bytes(G, Ms, mode ? 4 : 1);
+        if (smem > (size_t)h->max_smem - 2048)
+            return fail(h, LFB_EINVAL, "light curve too long / surface grid too dense for the flux kernel's shared memory");
+        if (4 * G.n_donor_q > 32767) return fail(h, LFB_EINVAL, "donor grid too dense (15-bit image index)");
+        const dim3 fgrid((unsigned)njobs);
+        KREC(LFB_K_FLUX);
+#define LFB_LAUNCH_FLUX(MS)                                                                                     \
     do {                                                                                                        \
-        CK(cudaFuncSetAttribute(flux_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        flux_kernel<MC><<<fgrid, kFluxThreads, smem, st>>>(A);                                                  \
+        CK(cudaFuncSetAttribute(flux_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        flux_kernel<MS><<<fgrid, kFluxThreads, smem, st>>>(A);                                                  \
     } while (0)
-        switch (h->Mc) {
-        case 256: LFB_LAUNCH_FLUX(256); break;
-        case 512: LFB_LAUNCH_FLUX(512); break;
-        case 768: LFB_LAUNCH_FLUX(768); break;
+        switch (Ms) {
         case 1024: LFB_LAUNCH_FLUX(1024); break;
+        case 1536: LFB_LAUNCH_FLUX(1536); break;
         case 2048: LFB_LAUNCH_FLUX(2048); break;
-        default: return fail(h, LFB_EINVAL, "unsupported chunk capacity");
+        case 3072: LFB_LAUNCH_FLUX(3072); break;
+        default: return fail(h, LFB_EINVAL, "unsupported segment capacity");
         }
 #undef LFB_LAUNCH_FLUX
         h->launches += 3;
@@ -425,15 +496,17 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         if (record) CK(cudaEventRecord(ln.ev[ST_FLUX], st));
     }
     if (record) CK(cudaEventRecord(ln.ev[ST_FINISH], st));
+    KREC(LFB_K_FINISH);
     if (d_out || d_chi) {
-        finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(what, L.n_ecl, n, ss.max_chunks,
-                                                                  ss.chunk_off.as<long long>(), ln.ws.as<WalkerScal>(),
+        finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(what, L.n_ecl, n, ln.ws.as<WalkerScal>(),
                                                                   ln.chi_part.as<double>(), d_chi, d_out);
         h->launches++;
     }
     if (record) {
         CK(cudaEventRecord(ln.ev[ST_COUNT], st));
     }
+    KREC(LFB_K_COUNT);
+#undef KREC
     CK(cudaGetLastError());
     return LFB_OK;
 }
@@ -559,15 +632,16 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
             G.quad_w[k] = cw / (3.0 * nint);
         }
     }
-    // capacity of a flux-kernel chunk in samples (multiple of kFluxThreads); LFB_MC overrides for tuning
-    h->Mc = 768;
+    // capacity of a flux-kernel segment in samples (LFB_MS overrides the chi-squared one for tuning)
+    h->Mc = 1536;
+    h->Mc_flux = 1024;
     if (const char* env = getenv("LFB_LANES")) {
         int v = atoi(env);
         if (v >= 1 && v <= kLanes) h->n_lanes = v;
     }
-    if (const char* env = getenv("LFB_MC")) {
+    if (const char* env = getenv("LFB_MS")) {
         int v = atoi(env);
-        if (v == 256 || v == 512 || v == 768 || v == 1024 || v == 2048) h->Mc = v;
+        if (v == 1024 || v == 1536 || v == 2048 || v == 3072) h->Mc = v;
     }
     *out = h;
     return LFB_OK;
@@ -622,6 +696,36 @@ int lfb_last_stage_ms(lfb_handle* h, float out[6])
     if (cudaEventElapsedTime(&out[5], h->t0_ev, h->t1_ev) != cudaSuccess) {
         cudaGetLastError();
         return fail(h, LFB_ECUDA, "stage events not complete: synchronise the stream first");
+    }
+    return LFB_OK;
+}
+
+int lfb_set_trace(lfb_handle* h, int on)
+{
+    if (!h) return LFB_EINVAL;
+    h->trace = on != 0;
+    return LFB_OK;
+}
+
+int lfb_last_trace_ms(lfb_handle* h, float out[LFB_K_COUNT + 1])
+{
+    if (!h || !out) return LFB_EINVAL;
+    for (int i = 0; i <= LFB_K_COUNT; ++i) out[i] = -1.0f;
+    if (!h->ev_valid || !h->trace) return fail(h, LFB_ESTATE, "no trace: lfb_set_trace(h, 1), then lfb_log_prob");
+    Lane& ln = h->lanes[0];
+    // a kernel's slot runs from its own record to the next one that was recorded
+    for (int i = 0; i < LFB_K_COUNT; ++i) {
+        if (!ln.kev_set[i]) continue;
+        int nx = i + 1;
+        while (nx <= LFB_K_COUNT && !ln.kev_set[nx]) ++nx;
+        if (nx > LFB_K_COUNT || cudaEventElapsedTime(&out[i], ln.kev[i], ln.kev[nx]) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, LFB_ECUDA, "trace events not complete: synchronise the stream first");
+        }
+    }
+    if (cudaEventElapsedTime(&out[LFB_K_COUNT], ln.sev[0], ln.sev[1]) != cudaSuccess) {
+        cudaGetLastError();
+        out[LFB_K_COUNT] = -1.0f;
     }
     return LFB_OK;
 }
@@ -698,7 +802,7 @@ int lfb_set_lightcurves(lfb_handle* h, int n_ecl, const long long* off, const do
     for (int e = 0; e < n_ecl; ++e)
         if (off[e + 1] < off[e] || off[e + 1] - off[e] > 100000000LL) return fail(h, LFB_EINVAL, "set_lightcurves: offsets must ascend");
     CK(cudaSetDevice(h->device));
-    int rc = build_samples(h, h->lc, n_ecl, off, phase, width, y, ye);
+    int rc = build_samples(h, h->lc, h->Mc, n_ecl, off, phase, width, y, ye);
     if (rc) return rc;
     h->have_lc = true;
     return LFB_OK;
@@ -771,9 +875,13 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
     const long long per = (n + nbatch - 1) / nbatch;
     int used = 0;
     long long b = 0;
+    // one lane: run on the caller's own stream (no cross-stream hand-off)
+    const bool inline_lane = h->n_lanes == 1;
+    cudaStream_t lane0_st = h->lanes[0].st;
+    if (inline_lane) h->lanes[0].st = st;
     for (long long w0 = 0; w0 < n; w0 += per, ++b) {
         Lane& ln = h->lanes[b % h->n_lanes];
-        if (b < h->n_lanes) {
+        if (b < h->n_lanes && !inline_lane) {
             CK(cudaStreamWaitEvent(ln.st, h->enter_ev, 0));
             used = (int)b + 1;
         }
@@ -781,8 +889,12 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
         const bool last_on_lane0 = (b % h->n_lanes) == 0 && w0 + (long long)h->n_lanes * per >= n;
         int rc = run_batch(h, ln, L, h->lc, what, 0, 0, nb, d_theta + w0 * h->ndim, d_out + w0, d_chi + w0 * h->n_ecl,
                            nullptr, nullptr, last_on_lane0);
-        if (rc) return rc;
+        if (rc) {
+            h->lanes[0].st = lane0_st;
+            return rc;
+        }
     }
+    h->lanes[0].st = lane0_st;
     for (int i = 0; i < used; ++i) {
         CK(cudaEventRecord(h->lanes[i].done_ev, h->lanes[i].st));
         CK(cudaStreamWaitEvent(st, h->lanes[i].done_ev, 0));
@@ -817,7 +929,7 @@ int lfb_calc_flux(lfb_handle* h, long long n_sets, const double* pars, int npars
     std::vector<int> gather(LFB_NPAR, 0);
     for (int k = 0; k < LFB_NPAR; ++k) gather[k] = k < npars ? k : 0;
     long long off[2] = {0, n_ph};
-    int rc = build_samples(h, h->cf_lc, 1, off, phase, width, nullptr, nullptr);
+    int rc = build_samples(h, h->cf_lc, h->Mc_flux, 1, off, phase, width, nullptr, nullptr);
     if (rc) return rc;
     CK(h->cf_gather.reserve(sizeof(int) * LFB_NPAR));
     CK(cudaMemcpyAsync(h->cf_gather.p, gather.data(), sizeof(int) * LFB_NPAR, cudaMemcpyHostToDevice, st));

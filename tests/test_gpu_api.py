@@ -258,6 +258,13 @@ def test_device_resident_buffers(engine):
     assert np.array_equal(out.cpu().numpy(), ref)
     ms = engine.last_stage_ms()
     assert ms["total"] > 0 and engine.launch_count > 0
+    engine.set_trace(True)
+    try:
+        assert np.array_equal(engine.log_prob(theta), ref)
+        tr = engine.last_trace_ms()
+        assert tr["flux_kernel"] > 0 and tr["elements_kernel<1> disc"] > 0 and len(tr) == 11
+    finally:
+        engine.set_trace(False)
 
 
 def test_device_resident_sampler_keeps_its_books(engine):
