@@ -74,7 +74,8 @@ struct GridCfg {
     int n_wd_half, n_disc_half;  // elements solved (the other half follows by the y -> -y mirror)
     double donor_ulimb, donor_gdexp;
     const int* donor_ring_off;  // [n_donor_th + 1] offsets of each ring's quarter tiles
-    const unsigned short* rec_widx;  // [n_wd + n_disc + n_bs] index of each tile record's weight in the job's weight table
+    const unsigned short* rec_widx;  // [n_wd + n_disc + n_bs] index of each stored tile record's weight in the job's weight table
+    const int* rec_slot;             // [n_wd + n_disc + n_bs] where tile record i is stored: neighbouring tiles far apart
     const int* disc_order;      // [n_disc_half] disc elements ordered along the line of centres, so that the
                                 // threads of a warp solve elements of the same kind (deep / shallow / never eclipsed)
     double quad_off[kMaxQuad], quad_w[kMaxQuad];
@@ -654,13 +655,13 @@ __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ 
             }
             const bool ecl = io.y > io.x;
             const EventRec r0 = ecl ? interval_pieces(X, io.x + phi0w, io.y + phi0w) : none;
-            ivp[i0] = r0;
+            ivp[__ldg(G.rec_slot + i0)] = r0;
             lo = dec_pos(r0.x, 0);
             hi = rec_last_close(r0);
             // the y -> -y image is eclipsed from -egress to -ingress
             if (mirror) {
                 const EventRec r1 = ecl ? interval_pieces(X, -io.y + phi0w, -io.x + phi0w) : none;
-                ivp[i0 + 1] = r1;
+                ivp[__ldg(G.rec_slot + i0 + 1)] = r1;
                 lo = min(lo, dec_pos(r1.x, 0));
                 hi = max(hi, rec_last_close(r1));
             }
@@ -724,25 +725,24 @@ __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ 
 //   * every sample then reads its three tile sums and the donor sums of the last event at or
 //     before it, evaluates the four components, and the exposure quadrature, residuals and a
 //     warp-shuffle + shared-memory chi-squared reduction follow.
-template <int Ms>
-__global__ void __launch_bounds__(kFluxThreads, (Ms <= 2048 ? 2 : 1)) flux_kernel(const __grid_constant__ FluxArgs A)
+template <int Ms, int EC, int CTAS>
+__global__ void __launch_bounds__(kFluxThreads, CTAS) flux_kernel(const __grid_constant__ FluxArgs A)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     const GridCfg& G = A.G;
     constexpr int NW = kFluxThreads / 32;
     constexpr int RP = Ms / kFluxThreads;  // samples per thread in the block scans
-    constexpr int EC = Ms / 2;             // donor events whose running sums fit at once
-    constexpr int EP = EC / kFluxThreads;  // ... per thread
+    constexpr int EP = EC / kFluxThreads;  // donor events per thread (EC = events whose running sums fit at once)
     constexpr int ND = kNumArr - 3;        // donor moment arrays
-    static_assert(Ms % (2 * kFluxThreads) == 0, "segment capacity: a multiple of twice the block size");
+    static_assert(Ms % kFluxThreads == 0 && EC % kFluxThreads == 0, "capacities: multiples of the block size");
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nF = A.mode ? 4 : 1;
     const int NDQ = G.n_donor_q;
     long long* qmom = (long long*)smraw;                              // [NDQ][8] donor moment parts of a quarter tile
-    unsigned long long* Dt = (unsigned long long*)(qmom + 8 * NDQ);  // [3][Ms] tile deltas, then running sums (f64)
-    double* Dsum = (double*)Dt;
-    double* Fs = (double*)(Dt + 3 * Ms);                              // [nF][Ms] flux per sample of the segment
-    double* P = Fs + (size_t)nF * Ms;                                 // [ND][EC] donor running sums after each event
+    unsigned long long* Dt = (unsigned long long*)(qmom + 8 * NDQ);  // [3][Ms] tile deltas, then running sums (f64),
+    double* Dsum = (double*)Dt;                                       // then, sample by sample, ...
+    double* Fs = Dsum;                                                // [nF][Ms] flux per sample of the segment
+    double* P = Dsum + (size_t)(nF > 3 ? nF : 3) * Ms;                // [ND][EC] donor running sums after each event
     int* S = (int*)(P + ND * EC);                                     // [Ms + 1] donor events per sample -> bucket ends
     unsigned short* ev = (unsigned short*)(S + Ms + 1);               // [6 * 4 NDQ] donor events sorted by sample
     __shared__ double red[NW];
@@ -827,6 +827,8 @@ __global__ void __launch_bounds__(kFluxThreads, (Ms <= 2048 ? 2 : 1)) flux_kerne
         for (int a = 0; a < kNumArr; ++a) base[a] = 0;
         if (tiles_matter || seg == 0)
             for (int i0 = tid; i0 < n_tile_iv; i0 += 4 * kFluxThreads) {
+                // (records are stored shuffled -- rec_slot -- so that the lanes of a warp hold tiles eclipsed at
+                // different samples and their shared-memory atomics rarely meet)
                 EventRec recs[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {

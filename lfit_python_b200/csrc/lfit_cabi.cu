@@ -141,7 +141,7 @@ struct lfb_handle {
     // layout
     bool have_layout = false, have_lc = false;
     int ndim = 0, n_ecl = 0, npars = 0, n_prior = 0;
-    DevBuf gather, consts, psrc, ptype, pisvar, pp1, pp2, pnorm, donor_off, disc_order, rec_widx;
+    DevBuf gather, consts, psrc, ptype, pisvar, pp1, pp2, pnorm, donor_off, disc_order, rec_widx, rec_slot;
     SampleSet lc, cf_lc;
     // calc_flux scratch
     DevBuf cf_gather, cf_pars, cf_tot, cf_comp;
@@ -341,11 +341,10 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const 
 
 // shared memory of flux_kernel<Ms>: donor moment parts, three tile delta arrays, flux per sample,
 // donor bucket offsets and sorted donor events (worst case 6 per image)
-static size_t flux_smem_bytes(const GridCfg& G, int Ms, int nF)
+static size_t flux_smem_bytes(const GridCfg& G, int Ms, int EC, int nF)
 {
     const size_t ndq = (size_t)G.n_donor_q;
-    size_t b = 64 * ndq + 24 * (size_t)Ms + 8 * (size_t)nF * Ms + 8 * 5 * ((size_t)Ms / 2) + 4 * ((size_t)Ms + 1) +
-               2 * 6 * 4 * ndq;
+    size_t b = 64 * ndq + 8 * (size_t)std::max(nF, 3) * Ms + 8 * 5 * (size_t)EC + 4 * ((size_t)Ms + 1) + 2 * 6 * 4 * ndq;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -471,22 +470,24 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         const long long per_job = ((G.n_wd_half + G.n_disc_half + G.n_bs + G.n_donor_q) + 31) & ~31;
         KREC(LFB_K_POSITIONS);
         positions_kernel<<<(unsigned)((njobs * per_job + 127) / 128), 128, 0, st>>>(A);
-        const size_t smem = flux_smem_bytes(G, Ms, mode ? 4 : 1);
+        const int EC = Ms == 1280 ? 512 : Ms == 1024 ? 256 : Ms / 2;
+        const size_t smem = flux_smem_bytes(G, Ms, EC, mode ? 4 : 1);
         if (smem > (size_t)h->max_smem - 2048)
             return fail(h, LFB_EINVAL, "light curve too long / surface grid too dense for the flux kernel's shared memory");
         if (4 * G.n_donor_q > 32767) return fail(h, LFB_EINVAL, "donor grid too dense (15-bit image index)");
         const dim3 fgrid((unsigned)njobs);
         KREC(LFB_K_FLUX);
-#define LFB_LAUNCH_FLUX(MS)                                                                                     \
-    do {                                                                                                        \
-        CK(cudaFuncSetAttribute(flux_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        flux_kernel<MS><<<fgrid, kFluxThreads, smem, st>>>(A);                                                  \
+#define LFB_LAUNCH_FLUX(MS, EC_, CTAS)                                                                                 \
+    do {                                                                                                               \
+        CK(cudaFuncSetAttribute(flux_kernel<MS, EC_, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        flux_kernel<MS, EC_, CTAS><<<fgrid, kFluxThreads, smem, st>>>(A);                                              \
     } while (0)
         switch (Ms) {
-        case 1024: LFB_LAUNCH_FLUX(1024); break;
-        case 1536: LFB_LAUNCH_FLUX(1536); break;
-        case 2048: LFB_LAUNCH_FLUX(2048); break;
-        case 3072: LFB_LAUNCH_FLUX(3072); break;
+        case 1024: LFB_LAUNCH_FLUX(1024, 256, 4); break;
+        case 1280: LFB_LAUNCH_FLUX(1280, 512, 3); break;
+        case 1536: LFB_LAUNCH_FLUX(1536, 768, 2); break;
+        case 2048: LFB_LAUNCH_FLUX(2048, 1024, 2); break;
+        case 3072: LFB_LAUNCH_FLUX(3072, 1536, 1); break;
         default: return fail(h, LFB_EINVAL, "unsupported segment capacity");
         }
 #undef LFB_LAUNCH_FLUX
@@ -615,10 +616,35 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
             delete h;
             return LFB_EINVAL;
         }
+        // Records are stored shuffled: slot s holds tile record (s * stride) mod n, stride co-prime with n.
+        // Neighbouring tiles are eclipsed at neighbouring samples; this way the lanes of a flux-kernel
+        // warp hold distant tiles and their shared-memory atomics rarely hit the same sample.
+        const long long nrec = (long long)widx.size();
+        long long stride = nrec > 4096 ? 521 : 67;
+        if (const char* env = getenv("LFB_REC_STRIDE")) stride = std::max(1, atoi(env));
+        auto gcd = [](long long a, long long b) {
+            while (b) {
+                long long r = a % b;
+                a = b;
+                b = r;
+            }
+            return a;
+        };
+        while (nrec > 1 && gcd(stride, nrec) != 1) ++stride;
+        std::vector<int> slot(widx.size());
+        std::vector<unsigned short> widx_slot(widx.size());
+        for (long long s = 0; s < nrec; ++s) {
+            const long long i = (s * stride) % nrec;
+            slot[(size_t)i] = (int)s;
+            widx_slot[(size_t)s] = widx[(size_t)i];
+        }
         if (h->rec_widx.reserve(widx.size() * sizeof(unsigned short)) != cudaSuccess ||
-            cudaMemcpy(h->rec_widx.p, widx.data(), widx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess)
+            cudaMemcpy(h->rec_widx.p, widx_slot.data(), widx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess ||
+            h->rec_slot.reserve(slot.size() * sizeof(int)) != cudaSuccess ||
+            cudaMemcpy(h->rec_slot.p, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail("record weight index table", cudaGetLastError());
         G.rec_widx = h->rec_widx.as<unsigned short>();
+        G.rec_slot = h->rec_slot.as<int>();
     }
     // composite Simpson nodes on [-1, 1] (exposure = phase +- width, CVModel.py:64)
     if (c.n_quad == 1) {
@@ -633,7 +659,7 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
         }
     }
     // capacity of a flux-kernel segment in samples (LFB_MS overrides the chi-squared one for tuning)
-    h->Mc = 1536;
+    h->Mc = 1280;
     h->Mc_flux = 1024;
     if (const char* env = getenv("LFB_LANES")) {
         int v = atoi(env);
@@ -641,7 +667,7 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
     }
     if (const char* env = getenv("LFB_MS")) {
         int v = atoi(env);
-        if (v == 1024 || v == 1536 || v == 2048 || v == 3072) h->Mc = v;
+        if (v == 1024 || v == 1280 || v == 1536 || v == 2048 || v == 3072) h->Mc = v;
     }
     *out = h;
     return LFB_OK;
@@ -653,7 +679,7 @@ void lfb_destroy(lfb_handle* h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->gather, &h->consts, &h->psrc, &h->ptype, &h->pisvar, &h->pp1, &h->pp2, &h->pnorm,
-                      &h->donor_off, &h->disc_order, &h->rec_widx, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
+                      &h->donor_off, &h->disc_order, &h->rec_widx, &h->rec_slot, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
                       &h->chisq, &h->h_in, &h->h_out, &h->h_chisq};
     for (DevBuf* b : bufs) b->release();
     h->lc.release();
