@@ -37,6 +37,10 @@ enum { P_WDFLUX = 0, P_DFLUX, P_SFLUX, P_RSFLUX, P_Q, P_DPHI, P_RDISC, P_ULIMB, 
 
 constexpr int kFluxThreads = 256;
 constexpr int kElemThreads = 128;
+#ifndef LFB_ELEM_BLOCKS
+#define LFB_ELEM_BLOCKS 7
+#endif
+constexpr int kElemBlocks = LFB_ELEM_BLOCKS;  // resident CTAs per SM the element kernels are compiled for
 constexpr int kMaxDonorRings = 128;
 constexpr int kMaxQuad = 15;
 constexpr int kNumArr = 8;  // event arrays: white dwarf, disc, bright spot, 5 donor moments
@@ -251,11 +255,13 @@ __device__ __forceinline__ bool walker_live(const ElemArgs& A, const WalkerScal&
 
 // COMP 0: white dwarf (per walker), 1: disc (per job), 2: bright spot (per job), 3: donor (per walker)
 template <int COMP>
-__global__ void __launch_bounds__(kElemThreads) elements_kernel(const __grid_constant__ ElemArgs A)
+__global__ void __launch_bounds__(kElemThreads, kElemBlocks) elements_kernel(const __grid_constant__ ElemArgs A)
 {
     const GridCfg& G = A.G;
     const int per_unit = COMP == 0 ? G.n_wd_half : COMP == 1 ? G.n_disc_half : COMP == 2 ? G.n_bs : G.n_donor_q;
-    const int padded = (per_unit + 31) & ~31;
+    // disc tiles keep whole warps per job (their order is tuned to warps, see disc_order); the other
+    // components are dealt to threads back to back -- a warp may straddle two walkers, no idle lanes
+    const int padded = COMP == 1 ? (per_unit + 31) & ~31 : per_unit;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long unit = gid / padded;
     const int t = (int)(gid - unit * padded);

@@ -406,13 +406,13 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         E.disc_io = ln.disc_io.as<double2>();
         E.bs_io = ln.bs_io.as<double2>();
         E.bs_b = ln.bs_b.as<double>();
-        auto blocks = [&](long long units, int per_unit) {
-            long long padded = (per_unit + 31) & ~31;
+        auto blocks = [&](long long units, int per_unit, bool whole_warps = false) {
+            const long long padded = whole_warps ? (per_unit + 31) & ~31 : per_unit;
             return (unsigned)((units * padded + kElemThreads - 1) / kElemThreads);
         };
         if (!(flags & LFB_FLAG_SKIP_DISC)) {
             KREC(LFB_K_ELEM_DISC);
-            elements_kernel<1><<<blocks(njobs, G.n_disc_half), kElemThreads, 0, st>>>(E);
+            elements_kernel<1><<<blocks(njobs, G.n_disc_half, true), kElemThreads, 0, st>>>(E);
             h->launches++;
         }
         if (!(flags & LFB_FLAG_SKIP_WD)) {

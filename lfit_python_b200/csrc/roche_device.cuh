@@ -339,6 +339,91 @@ LFB_HD_NOINLINE int ingress_egress_robust(const Roche& R, double si, double ci, 
     return 1;
 }
 
+// ---- single-precision warm-up of the grazing-LOS Newton ----
+// The FP64 pipe is what bounds the element solves.  The first Newton steps only have to get
+// near the root, so they run in FP32 (its own pipe, twice the rate); the FP64 iteration then
+// starts ~1e-6 from the root and converges in two or three steps instead of eight.  The root
+// the FP64 iteration converges to is unchanged -- FP32 only picks the starting point, and a
+// warm-up that misbehaves is dropped.
+struct DerivsF {
+    float S, St, Sl, Stl, Sll;
+};
+struct PointF {
+    float x, y, z, xi, eta;
+};
+
+LFB_HD float rsqrt_f(float x)
+{
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
+LFB_HD void ray_eval_f(float mu, float omu, float si, float ci, const PointF& T, float c, float s, float lam, DerivsF& D)
+{
+    float ex = si * c, ey = -si * s;
+    float dx = fmaf(lam, ex, -T.xi * s - T.eta * ci * c);
+    float dy = fmaf(lam, ey, -T.xi * c + T.eta * ci * s);
+    float dz = fmaf(lam, ci, T.eta * si);
+    float x = T.x + dx, y = T.y + dy, z = T.z + dz;
+    float tx = dy, ty = -dx;
+    float x2 = x - 1.0f;
+    float yz = y * y + z * z;
+    float ir1 = rsqrt_f(x * x + yz), ir2 = rsqrt_f(x2 * x2 + yz);
+    float a1 = omu * ir1 * ir1 * ir1, a2 = mu * ir2 * ir2 * ir2;
+    float b1 = 3.0f * a1 * ir1 * ir1, b2 = 3.0f * a2 * ir2 * ir2;
+    float a12 = a1 + a2, xc = x - mu;
+    float gx = a1 * x + a2 * x2 - xc, gy = a12 * y - y, gz = a12 * z;
+    float x_e = x * ex + y * ey + z * ci, d_e = x_e - ex;
+    float x_t = x * tx + y * ty, d_t = x_t - tx;
+    float e_t = ex * tx + ey * ty, e_xy = ex * ex + ey * ey;
+    D.S = -omu * ir1 - mu * ir2 - 0.5f * (xc * xc + y * y);
+    D.St = gx * tx + gy * ty;
+    D.Sl = gx * ex + gy * ey + gz * ci;
+    D.Sll = a12 - b1 * x_e * x_e - b2 * d_e * d_e - e_xy;
+    D.Stl = (a12 - 1.0f) * e_t - b1 * x_e * x_t - b2 * d_e * d_t + (gx * ey - gy * ex);
+}
+
+// (c, s) <- rotation by d radians, |d| <= 0.2, to single precision
+LFB_HD void rotate_cs_f(float& c, float& s, float d)
+{
+    float d2 = d * d;
+    float sd = d * fmaf(d2, fmaf(d2, fmaf(d2, -1.0f / 5040.0f, 1.0f / 120.0f), -1.0f / 6.0f), 1.0f);
+    float cd = fmaf(d2, fmaf(d2, fmaf(d2, -1.0f / 720.0f, 1.0f / 24.0f), -0.5f), 1.0f);
+    float cn = c * cd - s * sd;
+    s = s * cd + c * sd;
+    c = cn;
+}
+
+constexpr int kWarmIters = 10;
+
+// FP32 Newton towards the grazing LOS on side sg of the deepest LOS (cm, sm); true if it settled.
+LFB_HD bool warm_root(float mu, float omu, float phic, float si, float ci, const PointF& T, float cm, float sm, float sg,
+                      float& c, float& s, float& lam)
+{
+    DerivsF D;
+    for (int it = 0; it < kWarmIters; ++it) {
+        ray_eval_f(mu, omu, si, ci, T, c, s, lam, D);
+        float F1 = D.S - phic, F2 = D.Sl;
+        float idet = 1.0f / (D.St * D.Sll - D.Sl * D.Stl);
+        float dth = (-F1 * D.Sll + F2 * D.Sl) * idet, dl = (-D.St * F2 + D.Stl * F1) * idet;
+        dth = dth > 0.2f ? 0.2f : (dth < -0.2f ? -0.2f : dth);
+        dl = dl > 0.2f ? 0.2f : (dl < -0.2f ? -0.2f : dl);
+        float cross = s * cm - c * sm;
+        if (!(sg * (cross + dth * (c * cm + s * sm)) > 0.0f)) {
+            dth = -0.5f * asinf(cross > 1.0f ? 1.0f : (cross < -1.0f ? -1.0f : cross));
+            dl *= 0.5f;
+        }
+        rotate_cs_f(c, s, dth);
+        lam += dl;
+        if (!(fabsf(dth) < 1.0f)) return false;  // NaN
+        if (fabsf(dth) < 2e-5f && fabsf(dl) < 2e-4f) return true;
+    }
+    return false;
+}
+
 constexpr int kMinIters = 12;   // deepest-LOS Newton (shallow elements only), early exit
 constexpr int kRootIters = 16;  // grazing-LOS Newton, early exit
 
@@ -417,12 +502,24 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         lam1 = lam + slope * del;
     }
     double res[2];
+    const float muf = (float)R.mu, omuf = (float)R.omu, phicf = (float)R.phic, sif = (float)si, cif = (float)ci;
+    const PointF Tf = {(float)T.x, (float)T.y, (float)T.z, (float)T.xi, (float)T.eta};
 #pragma unroll 1
     for (int side = 0; side < 2; ++side) {
         const double sg = side ? 1.0 : -1.0;
         c = side ? c1 : c0;
         s = side ? s1 : s0;
         lam = side ? lam1 : lam0;
+        {
+            float cf = (float)c, sf = (float)s, lf = (float)lam;
+            if (warm_root(muf, omuf, phicf, sif, cif, Tf, (float)cm, (float)sm, (float)sg, cf, sf, lf)) {
+                const double cw = (double)cf, sw = (double)sf;
+                const double nrm = fast_rsqrt(cw * cw + sw * sw);
+                c = cw * nrm;
+                s = sw * nrm;
+                lam = (double)lf;
+            }
+        }
         bool conv = false;
         for (int it = 0; it < kRootIters; ++it) {
             ray_eval(R, si, ci, T, c, s, lam, D);
