@@ -113,6 +113,29 @@ int lfb_calc_flux(lfb_handle *h, long long n_sets, const double *pars, int npars
 int lfb_roche(lfb_handle *h, int which, long long n, const double *a, const double *b, double *out,
               int *ok);
 
+/* ---- Gaussian-process likelihood (GPLCModel / SimpleGPEclipse / ComplexGPEclipse, CVModel.py:494-711) ----
+ * With the GP on, lfb_log_prob's likelihood of an eclipse is george's
+ *     GP(ampin * Matern32(tau) + sum over gaps of ampout * Matern32(tau, block=gap)).compute(x, ye)
+ *       .log_likelihood(y - model, quiet=True)                       (CVModel.py:603-696)
+ * instead of -chi^2/2, evaluated exactly (4-state Kalman filter over the points in ascending x)
+ * rather than with george's approximate HODLR solver.  The gaps are the reference's change points
+ * [(e - 1) + dist_cp + phi0, e - dist_cp + phi0] (CVModel.py:580-599).
+ * gp_src[3]: where ln_ampin_gp, ln_ampout_gp, ln_tau_gp come from -- a column of theta (>= 0) or
+ * -(k + 1) for constant k of set_layout, like the gather table; dist_cp[n_ecl]: (dphi + dpwd) / 2
+ * of each eclipse (CVModel.py:558-568; the reference computes it once and caches it).
+ * chisq_out of lfb_log_prob then holds -2 ln L per eclipse.  enabled = 0 switches back. */
+int lfb_set_gp(lfb_handle *h, int enabled, const int gp_src[3], const double *dist_cp);
+/* The same likelihood for caller-supplied residuals (the scalar tree path and tests):
+ * x[n] ascending, ye[n], resid[n_sets][n], hyper[n_sets][3] = (ampin, ampout, tau) -- not
+ * logarithms --, gaps[n_sets][n_gaps][2] (n_gaps <= 8, disjoint, ascending); out[n_sets],
+ * -inf where george would return -inf (quiet=True). Host or device pointers. */
+int lfb_gp_loglike(lfb_handle *h, long long n_sets, int n, const double *x, const double *ye, const double *resid,
+                   const double *hyper, int n_gaps, const double *gaps, double *out);
+/* trm.roche.wdphases(q, iangle, r1, ntheta=...) (call site CVModel.py:562): third and fourth
+ * contact of the white dwarf, out[n][2] = (phi3, phi4); ok[n] = 0 where trm.roche would raise. */
+int lfb_wdphases(lfb_handle *h, long long n, const double *q, const double *incl_deg, const double *r1, int ntheta,
+                 double *out, int *ok);
+
 /* counters for bench.py: kernels launched by this handle since creation */
 long long lfb_launch_count(const lfb_handle *h);
 /* Device time (ms) of the stages of the last lfb_log_prob (its last batch), from CUDA events
@@ -136,6 +159,7 @@ enum {
     LFB_K_PREP,        /* prep_kernel */
     LFB_K_POSITIONS,   /* positions_kernel */
     LFB_K_FLUX,        /* flux_kernel */
+    LFB_K_GP,          /* gp_kernel (only with lfb_set_gp) */
     LFB_K_FINISH,      /* finish_kernel */
     LFB_K_COUNT        /* last_trace_ms slot of stream_kernel (side stream) */
 };

@@ -3,7 +3,8 @@
 Host-side mirror of /root/reference/CVModel.py.  Each eclipse leaf evaluates
 lfit.CV.calcFlux on the GPU (lfit_python_b200.lfit); the whole tree can be flattened with
 `model.vectorised()` (flatten.py) into one batched CUDA log-probability for every walker.
-The Gaussian-process variants (CVModel.py:494-711, george) are outside this path.
+The Gaussian-process variants (CVModel.py:494-711) evaluate george's likelihood exactly on the GPU
+(csrc/gp_device.cuh) instead of through george's approximate HODLR solver.
 """
 import os
 
@@ -197,37 +198,88 @@ class LCModel(Node):
         return VectorModel(self, engine=engine, device=device, **grid)
 
 
-class _GPUnsupported:
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError(
-            "{}: the Gaussian-process likelihood (george, CVModel.py:494-711) is outside the CUDA "
-            "hot path of this package; set useGP = 0".format(type(self).__name__))
+class GPLCModel(LCModel):
+    """Root of a tree whose eclipses are judged by a Gaussian process over their residuals
+    (CVModel.py:494-514): adds the ln of the in-eclipse amplitude, of the extra out-of-eclipse
+    amplitude and of the time scale."""
 
-
-class GPLCModel(_GPUnsupported, LCModel):
     node_par_names = LCModel.node_par_names + ('ln_ampin_gp', 'ln_ampout_gp', 'ln_tau_gp')
 
 
-class SimpleGPEclipse(_GPUnsupported, SimpleEclipse):
-    pass
+class SimpleGPEclipse(SimpleEclipse):
+    """SimpleEclipse whose ln_like is the GP likelihood of its residuals (CVModel.py:517-696)."""
+
+    # unrealistic start values: the first calcChangepoints computes dist_cp (CVModel.py:518-526)
+    _olddphi = 9e99
+    _oldq = 9e99
+    _oldrwd = 9e99
+    _dist_cp = 9e99
+
+    def dist_cp(self):
+        """Distance of the change points from mid-eclipse, (dphi + dpwd) / 2, with the reference's
+        cache: recomputed only when dphi, q or rwd moved by more than 120 % of their value since
+        the last computation (CVModel.py:548-579) -- in practice once."""
+        pd = self.ancestor_param_dict
+        dphi, q, rwd = pd['dphi'], pd['q'], pd['rwd']
+        dphi_change = np.fabs(self._olddphi - dphi.currVal) / dphi.currVal
+        q_change = np.fabs(self._oldq - q.currVal) / q.currVal
+        rwd_change = np.fabs(self._oldrwd - rwd.currVal) / rwd.currVal
+        if (dphi_change > 1.2) or (q_change > 1.2) or (rwd_change > 1.2):
+            inc = roche.findi(q.currVal, dphi.currVal)
+            phi3, phi4 = roche.wdphases(q.currVal, inc, rwd.currVal, ntheta=10)
+            self._dist_cp = (dphi.currVal + (phi4 - phi3)) / 2.
+            self._oldq, self._olddphi, self._oldrwd = q.currVal, dphi.currVal, rwd.currVal
+        return self._dist_cp
+
+    def calcChangepoints(self):
+        """[[egress of the previous eclipse, ingress of this one], ...] for every cycle the light
+        curve touches (CVModel.py:527-601)."""
+        dist_cp = self.dist_cp()
+        phi0 = self.ancestor_param_dict['phi0'].currVal
+        x = self.lc.x
+        eclipses = [e for e in range(int(np.floor(x.min())), int(np.ceil(x.max())) + 1)
+                    if e > x.min() and e < 1 + x.max()]
+        return [[(e - 1) + dist_cp + phi0, e - dist_cp + phi0] for e in eclipses]
+
+    def ln_like(self):
+        """ln L of the residuals under ampin * Matern32(tau) + ampout * Matern32(tau) between the
+        change points, with the data errors on the diagonal (CVModel.py:603-696)."""
+        flx = self.calcFlux()
+        residuals = self.lc.y - flx
+        if np.any(np.isinf(residuals)) or np.any(np.isnan(residuals)):
+            return -np.inf
+        pd = self.ancestor_param_dict
+        hyper = [np.exp(pd[k].currVal) for k in ('ln_ampin_gp', 'ln_ampout_gp', 'ln_tau_gp')]
+        gaps = self.calcChangepoints()
+        order = np.argsort(self.lc.x, kind='stable')
+        from . import _cabi
+        out = _cabi.default_engine().gp_loglike(self.lc.x[order], self.lc.ye[order], residuals[order], hyper, gaps)
+        return float(out[0])
 
 
-class ComplexGPEclipse(_GPUnsupported, ComplexEclipse):
-    pass
+class ComplexGPEclipse(SimpleGPEclipse):
+    """As SimpleGPEclipse with the complex bright spot (CVModel.py:699-711)."""
+
+    node_par_names = ComplexEclipse.node_par_names
+    cv_parnames = ComplexEclipse.cv_parnames
 
 
 def construct_model(input_file, debug=False, nodata=False):
     """Parse an mcmc_input.dat into a model tree (CVModel.py:713-924): LCModel 'core' -> one Band
-    per band label -> one Simple/ComplexEclipse per eclipse label, in order of first appearance
+    per band label -> one Simple/Complex(GP)Eclipse per eclipse label (GPLCModel root and GP leaves for
+    useGP = 1), in order of first appearance
     in the file; `neclipses` truncates; bands left without eclipses are pruned."""
     cfg = ConfigObj(input_file)
     is_complex = bool(int(cfg['complex']))
-    if bool(int(cfg.get('useGP', 0))):
-        GPLCModel()
+    use_gp = bool(int(cfg.get('useGP', 0)))
     neclipses = int(cfg['neclipses']) if 'neclipses' in cfg else 9999
 
-    model = LCModel('core', [Param.fromString(n, cfg[n]) for n in LCModel.node_par_names], DEBUG=debug)
-    ecl_cls = ComplexEclipse if is_complex else SimpleEclipse
+    root_cls = GPLCModel if use_gp else LCModel
+    model = root_cls('core', [Param.fromString(n, cfg[n]) for n in root_cls.node_par_names], DEBUG=debug)
+    if use_gp:
+        ecl_cls = ComplexGPEclipse if is_complex else SimpleGPEclipse
+    else:
+        ecl_cls = ComplexEclipse if is_complex else SimpleEclipse
     ecl_pars = ecl_cls.node_par_names
 
     bands, eclipses = [], []

@@ -22,11 +22,11 @@ EXPORTS = (
     "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_get_config", "lfb_set_layout",
     "lfb_set_priors", "lfb_set_lightcurves", "lfb_log_prob", "lfb_calc_flux", "lfb_roche",
     "lfb_launch_count", "lfb_last_kernel_ms", "lfb_last_stage_ms", "lfb_measure_fp64_peak",
-    "lfb_set_trace", "lfb_last_trace_ms",
+    "lfb_set_trace", "lfb_last_trace_ms", "lfb_set_gp", "lfb_gp_loglike", "lfb_wdphases",
 )
 TRACE_KERNELS = ("walker_kernel", "jobcheck_kernel", "elements_kernel<1> disc", "elements_kernel<0> white dwarf",
                  "elements_kernel<3> donor", "elements_kernel<2> strip", "prep_kernel", "positions_kernel",
-                 "flux_kernel", "finish_kernel", "stream_kernel (side stream)")
+                 "flux_kernel", "gp_kernel", "finish_kernel", "stream_kernel (side stream)")
 
 
 class EngineError(RuntimeError):
@@ -79,6 +79,9 @@ def load():
     lib.lfb_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.lfb_set_trace.argtypes = [vp, C.c_int]
     lib.lfb_last_trace_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.lfb_set_gp.argtypes = [vp, C.c_int, ip, dp]
+    lib.lfb_gp_loglike.argtypes = [vp, C.c_longlong, C.c_int, dp, dp, dp, dp, C.c_int, dp, dp]
+    lib.lfb_wdphases.argtypes = [vp, C.c_longlong, dp, dp, dp, C.c_int, dp, ip]
     _lib = lib
     return lib
 
@@ -160,6 +163,45 @@ class Engine:
         out = (C.c_float * len(TRACE_KERNELS))()
         self._check(self._lib.lfb_last_trace_ms(self._h, out), "lfb_last_trace_ms")
         return {k: float(x) for k, x in zip(TRACE_KERNELS, out) if x >= 0.0}
+
+    def set_gp(self, gp_src=None, dist_cp=None):
+        """Switch lfb_log_prob's likelihood to the Gaussian process of CVModel.py:603-696
+        (gp_src: sources of ln_ampin_gp, ln_ampout_gp, ln_tau_gp; dist_cp per eclipse), or back
+        to chi-squared with no arguments."""
+        if gp_src is None:
+            self._check(self._lib.lfb_set_gp(self._h, 0, None, None), "lfb_set_gp")
+            return
+        src = np.ascontiguousarray(gp_src, dtype=np.int32)
+        dist = _f64(dist_cp).ravel()
+        if src.shape != (3,) or dist.shape[0] != self.n_ecl:
+            raise ValueError("set_gp: need three sources and one dist_cp per eclipse")
+        self._check(self._lib.lfb_set_gp(self._h, 1, src.ctypes.data_as(C.POINTER(C.c_int)), _dp(dist)), "lfb_set_gp")
+
+    def gp_loglike(self, x, ye, resid, hyper, gaps):
+        """george-style GP log-likelihood of residual rows: x, ye of length n (x ascending),
+        resid (n_sets, n), hyper (n_sets, 3) = (ampin, ampout, tau), gaps (n_sets, n_gaps, 2)."""
+        x, ye = _f64(x).ravel(), _f64(ye).ravel()
+        resid = np.atleast_2d(_f64(resid))
+        hyper = np.atleast_2d(_f64(hyper))
+        n_sets, n = resid.shape
+        gaps = _f64(gaps).reshape(n_sets, -1, 2)
+        if x.shape[0] != n or ye.shape[0] != n or hyper.shape != (n_sets, 3):
+            raise ValueError("gp_loglike: inconsistent shapes")
+        out = np.empty(n_sets)
+        self._check(self._lib.lfb_gp_loglike(self._h, n_sets, n, _dp(x), _dp(ye), _dp(resid), _dp(hyper),
+                                             gaps.shape[1], _dp(gaps), _dp(out)), "lfb_gp_loglike")
+        return out
+
+    def wdphases(self, q, incl_deg, r1, ntheta=10):
+        """(phi3, phi4) rows and an ok mask (trm.roche.wdphases)."""
+        q, incl_deg, r1 = np.broadcast_arrays(_f64(q), _f64(incl_deg), _f64(r1))
+        q, incl_deg, r1 = (np.ascontiguousarray(a, dtype=np.float64).ravel() for a in (q, incl_deg, r1))
+        n = q.shape[0]
+        out = np.empty((n, 2))
+        ok = np.empty(n, dtype=np.int32)
+        self._check(self._lib.lfb_wdphases(self._h, n, _dp(q), _dp(incl_deg), _dp(r1), int(ntheta), _dp(out),
+                                           ok.ctypes.data_as(C.POINTER(C.c_int))), "lfb_wdphases")
+        return out, ok.astype(bool)
 
     def measure_fp64_peak(self, iters=20000):
         """Sustained DFMA rate of this device in TFLOP/s (roofline denominator)."""

@@ -29,6 +29,7 @@
 
 #include "../../include/lfit_b200.h"
 #include "roche_device.cuh"
+#include "gp_device.cuh"
 
 namespace lfb {
 
@@ -66,9 +67,9 @@ struct DevSamples {
     const int* bins;             // [K * total + n_ecl] per eclipse M + 1 entries (see SampleAxis)
     const int* pos;              // [total * K] sorted position of each (point, node); points in phase order
     const int* pt_index;         // [total] original index of each phase-ordered point
-    const int* dp;               // [K * total] sorted sample -> point * K + node
-    const int2* prange;          // [total] per point: suffix minimum (within its segment) of the first sample of
-                                 // this and all later points, and its own last sample
+    const double *gp_x, *gp_var; // [total] GP likelihood: raw phases ascending per eclipse, noise variances
+    const int* gp_slot;          // [total] rank in that order of each phase-ordered point
+    const double2* gp_span;      // [n_ecl] smallest and largest raw phase
     const long long* chunk_off;  // [n_ecl + 1] offsets into chunks
     const int4* chunks;          // per segment: first point, one past last point, first sample, last sample
 };
@@ -408,6 +409,12 @@ struct FluxArgs {
     double* chisq_job;      // [njobs] chi-squared of each job (NaN: not evaluated)
     double* flux_tot;       // mode 1: [njobs][n_ph]
     double* flux_comp;      // mode 1 (optional): [4][njobs][n_ph]
+    // Gaussian-process likelihood instead of chi-squared (lfb_set_gp): residuals y - model, one row per data
+    // point (ascending raw phase, all eclipses back to back), one column per walker of the batch
+    double* gp_resid;       // mode 0: [total points][n walkers] or null
+    long long n_walkers;
+    int gp_src[3];          // where ln_ampin_gp, ln_ampout_gp, ln_tau_gp come from (theta column / constant slot)
+    const double* gp_dist;  // [n_ecl] distance of the change points from mid-eclipse
 };
 
 __device__ __forceinline__ bool job_live(const FluxArgs& A, const WalkerScal& W, const JobScal& J)
@@ -1053,8 +1060,10 @@ __global__ void __launch_bounds__(kFluxThreads, CTAS) flux_kernel(const __grid_c
                 }
             }
             if (A.mode == 0) {
-                const double r = (__ldg(A.smp.y + lc0 + j) - acc[0]) / __ldg(A.smp.ye + lc0 + j);
+                const double dy = __ldg(A.smp.y + lc0 + j) - acc[0];
+                const double r = dy / __ldg(A.smp.ye + lc0 + j);
                 chi += r * r;
+                if (A.gp_resid) A.gp_resid[(lc0 + __ldg(A.smp.gp_slot + lc0 + j)) * A.n_walkers + w] = dy;
             } else {
                 const int jo = __ldg(A.smp.pt_index + lc0 + j);
                 A.flux_tot[job * n_ph + jo] = acc[0] + acc[1] + acc[2] + acc[3];
@@ -1069,6 +1078,94 @@ __global__ void __launch_bounds__(kFluxThreads, CTAS) flux_kernel(const __grid_c
         chi = block_sum<kFluxThreads>(chi, red);
         if (tid == 0) A.chisq_job[job] = chi;
     }
+}
+
+// ---------------------------------------------------------------- gp_kernel
+// SimpleGPEclipse.ln_like (CVModel.py:650-696): thread per (eclipse, walker) -- walkers fastest, so
+// that a warp reads one row of the residual matrix -- runs the Kalman filter of gp_device.cuh over
+// the eclipse's points and leaves -2 ln L where the chi-squared would be.
+__global__ void __launch_bounds__(128) gp_kernel(const __grid_constant__ FluxArgs A)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.njobs) return;
+    const int e = (int)(t / A.n_walkers);
+    const long long w = t - (long long)e * A.n_walkers;
+    const long long job = w * A.L.n_ecl + e;
+    if (!job_live(A, A.ws[w], A.js[job])) return;  // the flux kernel left NaN / +inf there
+    const double* th = A.theta + w * A.L.ndim;
+    const long long lc0 = A.smp.lc_off[e];
+    const int n_ph = (int)(A.smp.lc_off[e + 1] - lc0);
+    GpPars G;
+    G.a_in = exp(fetch(A.L, th, A.gp_src[0]));
+    G.a_out = exp(fetch(A.L, th, A.gp_src[1]));
+    G.tau = exp(fetch(A.L, th, A.gp_src[2]));
+    const double phi0 = fetch(A.L, th, A.L.gather[e * LFB_NPAR + P_PHI0]);
+    const double2 span = A.smp.gp_span[e];
+    const double dist = A.gp_dist[e];
+    double ll = -INFINITY;
+    if (dist > 0.0) {
+        gp_changepoints(span.x, span.y, dist, phi0, G);
+        const double* x = A.smp.gp_x + lc0;
+        const double* var = A.smp.gp_var + lc0;
+        const double* r = A.gp_resid + lc0 * A.n_walkers + w;
+        const long long stride = A.n_walkers;
+        ll = gp_loglike(
+            n_ph, [&](int k) { return __ldg(x + k); }, [&](int k) { return __ldg(var + k); },
+            [&](int k) { return r[(long long)k * stride]; }, G);
+    }
+    A.chisq_job[job] = -2.0 * ll;
+}
+
+// lfb_gp_loglike: the same likelihood for caller-supplied residuals, thread per set
+__global__ void gp_batch_kernel(long long n_sets, int n, const double* __restrict__ x, const double* __restrict__ ye,
+                                const double* __restrict__ resid, const double* __restrict__ hyper, int n_gaps,
+                                const double* __restrict__ gaps, double* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sets) return;
+    GpPars G;
+    G.a_in = hyper[3 * i];
+    G.a_out = hyper[3 * i + 1];
+    G.tau = hyper[3 * i + 2];
+    G.n_gaps = n_gaps;
+    for (int k = 0; k < n_gaps; ++k) {
+        G.gap[k][0] = gaps[(i * n_gaps + k) * 2];
+        G.gap[k][1] = gaps[(i * n_gaps + k) * 2 + 1];
+    }
+    const double* r = resid + i * n;
+    out[i] = gp_loglike(
+        n, [&](int k) { return x[k]; }, [&](int k) { return ye[k] * ye[k]; }, [&](int k) { return r[k]; }, G);
+}
+
+// lfb_wdphases: trm.roche.wdphases(q, iangle, r1, ntheta) (call site CVModel.py:562): earliest and
+// latest egress over ntheta points on the limb of the white dwarf's disc on the sky
+__global__ void wdphases_kernel(long long n, const double* __restrict__ q, const double* __restrict__ incl,
+                                const double* __restrict__ r1, int ntheta, double* __restrict__ out, int* __restrict__ ok)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Roche R;
+    int good = 0;
+    double p3 = 1e30, p4 = -1e30;
+    if (roche_init(q[i], R) && incl[i] > 0.0 && incl[i] <= 90.0 && r1[i] > 0.0 && ntheta > 0) {
+        double si, ci;
+        sincos_(incl[i] * kDeg, &si, &ci);
+        good = 1;
+        for (int k = 0; k < ntheta; ++k) {
+            double sa, ca, pin, pout;
+            sincos_(kTwoPi * k / ntheta, &sa, &ca);
+            Point T = {0.0, 0.0, 0.0, r1[i] * ca, r1[i] * sa};
+            if (!ingress_egress(R, si, ci, T, &pin, &pout)) {
+                good = 0;
+                break;
+            }
+            p3 = pout < p3 ? pout : p3;
+            p4 = pout > p4 ? pout : p4;
+        }
+    }
+    out[2 * i] = good ? p3 : NAN;
+    out[2 * i + 1] = good ? p4 : NAN;
+    ok[i] = good;
 }
 
 // ---------------------------------------------------------------- finish_kernel

@@ -44,13 +44,15 @@ struct DevBuf {
 
 // Sorted exposure samples of a set of light curves (device copies)
 struct SampleSet {
-    DevBuf lc_off, y, ye, S, cosS, sinS, bins, pos, pt_index, dp, prange, chunk_off, chunks;
+    DevBuf lc_off, y, ye, S, cosS, sinS, bins, pos, pt_index, chunk_off, chunks;
+    DevBuf gp_x, gp_var, gp_slot, gp_span;  // GP likelihood: points in ascending raw phase
     int max_chunks = 1;
     int max_nph = 0;
     long long total = 0;
     void release()
     {
-        DevBuf* b[] = {&lc_off, &y, &ye, &S, &cosS, &sinS, &bins, &pos, &pt_index, &dp, &prange, &chunk_off, &chunks};
+        DevBuf* b[] = {&lc_off, &y, &ye, &S, &cosS, &sinS, &bins, &pos, &pt_index, &chunk_off, &chunks,
+                       &gp_x, &gp_var, &gp_slot, &gp_span};
         for (DevBuf* x : b) x->release();
     }
     DevSamples view()
@@ -65,8 +67,10 @@ struct SampleSet {
         v.bins = bins.as<int>();
         v.pos = pos.as<int>();
         v.pt_index = pt_index.as<int>();
-        v.dp = dp.as<int>();
-        v.prange = prange.as<int2>();
+        v.gp_x = gp_x.as<double>();
+        v.gp_var = gp_var.as<double>();
+        v.gp_slot = gp_slot.as<int>();
+        v.gp_span = gp_span.as<double2>();
         v.chunk_off = chunk_off.as<long long>();
         v.chunks = chunks.as<int4>();
         return v;
@@ -84,7 +88,7 @@ struct Lane {
     cudaEvent_t ev[ST_COUNT + 1] = {};
     cudaEvent_t kev[LFB_K_COUNT + 1] = {}, sev[2] = {};  // per-kernel trace (lfb_set_trace), side-stream pair
     bool kev_set[LFB_K_COUNT + 1] = {};
-    DevBuf ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, qmom, ivp, chi_part;
+    DevBuf ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, qmom, ivp, chi_part, gp_resid;
     cudaError_t create()
     {
         cudaError_t e;
@@ -103,7 +107,7 @@ struct Lane {
     }
     void destroy()
     {
-        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &qmom, &ivp, &chi_part};
+        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &qmom, &ivp, &chi_part, &gp_resid};
         for (DevBuf* x : b) x->release();
         for (int i = 0; i <= ST_COUNT; ++i)
             if (ev[i]) cudaEventDestroy(ev[i]);
@@ -131,6 +135,10 @@ struct lfb_handle {
     cudaEvent_t enter_ev = nullptr, t0_ev = nullptr, t1_ev = nullptr;
     bool ev_valid = false;
     bool trace = false;  // lfb_set_trace
+    // Gaussian-process likelihood (lfb_set_gp)
+    bool gp_on = false;
+    int gp_src[3] = {0, 0, 0};
+    DevBuf gp_dist;
     std::string err;
     long long launches = 0;
     int sm_count = 148;
@@ -140,7 +148,7 @@ struct lfb_handle {
     int n_lanes = kLanes;  // LFB_LANES=1 serialises the batches (clean per-stage timings for profiling)
     // layout
     bool have_layout = false, have_lc = false;
-    int ndim = 0, n_ecl = 0, npars = 0, n_prior = 0;
+    int ndim = 0, n_ecl = 0, npars = 0, n_prior = 0, n_consts = 0;
     DevBuf gather, consts, psrc, ptype, pisvar, pp1, pp2, pnorm, donor_off, disc_order, rec_widx, rec_slot;
     SampleSet lc, cf_lc;
     // calc_flux scratch
@@ -203,8 +211,10 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const 
     const long long total = off[n_ecl];
     std::vector<double> S((size_t)total * K), cS((size_t)total * K), sS((size_t)total * K);
     std::vector<double> ys((size_t)total), yes((size_t)total);
-    std::vector<int> pos((size_t)total * K), bins((size_t)total * K + n_ecl, 0), pt_index((size_t)total), dp((size_t)total * K);
-    std::vector<int2> prange((size_t)total);
+    std::vector<int> pos((size_t)total * K), bins((size_t)total * K + n_ecl, 0), pt_index((size_t)total);
+    std::vector<double> gp_x((size_t)total), gp_var((size_t)total);
+    std::vector<int> gp_slot((size_t)total), gp_rank;
+    std::vector<double2> gp_span((size_t)std::max(n_ecl, 1));
     std::vector<long long> chunk_off(n_ecl + 1, 0);
     std::vector<int4> chunks;
     int max_nph = 0, max_chunks = 1;
@@ -247,7 +257,6 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const 
             cS[o * K + r] = cos(kTwoPi * raw[src]);
             sS[o * K + r] = sin(kTwoPi * raw[src]);
             pos[o * K + src] = r;
-            dp[o * K + r] = src;  // = point * K + node
         }
         // bin table: first sample at or after the start of each of M equal phase bins
         if (M > 0) {
@@ -300,20 +309,19 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const 
                 return LFB_EINVAL;
             }
         }
-        // per point: last sample, and the suffix minimum of the first samples inside its segment
-        for (int k = 0; k < nch; ++k) {
-            const int4 cur = chunks[chunks.size() - nch + k];
-            int sfx = cur.w + 1;
-            for (int j = cur.y - 1; j >= cur.x; --j) {
-                int lo = M, hi = -1;
-                for (int q = 0; q < K; ++q) {
-                    lo = std::min(lo, pos[o * K + j * K + q]);
-                    hi = std::max(hi, pos[o * K + j * K + q]);
-                }
-                sfx = std::min(sfx, lo);
-                prange[o + j] = make_int2(sfx, hi);
-            }
+        // GP likelihood (CVModel.py:650-696): the points in ascending raw (unwrapped) phase, their noise
+        // variances, and where each wrapped-phase-ordered point sits in that order
+        gp_rank.resize(n_ph);
+        std::iota(gp_rank.begin(), gp_rank.end(), 0);
+        std::stable_sort(gp_rank.begin(), gp_rank.end(), [&](int a, int b) { return phase[o + a] < phase[o + b]; });
+        for (int r = 0; r < n_ph; ++r) {
+            const int j = gp_rank[r];
+            gp_x[o + r] = phase[o + j];
+            gp_var[o + r] = ye ? ye[o + j] * ye[o + j] : 1.0;
+            wph[j] = (double)r;  // reuse: rank of original point j
         }
+        for (int jj = 0; jj < n_ph; ++jj) gp_slot[o + jj] = (int)wph[pt_index[o + jj]];
+        gp_span[e] = n_ph ? make_double2(gp_x[o], gp_x[o + n_ph - 1]) : make_double2(0.0, 0.0);
         chunk_off[e + 1] = chunk_off[e] + nch;
         max_chunks = std::max(max_chunks, nch);
     }
@@ -328,8 +336,10 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const 
     if ((rc = upload(h, ss.bins, bins.data(), sizeof(int) * bins.size()))) return rc;
     if ((rc = upload(h, ss.pos, pos.data(), sizeof(int) * pos.size()))) return rc;
     if ((rc = upload(h, ss.pt_index, pt_index.data(), sizeof(int) * pt_index.size()))) return rc;
-    if ((rc = upload(h, ss.dp, dp.data(), sizeof(int) * dp.size()))) return rc;
-    if ((rc = upload(h, ss.prange, prange.data(), sizeof(int2) * prange.size()))) return rc;
+    if ((rc = upload(h, ss.gp_x, gp_x.data(), sizeof(double) * gp_x.size()))) return rc;
+    if ((rc = upload(h, ss.gp_var, gp_var.data(), sizeof(double) * gp_var.size()))) return rc;
+    if ((rc = upload(h, ss.gp_slot, gp_slot.data(), sizeof(int) * gp_slot.size()))) return rc;
+    if ((rc = upload(h, ss.gp_span, gp_span.data(), sizeof(double2) * gp_span.size()))) return rc;
     if ((rc = upload(h, ss.chunk_off, chunk_off.data(), sizeof(long long) * chunk_off.size()))) return rc;
     if ((rc = upload(h, ss.chunks, chunks.data(), sizeof(int4) * chunks.size()))) return rc;
     CK(cudaStreamSynchronize(h->stream));  // the host vectors die here
@@ -465,6 +475,15 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         A.chisq_job = ln.chi_part.as<double>();
         A.flux_tot = d_tot;
         A.flux_comp = d_comp;
+        const bool gp = h->gp_on && mode == 0;
+        A.gp_resid = nullptr;
+        A.n_walkers = n;
+        A.gp_dist = h->gp_dist.as<double>();
+        for (int i = 0; i < 3; ++i) A.gp_src[i] = h->gp_src[i];
+        if (gp) {
+            CK(ln.gp_resid.reserve(sizeof(double) * (size_t)ss.total * (size_t)n));
+            A.gp_resid = ln.gp_resid.as<double>();
+        }
         KREC(LFB_K_PREP);
         prep_kernel<<<(unsigned)((njobs + 3) / 4), 128, 0, st>>>(A);
         const long long per_job = ((G.n_wd_half + G.n_disc_half + G.n_bs + G.n_donor_q) + 31) & ~31;
@@ -492,6 +511,11 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         }
 #undef LFB_LAUNCH_FLUX
         h->launches += 3;
+        if (gp) {
+            KREC(LFB_K_GP);
+            gp_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, st>>>(A);
+            h->launches++;
+        }
     } else {
         CK(cudaStreamWaitEvent(st, ln.join_ev, 0));
         if (record) CK(cudaEventRecord(ln.ev[ST_FLUX], st));
@@ -783,6 +807,8 @@ int lfb_set_layout(lfb_handle* h, int ndim, int n_ecl, int npars, const int* gat
     int rc;
     if ((rc = upload(h, h->gather, gather, sizeof(int) * (size_t)n_ecl * LFB_NPAR))) return rc;
     if ((rc = upload(h, h->consts, consts, sizeof(double) * (size_t)n_consts))) return rc;
+    h->n_consts = n_consts;
+    h->gp_on = false;  // a new layout: the GP sources must be set again
     CK(cudaStreamSynchronize(h->stream));
     h->ndim = ndim;
     h->n_ecl = n_ecl;
@@ -995,6 +1021,100 @@ int lfb_calc_flux(lfb_handle* h, long long n_sets, const double* pars, int npars
     if (!tot_dev) CK(cudaMemcpyAsync(out_total, d_tot, cur, cudaMemcpyDeviceToHost, st));
     if (out_comp && !comp_dev) CK(cudaMemcpyAsync(out_comp, d_comp, 4 * cur, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return LFB_OK;
+}
+
+int lfb_set_gp(lfb_handle* h, int enabled, const int gp_src[3], const double* dist_cp)
+{
+    if (!h) return LFB_EINVAL;
+    if (!enabled) {
+        h->gp_on = false;
+        return LFB_OK;
+    }
+    if (!h->have_layout || !gp_src || !dist_cp) return fail(h, LFB_ESTATE, "set_gp: set_layout first; need gp_src[3] and dist_cp[n_ecl]");
+    for (int i = 0; i < 3; ++i) {
+        if (gp_src[i] >= h->ndim || gp_src[i] < -h->n_consts)
+            return fail(h, LFB_EINVAL, "set_gp: hyper-parameter source out of range");
+        h->gp_src[i] = gp_src[i];
+    }
+    CK(cudaSetDevice(h->device));
+    int rc = upload(h, h->gp_dist, dist_cp, sizeof(double) * (size_t)h->n_ecl);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->gp_on = true;
+    return LFB_OK;
+}
+
+int lfb_gp_loglike(lfb_handle* h, long long n_sets, int n, const double* x, const double* ye, const double* resid,
+                   const double* hyper, int n_gaps, const double* gaps, double* out)
+{
+    if (!h) return LFB_EINVAL;
+    if (n_sets < 0 || n < 0 || n_gaps < 0 || n_gaps > kMaxGaps || (n_sets && (!hyper || !out)) ||
+        (n_sets && n && (!x || !ye || !resid)) || (n_sets && n_gaps && !gaps))
+        return fail(h, LFB_EINVAL, "gp_loglike: bad arguments (at most 8 gaps)");
+    if (n_sets == 0) return LFB_OK;
+    for (int k = 1; k < n; ++k)
+        if (!(x[k] >= x[k - 1])) return fail(h, LFB_EINVAL, "gp_loglike: x must ascend");
+    CK(cudaSetDevice(h->device));
+    DevBuf dx, dye, dr, dh, dg, dout;
+    auto cleanup = [&]() { dx.release(); dye.release(); dr.release(); dh.release(); dg.release(); dout.release(); };
+    cudaError_t e = cudaSuccess;
+    const size_t nn = (size_t)std::max(n, 1), ng = (size_t)std::max(n_gaps, 1);
+    if ((e = dx.reserve(8 * nn)) != cudaSuccess || (e = dye.reserve(8 * nn)) != cudaSuccess ||
+        (e = dr.reserve(8 * nn * (size_t)n_sets)) != cudaSuccess || (e = dh.reserve(24 * (size_t)n_sets)) != cudaSuccess ||
+        (e = dg.reserve(16 * ng * (size_t)n_sets)) != cudaSuccess || (e = dout.reserve(8 * (size_t)n_sets)) != cudaSuccess) {
+        cleanup();
+        return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    }
+    cudaStream_t st = h->stream;
+    if (n) {
+        cudaMemcpyAsync(dx.p, x, 8 * (size_t)n, cudaMemcpyDefault, st);
+        cudaMemcpyAsync(dye.p, ye, 8 * (size_t)n, cudaMemcpyDefault, st);
+        cudaMemcpyAsync(dr.p, resid, 8 * (size_t)n * (size_t)n_sets, cudaMemcpyDefault, st);
+    }
+    cudaMemcpyAsync(dh.p, hyper, 24 * (size_t)n_sets, cudaMemcpyDefault, st);
+    if (n_gaps) cudaMemcpyAsync(dg.p, gaps, 16 * (size_t)n_gaps * (size_t)n_sets, cudaMemcpyDefault, st);
+    gp_batch_kernel<<<(unsigned)((n_sets + 63) / 64), 64, 0, st>>>(n_sets, n, dx.as<double>(), dye.as<double>(), dr.as<double>(),
+                                                                    dh.as<double>(), n_gaps, dg.as<double>(), dout.as<double>());
+    h->launches++;
+    cudaMemcpyAsync(out, dout.p, 8 * (size_t)n_sets, cudaMemcpyDefault, st);
+    e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    return LFB_OK;
+}
+
+int lfb_wdphases(lfb_handle* h, long long n, const double* q, const double* incl_deg, const double* r1, int ntheta,
+                 double* out, int* ok)
+{
+    if (!h) return LFB_EINVAL;
+    if (n < 0 || ntheta < 1 || (n && (!q || !incl_deg || !r1 || !out || !ok)))
+        return fail(h, LFB_EINVAL, "wdphases: bad arguments");
+    if (n == 0) return LFB_OK;
+    CK(cudaSetDevice(h->device));
+    DevBuf dq, di, dr, dout, dok;
+    auto cleanup = [&]() { dq.release(); di.release(); dr.release(); dout.release(); dok.release(); };
+    cudaError_t e;
+    if ((e = dq.reserve(8 * (size_t)n)) != cudaSuccess || (e = di.reserve(8 * (size_t)n)) != cudaSuccess ||
+        (e = dr.reserve(8 * (size_t)n)) != cudaSuccess || (e = dout.reserve(16 * (size_t)n)) != cudaSuccess ||
+        (e = dok.reserve(4 * (size_t)n)) != cudaSuccess) {
+        cleanup();
+        return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    }
+    cudaStream_t st = h->stream;
+    cudaMemcpyAsync(dq.p, q, 8 * (size_t)n, cudaMemcpyDefault, st);
+    cudaMemcpyAsync(di.p, incl_deg, 8 * (size_t)n, cudaMemcpyDefault, st);
+    cudaMemcpyAsync(dr.p, r1, 8 * (size_t)n, cudaMemcpyDefault, st);
+    wdphases_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, dq.as<double>(), di.as<double>(), dr.as<double>(), ntheta,
+                                                              dout.as<double>(), dok.as<int>());
+    h->launches++;
+    cudaMemcpyAsync(out, dout.p, 16 * (size_t)n, cudaMemcpyDefault, st);
+    cudaMemcpyAsync(ok, dok.p, 4 * (size_t)n, cudaMemcpyDefault, st);
+    e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
     return LFB_OK;
 }
 

@@ -62,6 +62,17 @@ class FlatLayout:
                 gather[k, j] = src_of[id(pd[nm])]
         self.gather = gather
         self.n_ecl = len(self.eclipses)
+        # Gaussian-process likelihood (GPLCModel, CVModel.py:494-711): where the three hyper-parameters
+        # come from, and every eclipse's change-point distance at the tree's current values (the
+        # reference computes it on the first evaluation and keeps it, CVModel.py:548-579)
+        self.gp = all(hasattr(e, "calcChangepoints") for e in self.eclipses)
+        if self.gp:
+            pd = self.eclipses[0].ancestor_param_dict
+            self.gp_src = np.asarray([src_of[id(pd[k])] for k in ('ln_ampin_gp', 'ln_ampout_gp', 'ln_tau_gp')],
+                                     dtype=np.int32)
+            self.gp_dist = np.asarray([e.dist_cp() for e in self.eclipses], dtype=np.float64)
+        elif any(hasattr(e, "calcChangepoints") for e in self.eclipses):
+            raise ValueError("the tree mixes GP and chi-squared eclipses")
         n = [e.lc.n_data for e in self.eclipses]
         self.lc_off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
         cat = lambda attr: np.concatenate([np.asarray(getattr(e.lc, attr), dtype=np.float64) for e in self.eclipses])
@@ -72,6 +83,10 @@ class FlatLayout:
         engine.set_priors(self.prior_src, self.prior_type, self.prior_p1, self.prior_p2, self.prior_norm,
                           self.prior_isvar)
         engine.set_lightcurves(self.lc_off, self.lc_phase, self.lc_width, self.lc_y, self.lc_ye)
+        if self.gp:
+            engine.set_gp(self.gp_src, self.gp_dist)
+        else:
+            engine.set_gp()
 
 
 class VectorModel:
@@ -110,5 +125,6 @@ class VectorModel:
     __call__ = ln_prob
 
     def chisq(self, theta):
-        """Per-eclipse chi-squared, shape (n, n_ecl) (SimpleEclipse.chisq for every leaf)."""
+        """Per-eclipse chi-squared, shape (n, n_ecl) (SimpleEclipse.chisq for every leaf); for a GP
+        tree, -2 ln L of every leaf."""
         return self._eval(theta, _cabi.LN_LIKE, return_chisq=True)[1]

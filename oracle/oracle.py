@@ -205,3 +205,71 @@ def log_prob(layout, theta, what=2, cfg=None, nthreads=0, return_chisq=False):
 
 def max_threads():
     return lib().lfo_max_threads()
+
+
+# ---------------------------------------------------------------------------------------------
+# Gaussian-process likelihood (/root/reference/CVModel.py:527-696).
+# george is not installed and its HODLR solver only approximates K^-1 (default tol 0.1), so the
+# oracle is the exact dense statement of the same kernel: build K, Cholesky, ln L.  PARITY
+# UNPINNED against george for the same reason as the rest of this file.
+
+GP_WHITE_NOISE = 1.25e-12  # george.GP default white_noise = ln(TINY), TINY = 1.25e-12
+
+
+def wdphases(q, incl_deg, r1, ntheta=10):
+    """Third and fourth contact phases of the white dwarf (trm.roche.wdphases; call site
+    CVModel.py:562, which passes rwd as r1): the earliest and the latest egress phase over
+    ntheta points on the limb of a disc of radius r1 (units of a) facing the observer."""
+    eg = []
+    for k in range(int(ntheta)):
+        a = 2.0 * np.pi * k / ntheta
+        res = ingress_egress(q, incl_deg, (0.0, 0.0, 0.0), xi=r1 * np.cos(a), eta=r1 * np.sin(a), solver=SOLVER_ROBUST)
+        if res is None:
+            raise RocheError("wdphases: a limb point is never eclipsed")
+        eg.append(res[1])
+    return min(eg), max(eg)
+
+
+def gp_dist_cp(q, dphi, rwd, ntheta=10):
+    """Distance of the GP change points from mid-eclipse (CVModel.py:558-568)."""
+    inc = findi(q, dphi)
+    phi3, phi4 = wdphases(q, inc, rwd, ntheta)
+    return (dphi + (phi4 - phi3)) / 2.0
+
+
+def gp_changepoints(x, dist_cp, phi0):
+    """[[egress of the previous eclipse, ingress of this one], ...] (CVModel.py:580-599)."""
+    x = np.asarray(x, dtype=np.float64)
+    lo, hi = int(np.floor(x.min())), int(np.ceil(x.max()))
+    return [[(e - 1) + dist_cp + phi0, e - dist_cp + phi0] for e in range(lo, hi + 1)
+            if e > x.min() and e < 1 + x.max()]
+
+
+def gp_kernel_matrix(x, ye, ampin, ampout, tau, gaps):
+    """ampin * Matern32(tau) + sum over gaps of ampout * Matern32(tau, block=gap), plus the
+    diagonal george adds in compute(x, yerr) (CVModel.py:636-645,687)."""
+    x = np.asarray(x, dtype=np.float64)
+    r = np.sqrt(3.0 * (x[:, None] - x[None, :]) ** 2 / tau)
+    m32 = (1.0 + r) * np.exp(-r)
+    K = ampin * m32
+    for a, b in gaps:
+        ins = (x >= a) & (x <= b)
+        K = K + ampout * m32 * (ins[:, None] & ins[None, :])
+    return K + np.diag(np.asarray(ye, dtype=np.float64) ** 2 + GP_WHITE_NOISE)
+
+
+def gp_log_like(x, ye, resid, ampin, ampout, tau, gaps):
+    """george.GP.log_likelihood(resid, quiet=True) for that kernel, evaluated exactly."""
+    resid = np.asarray(resid, dtype=np.float64)
+    if not np.all(np.isfinite(resid)):
+        return -np.inf
+    if not (ampin > 0 and ampout > 0 and tau > 0 and np.isfinite(ampin + ampout + tau)):
+        return -np.inf
+    K = gp_kernel_matrix(x, ye, ampin, ampout, tau, gaps)
+    try:
+        L = np.linalg.cholesky(K)
+    except np.linalg.LinAlgError:
+        return -np.inf
+    z = np.linalg.solve(L, resid)
+    out = -0.5 * (z @ z) - np.log(np.diag(L)).sum() - 0.5 * len(resid) * np.log(2.0 * np.pi)
+    return float(out) if np.isfinite(out) else -np.inf

@@ -160,11 +160,11 @@ def test_nodata_dummy(tmp_path):
     assert lc.n_data == 1000 and lc.x[0] == -0.5 and np.all(lc.y == 0) and np.all(lc.ye == 1)
 
 
-def test_gp_is_refused(tmp_path):
+def test_gp_input_needs_the_hyper_parameters(tmp_path):
     path = write_input(tmp_path)
     txt = open(path).read().replace("useGP = 0", "useGP = 1")
     open(path, "w").write(txt)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(KeyError):        # ln_ampin_gp & co. are missing from the file (tests/test_gp.py has them)
         construct_model(path)
 
 
