@@ -301,6 +301,27 @@ def run_gpu(args, rank, local_rank, world):
             serial_trace.append(eng1.last_trace_ms())
     eng1.close()
 
+    # the same pass judged by the Gaussian process (useGP = 1 trees): residuals + gp_kernel instead of chi-squared
+    gp = None
+    if rank == 0 and not args.no_gp:
+        os.environ["LFB_LANES"] = "1"
+        eng_gp = _cabi.Engine(local_rank, **wl.grid)
+        os.environ.pop("LFB_LANES")
+        wl.apply_gp(eng_gp)
+        eng_gp.set_trace(True)
+        gp_ms, gp_tr = [], []
+        for i in range(3 + args.steps):
+            flush.fill_(float(i))
+            eng_gp.log_prob_device(theta_d.data_ptr(), n, lnp_d.data_ptr(), what=_cabi.LN_PROB, stream=stream)
+            torch.cuda.synchronize()
+            if i >= 3:
+                gp_ms.append(eng_gp.last_stage_ms()["total"])
+                gp_tr.append(eng_gp.last_trace_ms()["gp_kernel"])
+        eng_gp.close()
+        gp = {"ms_per_pass_one_lane": float(np.mean(gp_ms)), "gp_kernel_ms": float(np.mean(gp_tr)),
+              "lightcurve_evals_per_s": n * wl.n_ecl / (float(np.mean(gp_ms)) * 1e-3),
+              "note": "GPLCModel likelihood (4-state Kalman filter per eclipse) on the same walkers, one lane"}
+
     if rank == 0:
         evals_per_step = world * n * wl.n_ecl
         value = evals_per_step * args.steps / (total_ms * 1e-3)
@@ -348,6 +369,7 @@ def run_gpu(args, rank, local_rank, world):
                        "parallelism": "walkers sharded, %d rank(s)" % world,
                        "collective": "nccl all_gather of ln_prob + positions" if world > 1 else "none"},
             "ensemble_passes_per_s": args.steps / (total_ms * 1e-3),
+            "gp_likelihood": gp,
             "emcee_steps_per_s": mc_steps_per_s,
             "emcee": {"walkers_per_gpu": n, "steps_timed": n_mc, "acceptance_fraction": acc_frac,
                       "note": "host stretch move (numpy) + one CUDA ln_prob call per half-step, host buffers",
@@ -380,6 +402,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--kernel-rev", default="r1")
+    ap.add_argument("--no-gp", action="store_true", help="skip the Gaussian-process likelihood leg")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":

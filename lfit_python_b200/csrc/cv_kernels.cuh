@@ -1081,39 +1081,58 @@ __global__ void __launch_bounds__(kFluxThreads, CTAS) flux_kernel(const __grid_c
 }
 
 // ---------------------------------------------------------------- gp_kernel
-// SimpleGPEclipse.ln_like (CVModel.py:650-696): thread per (eclipse, walker) -- walkers fastest, so
-// that a warp reads one row of the residual matrix -- runs the Kalman filter of gp_device.cuh over
-// the eclipse's points and leaves -2 ln L where the chi-squared would be.
-__global__ void __launch_bounds__(128) gp_kernel(const __grid_constant__ FluxArgs A)
+// SimpleGPEclipse.ln_like (CVModel.py:650-696): thread per (eclipse, walker); a block holds kGpThreads
+// walkers of one eclipse.  The filter is a serial recursion over the eclipse's points, so what
+// matters is the latency of one step: the block stages tiles of kGpTile points (coalesced rows of
+// the residual matrix, the shared times and variances) in shared memory and every thread steps its
+// filter from there.  Leaves -2 ln L where the chi-squared would be.
+constexpr int kGpThreads = 32;
+constexpr int kGpTile = 32;
+
+__global__ void __launch_bounds__(kGpThreads) gp_kernel(const __grid_constant__ FluxArgs A)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= A.njobs) return;
-    const int e = (int)(t / A.n_walkers);
-    const long long w = t - (long long)e * A.n_walkers;
-    const long long job = w * A.L.n_ecl + e;
-    if (!job_live(A, A.ws[w], A.js[job])) return;  // the flux kernel left NaN / +inf there
-    const double* th = A.theta + w * A.L.ndim;
+    __shared__ double r_tile[kGpTile][kGpThreads];
+    __shared__ double x_tile[kGpTile], v_tile[kGpTile];
+    const int e = blockIdx.y, tid = threadIdx.x;
+    const long long w0 = (long long)blockIdx.x * kGpThreads, w = w0 + tid;
     const long long lc0 = A.smp.lc_off[e];
     const int n_ph = (int)(A.smp.lc_off[e + 1] - lc0);
+    const long long job = w * A.L.n_ecl + e;
+    const bool live = w < A.n_walkers && job_live(A, A.ws[w], A.js[job]);  // else the flux kernel left NaN / +inf
     GpPars G;
-    G.a_in = exp(fetch(A.L, th, A.gp_src[0]));
-    G.a_out = exp(fetch(A.L, th, A.gp_src[1]));
-    G.tau = exp(fetch(A.L, th, A.gp_src[2]));
-    const double phi0 = fetch(A.L, th, A.L.gather[e * LFB_NPAR + P_PHI0]);
-    const double2 span = A.smp.gp_span[e];
-    const double dist = A.gp_dist[e];
-    double ll = -INFINITY;
-    if (dist > 0.0) {
-        gp_changepoints(span.x, span.y, dist, phi0, G);
-        const double* x = A.smp.gp_x + lc0;
-        const double* var = A.smp.gp_var + lc0;
-        const double* r = A.gp_resid + lc0 * A.n_walkers + w;
-        const long long stride = A.n_walkers;
-        ll = gp_loglike(
-            n_ph, [&](int k) { return __ldg(x + k); }, [&](int k) { return __ldg(var + k); },
-            [&](int k) { return r[(long long)k * stride]; }, G);
+    GpFilter F;
+    bool run = false;
+    if (live) {
+        const double* th = A.theta + w * A.L.ndim;
+        G.a_in = exp(fetch(A.L, th, A.gp_src[0]));
+        G.a_out = exp(fetch(A.L, th, A.gp_src[1]));
+        G.tau = exp(fetch(A.L, th, A.gp_src[2]));
+        const double phi0 = fetch(A.L, th, A.L.gather[e * LFB_NPAR + P_PHI0]);
+        const double2 span = A.smp.gp_span[e];
+        const double dist = A.gp_dist[e];
+        run = dist > 0.0;
+        if (run) {
+            gp_changepoints(span.x, span.y, dist, phi0, G);
+            F.init(G);
+        }
     }
-    A.chisq_job[job] = -2.0 * ll;
+    const int ncol = (int)min((long long)kGpThreads, A.n_walkers - w0);
+    for (int k0 = 0; k0 < n_ph; k0 += kGpTile) {
+        const int rows = min(kGpTile, n_ph - k0);
+        __syncthreads();
+        for (int i = tid; i < rows * kGpThreads; i += kGpThreads) {
+            const int row = i / kGpThreads, col = i - row * kGpThreads;
+            if (col < ncol) r_tile[row][col] = A.gp_resid[(lc0 + k0 + row) * A.n_walkers + w0 + col];
+        }
+        if (tid < rows) {
+            x_tile[tid] = __ldg(A.smp.gp_x + lc0 + k0 + tid);
+            v_tile[tid] = __ldg(A.smp.gp_var + lc0 + k0 + tid);
+        }
+        __syncthreads();
+        if (run)
+            for (int r = 0; r < rows; ++r) F.step(G, x_tile[r], v_tile[r], r_tile[r][tid]);
+    }
+    if (live) A.chisq_job[job] = run ? -2.0 * F.result() : INFINITY;
 }
 
 // lfb_gp_loglike: the same likelihood for caller-supplied residuals, thread per set

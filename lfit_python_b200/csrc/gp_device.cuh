@@ -31,9 +31,11 @@ struct GpPars {
 // index of the gap holding x, -1 if none
 LFB_HD int gp_gap_of(const GpPars& G, double x)
 {
-    for (int k = 0; k < G.n_gaps; ++k)
-        if (x >= G.gap[k][0] && x <= G.gap[k][1]) return k;
-    return -1;
+    int found = -1;
+#pragma unroll
+    for (int k = kMaxGaps - 1; k >= 0; --k)  // fixed trip count: the table stays in registers
+        if (k < G.n_gaps && x >= G.gap[k][0] && x <= G.gap[k][1]) found = k;
+    return found;
 }
 
 // The change points of an eclipse's light curve (CVModel.py:580-599): one gap per cycle number e
@@ -50,28 +52,49 @@ LFB_HD void gp_changepoints(double x_min, double x_max, double dist_cp, double p
     }
 }
 
-// ln L of residuals r(k), k = 0..n-1, taken at ascending times x(k) with noise variances var(k).
-// -inf for a non-finite residual or an invalid kernel (what quiet=True returns).
-template <class FX, class FV, class FR>
-LFB_HD double gp_loglike(int n, FX x, FV var, FR r, const GpPars& G)
-{
-    const double ninf = -INFINITY;
-    if (!(G.a_in > 0.0) || !(G.a_out > 0.0) || !(G.tau > 0.0) || !(G.a_in < 1e300) || !(G.a_out < 1e300) ||
-        !(G.tau < 1e300))
-        return ninf;
-    const double c = sqrt(3.0 / G.tau), c2 = c * c;
-    // state (f1, f1', f2, f2'): mean m, covariance P (upper triangle), both processes at their priors
-    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
-    double p00 = G.a_in, p01 = 0.0, p11 = G.a_in * c2;
-    double p02 = 0.0, p03 = 0.0, p12 = 0.0, p13 = 0.0;
-    double p22 = G.a_out, p23 = 0.0, p33 = G.a_out * c2;
-    int cur_gap = -1;
-    double xp = 0.0, ll = 0.0;
-    for (int k = 0; k < n; ++k) {
-        const double xk = x(k);
+// The filter, one data point at a time (so that a kernel can feed it from staged tiles).
+struct GpFilter {
+    double c, c2;
+    double m0, m1, m2, m3;                                    // state mean (f1, f1', f2, f2')
+    double p00, p01, p11, p02, p03, p12, p13, p22, p23, p33;  // state covariance, upper triangle
+    double xp, ll, sprod;
+    double g_lo, g_hi;  // the first gap that does not end before the current point (times ascend)
+    int gi, cur_gap, k, nprod;
+    bool bad;
+
+    LFB_HD void init(const GpPars& G)
+    {
+        bad = !(G.a_in > 0.0) || !(G.a_out > 0.0) || !(G.tau > 0.0) || !(G.a_in < 1e300) || !(G.a_out < 1e300) ||
+              !(G.tau < 1e300);
+        const double tau = bad ? 1.0 : G.tau;
+        c = sqrt(3.0 / tau);
+        c2 = c * c;
+        // both processes at their priors
+        m0 = m1 = m2 = m3 = 0.0;
+        p00 = G.a_in; p01 = 0.0; p11 = G.a_in * c2;
+        p02 = p03 = p12 = p13 = 0.0;
+        p22 = G.a_out; p23 = 0.0; p33 = G.a_out * c2;
+        cur_gap = -1;
+        k = 0;
+        xp = 0.0;
+        ll = 0.0;
+        sprod = 1.0;
+        nprod = 0;
+        gi = 0;
+        g_lo = G.n_gaps > 0 ? G.gap[0][0] : INFINITY;
+        g_hi = G.n_gaps > 0 ? G.gap[0][1] : INFINITY;
+    }
+
+    // one data point: time xk (not before the previous one), noise variance vk, residual rk
+    LFB_HD void step(const GpPars& G, double xk, double vk, double rk)
+    {
+        if (bad) return;
         if (k > 0) {
             const double dt = xk - xp;
-            if (!(dt >= 0.0)) return ninf;  // times must ascend
+            if (!(dt >= 0.0)) {  // times must ascend
+                bad = true;
+                return;
+            }
             const double ed = exp(-c * dt);
             const double a = ed * (1.0 + c * dt), b = ed * dt, cc = -ed * c2 * dt, d = ed * (1.0 - c * dt);
             // mean
@@ -101,7 +124,13 @@ LFB_HD double gp_loglike(int n, FX x, FV var, FR r, const GpPars& G)
             }
         }
         xp = xk;
-        const int gk = gp_gap_of(G, xk);
+        ++k;
+        while (xk > g_hi) {  // rarely: the point has left gap gi behind
+            ++gi;
+            g_lo = gi < G.n_gaps ? G.gap[gi][0] : INFINITY;
+            g_hi = gi < G.n_gaps ? G.gap[gi][1] : INFINITY;
+        }
+        const int gk = xk >= g_lo ? gi : -1;
         if (gk >= 0 && gk != cur_gap) {
             // a new gap: its process is independent of everything before
             cur_gap = gk;
@@ -112,22 +141,57 @@ LFB_HD double gp_loglike(int n, FX x, FV var, FR r, const GpPars& G)
             p33 = G.a_out * c2;
         }
         const double g = gk >= 0 ? 1.0 : 0.0;
-        const double rk = r(k), vk = var(k) + kGpWhiteNoise;
-        if (!(fabs(rk) < 1e300) || !(vk > 0.0)) return ninf;
+        vk += kGpWhiteNoise;
+        if (!(fabs(rk) < 1e300) || !(vk > 0.0)) {
+            bad = true;
+            return;
+        }
         // observation H = (1, 0, g, 0)
         const double h0 = p00 + g * p02, h1 = p01 + g * p12, h2 = p02 + g * p22, h3 = p03 + g * p23;  // P H^T
         const double s = h0 + g * h2 + vk;
-        if (!(s > 0.0) || !(s < 1e300)) return ninf;
-        const double v = rk - (m0 + g * m2), is = 1.0 / s;
+        if (!(s > 0.0) || !(s < 1e300)) {
+            bad = true;
+            return;
+        }
+        double is = fast_rcp(s);
+        is = is * fma(-s, is, 2.0);  // fast_rcp is good to ~1e-11; one more Newton step
+        const double v = rk - (m0 + g * m2);
         const double k0 = h0 * is, k1 = h1 * is, k2 = h2 * is, k3 = h3 * is;
         m0 += k0 * v; m1 += k1 * v; m2 += k2 * v; m3 += k3 * v;
         p00 -= k0 * h0; p01 -= k0 * h1; p02 -= k0 * h2; p03 -= k0 * h3;
         p11 -= k1 * h1; p12 -= k1 * h2; p13 -= k1 * h3;
         p22 -= k2 * h2; p23 -= k2 * h3;
         p33 -= k3 * h3;
-        ll -= 0.5 * (v * v * is + log(s) + kLn2Pi);
+        // ln s summed as the ln of a running product, eight factors at a time (s is a variance of order
+        // 1e-10..1; the guard keeps the product far from under- and overflow)
+        ll -= 0.5 * (v * v * is + kLn2Pi);
+        sprod *= s;
+        if (++nprod == 8 || !(sprod > 1e-250) || !(sprod < 1e250)) flush();
     }
-    return ll == ll ? ll : ninf;
+
+    LFB_HD void flush()
+    {
+        ll -= 0.5 * log(sprod);
+        sprod = 1.0;
+        nprod = 0;
+    }
+
+    // -inf for a non-finite residual or an invalid kernel (what quiet=True returns)
+    LFB_HD double result()
+    {
+        flush();
+        return (!bad && ll == ll) ? ll : -INFINITY;
+    }
+};
+
+// ln L of residuals r(k), k = 0..n-1, taken at ascending times x(k) with noise variances var(k).
+template <class FX, class FV, class FR>
+LFB_HD double gp_loglike(int n, FX x, FV var, FR r, const GpPars& G)
+{
+    GpFilter F;
+    F.init(G);
+    for (int k = 0; k < n; ++k) F.step(G, x(k), var(k), r(k));
+    return F.result();
 }
 
 }  // namespace lfb

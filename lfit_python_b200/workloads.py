@@ -183,6 +183,27 @@ class Workload:
             engine.set_lightcurves(self.lc_off, self.lc_phase, self.lc_width, self.lc_y, self.lc_ye)
 
 
+    def apply_gp(self, engine, ln_hyper=(-9.5118, -9.0953, -2.2131)):
+        """The same layout judged by the Gaussian process (GPLCModel, CVModel.py:494-711): the three
+        ln hyper-parameters as fixed Params (defaults: test_data/mcmc_input.dat:43-45), change points
+        from the truth parameters."""
+        consts = np.concatenate([self.consts, np.asarray(ln_hyper, dtype=np.float64)])
+        nc = self.consts.shape[0]
+        engine.set_layout(self.ndim, self.npars, self.gather, consts)
+        engine.set_priors(self.prior_src, self.prior_type, self.prior_p1, self.prior_p2, self.prior_norm,
+                          self.prior_isvar)
+        engine.set_lightcurves(self.lc_off, self.lc_phase, self.lc_width, self.lc_y, self.lc_ye)
+        q, dphi, rwd = (self.p0[self.names.index(n + "_core")] for n in ("q", "dphi", "rwd"))
+        from . import _cabi
+        inc, ok = engine.roche(_cabi.ROCHE_FINDI, q, dphi)
+        ph, ok2 = engine.wdphases(q, inc[0, 0], rwd, 10)
+        if not (ok.all() and ok2.all()):
+            raise RuntimeError("no change points for the truth parameters")
+        dist = (dphi + (ph[0, 1] - ph[0, 0])) / 2.0
+        engine.set_gp(np.asarray([-(nc + 1), -(nc + 2), -(nc + 3)], dtype=np.int32), np.full(self.n_ecl, dist))
+        return dist
+
+
 def config(idx, **over):
     """The five BASELINE.json configurations (index 0..4)."""
     specs = [
