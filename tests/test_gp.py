@@ -216,3 +216,24 @@ def test_gp_tree_vector_path_matches_oracle_and_scalar_path(tmp_path, engine):
     vec.engine.set_gp()
     chi = vec.ln_like(theta[:2])
     assert np.all(chi != got[:2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_gp", [0, 1])
+def test_driver_runs_end_to_end(tmp_path, monkeypatch, capsys, use_gp):
+    """python -m lfit_python_b200.mcmcfit input.dat: burn-in, production chain, chain file (mcmcfit.py:162-330)."""
+    from lfit_python_b200 import mcmcfit, mcmc_utils
+    path = gp_input(tmp_path) if use_gp else write_input(tmp_path)
+    txt = open(path).read().replace("fit = 0", "fit = 1").replace("nburn = 10", "nburn = 3")
+    txt = txt.replace("nprod = 10", "nprod = 4").replace("nwalkers = 40", "nwalkers = 96")
+    open(path, "w").write(txt)
+    monkeypatch.chdir(tmp_path)
+    sampler = mcmcfit.main([path, "--seed", "3"])
+    out = capsys.readouterr().out
+    assert "Initial guess has a chisq of" in out and "Starting the main MCMC chain." in out
+    ndim = sampler.chain.shape[-1]
+    assert sampler.chain.shape == (96, 4, ndim)
+    assert np.all(np.isfinite(sampler.lnprobability))
+    chain = mcmc_utils.readchain(str(tmp_path / "chain_prod.txt"))
+    assert chain.shape == (96, 4, ndim + 1)
+    assert np.allclose(chain[:, -1, :ndim], sampler.chain[:, -1, :], rtol=1e-5, atol=1e-6)   # "%f"-style file precision
