@@ -57,7 +57,7 @@ def env_int(name, default):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons with NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -261,7 +261,7 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    n_mc = max(5, args.steps)
+    n_mc = min(max(5, args.steps), 50)
     sampler.run_mcmc(state[0], n_mc, log_prob0=state[1], store=False)
     mc_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -292,7 +292,7 @@ def run_gpu(args, rank, local_rank, world):
     wl.apply(eng1)
     eng1.set_trace(True)
     serial_stage, serial_trace = [], []
-    for i in range(3 + args.steps):
+    for i in range(3 + min(args.steps, 20)):
         flush.fill_(float(i))
         eng1.log_prob_device(theta_d.data_ptr(), n, lnp_d.data_ptr(), what=_cabi.LN_PROB, stream=stream)
         torch.cuda.synchronize()
@@ -310,7 +310,7 @@ def run_gpu(args, rank, local_rank, world):
         wl.apply_gp(eng_gp)
         eng_gp.set_trace(True)
         gp_ms, gp_tr = [], []
-        for i in range(3 + args.steps):
+        for i in range(3 + min(args.steps, 20)):
             flush.fill_(float(i))
             eng_gp.log_prob_device(theta_d.data_ptr(), n, lnp_d.data_ptr(), what=_cabi.LN_PROB, stream=stream)
             torch.cuda.synchronize()
@@ -392,7 +392,7 @@ def run_gpu(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, help="BASELINE.json config index (default 1: the metric's config)")

@@ -136,6 +136,14 @@ int lfb_gp_loglike(lfb_handle *h, long long n_sets, int n, const double *x, cons
 int lfb_wdphases(lfb_handle *h, long long n, const double *q, const double *incl_deg, const double *r1, int ntheta,
                  double *out, int *ok);
 
+/* Stage (1) on its own: ingress / egress phases (cycles, ingress < egress) of surface elements
+ * seen at inclination incl_deg in a binary of mass ratio q.  pts[n][5] = (x, y, z, xi, eta): a
+ * point fixed in the rotating frame (units of a, origin at the white dwarf) plus an offset fixed
+ * on the sky (xi along the orbital motion at phase 0, eta towards the projected pole).  ok[n] = 0:
+ * never eclipsed (out = NaN).  No reference counterpart (lfit does this internally); parity tests. */
+int lfb_ingress_egress(lfb_handle *h, long long n, const double *q, const double *incl_deg, const double *pts,
+                       double *out, int *ok);
+
 /* counters for bench.py: kernels launched by this handle since creation */
 long long lfb_launch_count(const lfb_handle *h);
 /* Device time (ms) of the stages of the last lfb_log_prob (its last batch), from CUDA events

@@ -22,7 +22,7 @@ EXPORTS = (
     "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_get_config", "lfb_set_layout",
     "lfb_set_priors", "lfb_set_lightcurves", "lfb_log_prob", "lfb_calc_flux", "lfb_roche",
     "lfb_launch_count", "lfb_last_kernel_ms", "lfb_last_stage_ms", "lfb_measure_fp64_peak",
-    "lfb_set_trace", "lfb_last_trace_ms", "lfb_set_gp", "lfb_gp_loglike", "lfb_wdphases",
+    "lfb_set_trace", "lfb_last_trace_ms", "lfb_set_gp", "lfb_gp_loglike", "lfb_wdphases", "lfb_ingress_egress",
 )
 TRACE_KERNELS = ("walker_kernel", "jobcheck_kernel", "elements_kernel<1> disc", "elements_kernel<0> white dwarf",
                  "elements_kernel<3> donor", "elements_kernel<2> strip", "prep_kernel", "positions_kernel",
@@ -82,6 +82,7 @@ def load():
     lib.lfb_set_gp.argtypes = [vp, C.c_int, ip, dp]
     lib.lfb_gp_loglike.argtypes = [vp, C.c_longlong, C.c_int, dp, dp, dp, dp, C.c_int, dp, dp]
     lib.lfb_wdphases.argtypes = [vp, C.c_longlong, dp, dp, dp, C.c_int, dp, ip]
+    lib.lfb_ingress_egress.argtypes = [vp, C.c_longlong, dp, dp, dp, dp, ip]
     _lib = lib
     return lib
 
@@ -201,6 +202,20 @@ class Engine:
         ok = np.empty(n, dtype=np.int32)
         self._check(self._lib.lfb_wdphases(self._h, n, _dp(q), _dp(incl_deg), _dp(r1), int(ntheta), _dp(out),
                                            ok.ctypes.data_as(C.POINTER(C.c_int))), "lfb_wdphases")
+        return out, ok.astype(bool)
+
+    def ingress_egress(self, q, incl_deg, pts):
+        """Ingress / egress phases of elements pts (n, 5) = (x, y, z, xi, eta); (n, 2) and an ok mask."""
+        pts = np.atleast_2d(_f64(pts))
+        n = pts.shape[0]
+        q = np.ascontiguousarray(np.broadcast_to(_f64(q), (n,)))
+        incl_deg = np.ascontiguousarray(np.broadcast_to(_f64(incl_deg), (n,)))
+        if pts.shape[1] != 5:
+            raise ValueError("ingress_egress: pts must be (n, 5)")
+        out = np.empty((n, 2))
+        ok = np.empty(n, dtype=np.int32)
+        self._check(self._lib.lfb_ingress_egress(self._h, n, _dp(q), _dp(incl_deg), _dp(pts), _dp(out),
+                                                 ok.ctypes.data_as(C.POINTER(C.c_int))), "lfb_ingress_egress")
         return out, ok.astype(bool)
 
     def measure_fp64_peak(self, iters=20000):

@@ -1187,6 +1187,26 @@ __global__ void wdphases_kernel(long long n, const double* __restrict__ q, const
     ok[i] = good;
 }
 
+// lfb_ingress_egress: the element solve of stage (1) on its own, thread per element
+__global__ void ingress_egress_kernel(long long n, const double* __restrict__ q, const double* __restrict__ incl,
+                                      const double* __restrict__ pts, double* __restrict__ out, int* __restrict__ ok)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Roche R;
+    int good = 0;
+    double pin = NAN, pout = NAN;
+    if (roche_init(q[i], R) && incl[i] > 0.0 && incl[i] <= 90.0) {
+        double si, ci;
+        sincos_(incl[i] * kDeg, &si, &ci);
+        const Point T = {pts[5 * i], pts[5 * i + 1], pts[5 * i + 2], pts[5 * i + 3], pts[5 * i + 4]};
+        good = ingress_egress(R, si, ci, T, &pin, &pout);
+    }
+    out[2 * i] = good ? pin : NAN;
+    out[2 * i + 1] = good ? pout : NAN;
+    ok[i] = good;
+}
+
 // ---------------------------------------------------------------- finish_kernel
 // Node.ln_prob = ln_prior + sum of -chi^2/2 with the -inf rules (model.py:476-498)
 __global__ void finish_kernel(int what, int n_ecl, long long n, const WalkerScal* __restrict__ ws,

@@ -1118,6 +1118,38 @@ int lfb_wdphases(lfb_handle* h, long long n, const double* q, const double* incl
     return LFB_OK;
 }
 
+int lfb_ingress_egress(lfb_handle* h, long long n, const double* q, const double* incl_deg, const double* pts, double* out,
+                       int* ok)
+{
+    if (!h) return LFB_EINVAL;
+    if (n < 0 || (n && (!q || !incl_deg || !pts || !out || !ok))) return fail(h, LFB_EINVAL, "ingress_egress: bad arguments");
+    if (n == 0) return LFB_OK;
+    CK(cudaSetDevice(h->device));
+    DevBuf dq, di, dp, dout, dok;
+    auto cleanup = [&]() { dq.release(); di.release(); dp.release(); dout.release(); dok.release(); };
+    cudaError_t e;
+    if ((e = dq.reserve(8 * (size_t)n)) != cudaSuccess || (e = di.reserve(8 * (size_t)n)) != cudaSuccess ||
+        (e = dp.reserve(40 * (size_t)n)) != cudaSuccess || (e = dout.reserve(16 * (size_t)n)) != cudaSuccess ||
+        (e = dok.reserve(4 * (size_t)n)) != cudaSuccess) {
+        cleanup();
+        return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    }
+    cudaStream_t st = h->stream;
+    cudaMemcpyAsync(dq.p, q, 8 * (size_t)n, cudaMemcpyDefault, st);
+    cudaMemcpyAsync(di.p, incl_deg, 8 * (size_t)n, cudaMemcpyDefault, st);
+    cudaMemcpyAsync(dp.p, pts, 40 * (size_t)n, cudaMemcpyDefault, st);
+    ingress_egress_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, dq.as<double>(), di.as<double>(), dp.as<double>(),
+                                                                      dout.as<double>(), dok.as<int>());
+    h->launches++;
+    cudaMemcpyAsync(out, dout.p, 16 * (size_t)n, cudaMemcpyDefault, st);
+    cudaMemcpyAsync(ok, dok.p, 4 * (size_t)n, cudaMemcpyDefault, st);
+    e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    return LFB_OK;
+}
+
 int lfb_roche(lfb_handle* h, int which, long long n, const double* a, const double* b, double* out, int* ok)
 {
     if (!h) return LFB_EINVAL;

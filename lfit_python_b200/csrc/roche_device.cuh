@@ -510,6 +510,7 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         c = side ? c1 : c0;
         s = side ? s1 : s0;
         lam = side ? lam1 : lam0;
+#ifndef LFB_NO_WARMUP
         {
             float cf = (float)c, sf = (float)s, lf = (float)lam;
             if (warm_root(muf, omuf, phicf, sif, cif, Tf, (float)cm, (float)sm, (float)sg, cf, sf, lf)) {
@@ -520,6 +521,7 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
                 lam = (double)lf;
             }
         }
+#endif
         bool conv = false;
         for (int it = 0; it < kRootIters; ++it) {
             ray_eval(R, si, ci, T, c, s, lam, D);

@@ -122,11 +122,19 @@ static void tileset_free(tileset *t)
     memset(t, 0, sizeof(*t));
 }
 
+/* Orbital phase is periodic and the solvers may return an interval that runs past +-0.5 (elements
+ * on the far side of the donor, eclipsed around phase 0.5): test the neighbouring cycles too. */
 static inline double tileset_visible(const tileset *t, double ph)
 {
     double s = 0.0;
-    for (int k = 0; k < t->n; ++k)
-        if (!(t->has[k] && ph > t->in[k] && ph < t->out[k])) s += t->w[k];
+    for (int k = 0; k < t->n; ++k) {
+        int ecl = 0;
+        if (t->has[k]) {
+            const double a = t->in[k], b = t->out[k];
+            ecl = (ph > a && ph < b) || (ph + 1.0 > a && ph + 1.0 < b) || (ph - 1.0 > a && ph - 1.0 < b);
+        }
+        if (!ecl) s += t->w[k];
+    }
     return s;
 }
 

@@ -143,3 +143,58 @@ def test_log_prob_tree(engine):
     np.testing.assert_allclose(got[fin], ref[fin], rtol=1e-7)
     m = np.isfinite(rchi)
     np.testing.assert_allclose(chi[m], rchi[m], rtol=1e-7)
+
+
+def test_element_solver_on_the_device_matches_the_oracle(engine):
+    """Stage (1) alone through lfb_ingress_egress: disc-plane, sky-plane and far-away elements (behind the
+    donor, eclipsed around phase 0.5) against the oracle's Newton and scan + bisection solvers."""
+    rng = np.random.default_rng(21)
+    n = 3000
+    q = rng.uniform(0.03, 1.0, n)
+    inc = rng.uniform(65.0, 90.0, n)
+    pts = np.zeros((n, 5))
+    r = 10.0 ** rng.uniform(-1.5, 0.9, n)
+    az = rng.uniform(0, 2 * np.pi, n)
+    pts[:, 0], pts[:, 1] = r * np.cos(az), r * np.sin(az)
+    pts[::3, 2] = rng.uniform(-0.02, 0.02, len(pts[::3]))
+    sky = np.arange(n) % 5 == 0                      # white-dwarf tiles: offsets fixed on the sky
+    pts[sky, :3] = 0.0
+    pts[sky, 3] = rng.uniform(-0.03, 0.03, sky.sum())
+    pts[sky, 4] = rng.uniform(-0.03, 0.03, sky.sum())
+    out, ok = engine.ingress_egress(q, inc, pts)
+    worst, necl = 0.0, 0
+    for k in range(n):
+        solver = O.SOLVER_ROBUST if k % 8 == 0 else O.SOLVER_NEWTON
+        ref = O.ingress_egress(q[k], inc[k], tuple(pts[k, :3]), xi=pts[k, 3], eta=pts[k, 4], solver=solver)
+        assert (ref is not None) == bool(ok[k]), (k, q[k], inc[k], pts[k])
+        if ref is not None:
+            necl += 1
+            worst = max(worst, abs(ref[0] - out[k, 0]), abs(ref[1] - out[k, 1]))
+    assert necl > n // 4 and worst < 1e-11
+
+
+@pytest.mark.parametrize("cfg,n,n_ph", [(1, 1500, 160), (0, 800, 200), (2, 300, 120)])
+def test_whole_prior_box(engine, cfg, n, n_ph):
+    """Walkers drawn uniformly between the prior limits (long strips reaching behind the donor, grazing
+    inclinations, huge discs ...): validity masks identical, chi-squared to 1e-7 (tools/wide_sweep.py)."""
+    wl = workloads.config(cfg, n_ph=n_ph)
+    wl.make_data(lambda p, x, w: engine.calc_flux(p, x, w))
+    wl.apply(engine)
+    lay = O.FlatLayout(wl.ndim, wl.npars, wl.gather, wl.consts, wl.prior_src, wl.prior_type, wl.prior_p1, wl.prior_p2,
+                       wl.prior_norm, wl.prior_isvar, wl.lc_off, wl.lc_phase, wl.lc_width, wl.lc_y, wl.lc_ye)
+    rng = np.random.default_rng(5 + cfg)
+    lo, hi = wl.prior_p1.copy(), wl.prior_p2.copy()
+    gauss = np.isin(wl.prior_type, (0, 1))
+    lo[gauss], hi[gauss] = wl.prior_p1[gauss] - 3 * wl.prior_p2[gauss], wl.prior_p1[gauss] + 3 * wl.prior_p2[gauss]
+    theta = lo + (hi - lo) * rng.random((n, wl.ndim))
+    keep = rng.random((n // 2, wl.ndim)) < 0.7      # half of them: mostly the truth, a few wide-open parameters
+    theta[:n // 2] = np.where(keep, wl.p0, theta[:n // 2])
+    ref, rchi = O.log_prob(lay, theta, what=_cabi.LN_LIKE, return_chisq=True)
+    got, chi = engine.log_prob(theta, what=_cabi.LN_LIKE, return_chisq=True)
+    assert np.array_equal(np.isfinite(rchi), np.isfinite(chi))
+    assert np.array_equal(np.isfinite(O.log_prob(lay, theta, what=_cabi.LN_PRIOR)),
+                          np.isfinite(engine.log_prob(theta, what=_cabi.LN_PRIOR)))
+    m = np.isfinite(rchi)
+    assert m.sum() > n // 3
+    np.testing.assert_allclose(chi[m], rchi[m], rtol=1e-7)
+    assert not np.isnan(got).any()

@@ -1,2 +1,4 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 5 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['gp_likelihood'])"
+PYTHONPATH=. python tools/_dbg3.py 2>&1 | grep -E "walker|spot"
+cp lfit_python_b200/liblfit_b200.so /tmp/keep.so; cp lfit_python_b200/liblfit_b200_nowarm.so lfit_python_b200/liblfit_b200.so
+echo "--- no warm-up"
+PYTHONPATH=. python tools/_dbg3.py 2>&1 | grep -E "spot"
