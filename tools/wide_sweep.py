@@ -13,9 +13,23 @@ from oracle import oracle as O
 from lfit_python_b200 import _cabi, workloads
 
 
-def main(n=2000, n_ph=200, cfg=1, seed=5):
+def main(n=2000, n_ph=200, cfg=1, seed=5, shape=0):
     wl = workloads.config(cfg, n_ph=n_ph)
     eng = _cabi.Engine(0, **wl.grid)
+    srng = np.random.default_rng(100 + shape)
+    if shape:  # other light-curve shapes: irregular / unsorted / several cycles / uneven exposures
+        for e in range(wl.n_ecl):
+            sl = slice(wl.lc_off[e], wl.lc_off[e + 1])
+            if shape == 1:
+                x = np.sort(srng.uniform(-0.5, 0.5, n_ph))
+            elif shape == 2:
+                x = srng.permutation(np.linspace(-0.3, 0.4, n_ph))
+            elif shape == 3:
+                x = np.linspace(-1.2, 1.3, n_ph)
+            else:
+                x = np.sort(srng.uniform(0.7, 1.4, n_ph))
+            wl.lc_phase[sl] = x
+            wl.lc_width[sl] = srng.uniform(0.0, 0.004, n_ph) if shape in (1, 4) else np.full(n_ph, 0.5 * (x.max() - x.min()) / n_ph)
     wl.make_data(lambda p, x, w: eng.calc_flux(p, x, w))
     wl.apply(eng)
     rng = np.random.default_rng(seed)
@@ -30,10 +44,11 @@ def main(n=2000, n_ph=200, cfg=1, seed=5):
     lay = O.FlatLayout(wl.ndim, wl.npars, wl.gather, wl.consts, wl.prior_src, wl.prior_type, wl.prior_p1, wl.prior_p2,
                        wl.prior_norm, wl.prior_isvar, wl.lc_off, wl.lc_phase, wl.lc_width, wl.lc_y, wl.lc_ye)
     t0 = time.time()
-    ref, rchi = O.log_prob(lay, theta, what=_cabi.LN_LIKE, return_chisq=True)
+    ocfg = O.config(**wl.grid)
+    ref, rchi = O.log_prob(lay, theta, what=_cabi.LN_LIKE, return_chisq=True, cfg=ocfg)
     t1 = time.time()
     got, chi = eng.log_prob(theta, what=_cabi.LN_LIKE, return_chisq=True)
-    pri_ref = O.log_prob(lay, theta, what=_cabi.LN_PRIOR)
+    pri_ref = O.log_prob(lay, theta, what=_cabi.LN_PRIOR, cfg=ocfg)
     pri = eng.log_prob(theta, what=_cabi.LN_PRIOR)
     fin_r, fin_g = np.isfinite(rchi[:, 0]), np.isfinite(chi[:, 0])
     print("walkers %d, oracle %.1f s; valid models: oracle %d, cuda %d; mask mismatches %d; prior mask mismatches %d" % (
