@@ -6,21 +6,25 @@
 //   SimpleEclipse.chisq / ln_like                       CVModel.py:157-191
 //   LCModel.ln_prior / SimpleEclipse.ln_prior           CVModel.py:440-491,193-324
 //   Node.ln_prior / Node.ln_prob, Prior.ln_prob         model.py:426-498,83-113
-//   trm.roche.xl1 / findphi / findi / bspot             CVModel.py:222,288,460,561
+//   trm.roche.xl1 / findphi / findi / bspot / wdphases  CVModel.py:222,288,460,559,562
+//   SimpleGPEclipse.ln_like (george GP)                 CVModel.py:603-696
 //
 // Pipeline of one log-probability call over n walkers x n_ecl eclipses ("jobs"):
 //   walker_kernel    thread per walker: L1, Phi_c, inclination from (q, dphi), Param priors,
 //                    scalar validity rules
-//   stream_kernel    thread per job: ballistic stream -> bright-spot impact point, azimuth
-//                    rule, strip constants, parameter validity
+//   jobcheck_kernel  thread per job: per-eclipse validity rules that need no stream
+//   stream_kernel    thread per job, side stream: ballistic stream -> bright-spot impact point,
+//                    azimuth rule, strip constants
 //   elements_kernel  thread per surface element (white dwarf and donor per walker, disc and
 //                    bright spot per job): ingress/egress phases from the Roche LOS solve /
 //                    donor surface tiles -> HBM (16-32 B per element)
-//   flux_kernel      CTA per job: every element's eclipse interval becomes two events on the
-//                    sorted exposure-sample axis (fixed-point shared-memory atomics), a block
-//                    scan turns events into eclipsed flux per sample, the donor's facing
-//                    intervals carry five trigonometric moments the same way; then component
-//                    mix, exposure quadrature and the chi-squared reduction
+//   prep_kernel      warp per job: component totals, fixed-point element weights, constants
+//   positions_kernel thread per element: the element's eclipse / facing interval as events on the
+//                    job's sorted exposure-sample axis (16 B record), donor moment parts
+//   flux_kernel      CTA per job, in segments of the axis: tile events -> shared-memory atomics ->
+//                    block scan; donor events -> counting sort -> block scan of five trigonometric
+//                    moments; then component mix, exposure quadrature and the chi-squared reduction
+//   gp_kernel        (lfb_set_gp) thread per job: Kalman-filter GP likelihood of the residuals
 //   finish_kernel    thread per walker: ln_prior - chi^2/2 with the -inf rules
 #pragma once
 #include <cuda_runtime.h>
@@ -391,7 +395,6 @@ struct FluxArgs {
     DevSamples smp;
     int what, flags, mode;  // mode 0: chi-squared, 1: flux curves
     int Ms;                 // capacity of a segment of the sample axis in samples
-    int max_nph;            // points of the longest light curve (stride of the per-point sums)
     int ni_total;           // event records per job: n_wd + n_disc + n_bs + 4 n_donor_q
     long long njobs;
     const double* theta;

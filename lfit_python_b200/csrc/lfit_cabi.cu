@@ -143,7 +143,7 @@ struct lfb_handle {
     long long launches = 0;
     int sm_count = 148;
     int max_smem = 0;
-    int Mc = 3072, Mc_flux = 2048;  // segment capacity of the flux kernel: chi-squared mode / flux-curve mode
+    int Mc = 1280, Mc_flux = 1024;  // segment capacity of the flux kernel in samples: chi-squared mode / flux-curve mode
     long long max_jobs_per_batch = 131072;
     int n_lanes = kLanes;  // LFB_LANES=1 serialises the batches (clean per-stage timings for profiling)
     // layout
@@ -451,7 +451,6 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         A.mode = mode;
         const int Ms = mode ? h->Mc_flux : h->Mc;
         A.Ms = Ms;
-        A.max_nph = ss.max_nph;
         A.ni_total = G.n_wd + G.n_disc + G.n_bs + 4 * G.n_donor_q;
         A.njobs = njobs;
         A.theta = d_theta;
