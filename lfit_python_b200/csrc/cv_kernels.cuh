@@ -1084,26 +1084,32 @@ __global__ void __launch_bounds__(kFluxThreads, CTAS) flux_kernel(const __grid_c
 }
 
 // ---------------------------------------------------------------- gp_kernel
-// SimpleGPEclipse.ln_like (CVModel.py:650-696): thread per (eclipse, walker); a block holds kGpThreads
-// walkers of one eclipse.  The filter is a serial recursion over the eclipse's points, so what
-// matters is the latency of one step: the block stages tiles of kGpTile points (coalesced rows of
-// the residual matrix, the shared times and variances) in shared memory and every thread steps its
-// filter from there.  Leaves -2 ln L where the chi-squared would be.
-constexpr int kGpThreads = 32;
+// SimpleGPEclipse.ln_like (CVModel.py:650-696).  The filter is a serial recursion over the eclipse's
+// points, so what matters for a thin batch is the latency of one job: two neighbouring lanes share a
+// (walker, eclipse) -- one filters the first half of the points forwards, the other the second half
+// backwards, and they meet in the middle (gp_merge) -- and the block (kGpWalkers walkers of one
+// eclipse) stages tiles of kGpTile points per direction in shared memory: coalesced rows of the
+// residual matrix, the shared times and variances.  Leaves -2 ln L where the chi-squared would be.
+constexpr int kGpWalkers = 32;
+constexpr int kGpThreads = 2 * kGpWalkers;
 constexpr int kGpTile = 32;
 
 __global__ void __launch_bounds__(kGpThreads) gp_kernel(const __grid_constant__ FluxArgs A)
 {
-    __shared__ double r_tile[kGpTile][kGpThreads];
-    __shared__ double x_tile[kGpTile], v_tile[kGpTile];
+    __shared__ double r_tile[2][kGpTile][kGpWalkers];
+    __shared__ double x_tile[2][kGpTile], v_tile[2][kGpTile];
     const int e = blockIdx.y, tid = threadIdx.x;
-    const long long w0 = (long long)blockIdx.x * kGpThreads, w = w0 + tid;
+    const int wl = tid >> 1, dir = tid & 1;  // dir 0: forwards over points [0, m); 1: backwards over [m, n)
+    const long long w0 = (long long)blockIdx.x * kGpWalkers, w = w0 + wl;
     const long long lc0 = A.smp.lc_off[e];
     const int n_ph = (int)(A.smp.lc_off[e + 1] - lc0);
+    const int m = n_ph < 4 ? n_ph : n_ph / 2;  // a handful of points: one filter does it all
+    const int n_mine = dir ? n_ph - m : m, n_max = max(m, n_ph - m);
     const long long job = w * A.L.n_ecl + e;
     const bool live = w < A.n_walkers && job_live(A, A.ws[w], A.js[job]);  // else the flux kernel left NaN / +inf
     GpPars G;
-    GpFilter F;
+    G.a_in = G.a_out = G.tau = 1.0;
+    G.n_gaps = 0;
     bool run = false;
     if (live) {
         const double* th = A.theta + w * A.L.ndim;
@@ -1114,28 +1120,58 @@ __global__ void __launch_bounds__(kGpThreads) gp_kernel(const __grid_constant__ 
         const double2 span = A.smp.gp_span[e];
         const double dist = A.gp_dist[e];
         run = dist > 0.0;
+        if (run) gp_changepoints(span.x, span.y, dist, phi0, G);
+    }
+    GpFilter F;
+    F.init(G, dir ? -1 : 1);
+    const int ncol = (int)min((long long)kGpWalkers, A.n_walkers - w0);
+    for (int k0 = 0; k0 < n_max; k0 += kGpTile) {
+        __syncthreads();
+        for (int i = tid; i < 2 * kGpTile * kGpWalkers; i += kGpThreads) {
+            const int d = i / (kGpTile * kGpWalkers), rem = i - d * (kGpTile * kGpWalkers);
+            const int row = rem / kGpWalkers, col = rem - row * kGpWalkers;
+            const int k = k0 + row;
+            if (col < ncol && k < (d ? n_ph - m : m))
+                r_tile[d][row][col] = A.gp_resid[(lc0 + (d ? n_ph - 1 - k : k)) * A.n_walkers + w0 + col];
+        }
+        {
+            const int d = tid / kGpTile, row = tid - d * kGpTile, k = k0 + row;  // kGpThreads == 2 * kGpTile
+            if (k < (d ? n_ph - m : m)) {
+                const long long p = lc0 + (d ? n_ph - 1 - k : k);
+                x_tile[d][row] = __ldg(A.smp.gp_x + p);
+                v_tile[d][row] = __ldg(A.smp.gp_var + p);
+            }
+        }
+        __syncthreads();
         if (run) {
-            gp_changepoints(span.x, span.y, dist, phi0, G);
-            F.init(G);
+            const int rows = min(kGpTile, n_mine - k0);
+            for (int r = 0; r < rows; ++r) F.step(G, x_tile[dir][r], v_tile[dir][r], r_tile[dir][r][wl]);
         }
     }
-    const int ncol = (int)min((long long)kGpThreads, A.n_walkers - w0);
-    for (int k0 = 0; k0 < n_ph; k0 += kGpTile) {
-        const int rows = min(kGpTile, n_ph - k0);
-        __syncthreads();
-        for (int i = tid; i < rows * kGpThreads; i += kGpThreads) {
-            const int row = i / kGpThreads, col = i - row * kGpThreads;
-            if (col < ncol) r_tile[row][col] = A.gp_resid[(lc0 + k0 + row) * A.n_walkers + w0 + col];
+    // the backward lane hands its half to the forward lane
+    const double ll_mine = F.result();
+    GpFilter B = F;
+    const unsigned full = 0xffffffffu;
+    B.m0 = __shfl_xor_sync(full, F.m0, 1); B.m1 = __shfl_xor_sync(full, F.m1, 1);
+    B.m2 = __shfl_xor_sync(full, F.m2, 1); B.m3 = __shfl_xor_sync(full, F.m3, 1);
+    B.p00 = __shfl_xor_sync(full, F.p00, 1); B.p01 = __shfl_xor_sync(full, F.p01, 1); B.p11 = __shfl_xor_sync(full, F.p11, 1);
+    B.p02 = __shfl_xor_sync(full, F.p02, 1); B.p03 = __shfl_xor_sync(full, F.p03, 1);
+    B.p12 = __shfl_xor_sync(full, F.p12, 1); B.p13 = __shfl_xor_sync(full, F.p13, 1);
+    B.p22 = __shfl_xor_sync(full, F.p22, 1); B.p23 = __shfl_xor_sync(full, F.p23, 1); B.p33 = __shfl_xor_sync(full, F.p33, 1);
+    B.last_gap = __shfl_xor_sync(full, F.last_gap, 1);
+    B.bad = __shfl_xor_sync(full, (int)F.bad, 1) != 0;
+    const double ll_other = __shfl_xor_sync(full, ll_mine, 1);
+    if (live && dir == 0) {
+        double ll = INFINITY;  // -> chi-squared + inf when there are no change points
+        if (run) {
+            ll = ll_mine;
+            if (m < n_ph) {
+                F.advance(G, __ldg(A.smp.gp_x + lc0 + m));
+                ll += ll_other + gp_merge(F, B, G, F.last_gap >= 0 && F.last_gap == B.last_gap);
+            }
         }
-        if (tid < rows) {
-            x_tile[tid] = __ldg(A.smp.gp_x + lc0 + k0 + tid);
-            v_tile[tid] = __ldg(A.smp.gp_var + lc0 + k0 + tid);
-        }
-        __syncthreads();
-        if (run)
-            for (int r = 0; r < rows; ++r) F.step(G, x_tile[r], v_tile[r], r_tile[r][tid]);
+        A.chisq_job[job] = run ? -2.0 * ll : INFINITY;
     }
-    if (live) A.chisq_job[job] = run ? -2.0 * F.result() : INFINITY;
 }
 
 // lfb_gp_loglike: the same likelihood for caller-supplied residuals, thread per set

@@ -512,7 +512,7 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         h->launches += 3;
         if (gp) {
             KREC(LFB_K_GP);
-            gp_kernel<<<dim3((unsigned)((n + kGpThreads - 1) / kGpThreads), (unsigned)L.n_ecl), kGpThreads, 0, st>>>(A);
+            gp_kernel<<<dim3((unsigned)((n + kGpWalkers - 1) / kGpWalkers), (unsigned)L.n_ecl), kGpThreads, 0, st>>>(A);
             h->launches++;
         }
     } else {

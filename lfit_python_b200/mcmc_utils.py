@@ -236,10 +236,10 @@ class DeviceEnsembleSampler:
                     lnpdiff = (self.ndim - 1.0) * torch.log(zz) + new_lnp - lnp[first]
                     accept = lnpdiff > torch.log(torch.rand(half, dtype=torch.float64, device=self.device,
                                                             generator=self.gen))
-                    idx = first[accept]
-                    pos[idx] = prop[accept]
-                    lnp[idx] = new_lnp[accept]
-                    self.naccepted[idx] += 1
+                    # masked updates with fixed shapes: nothing here makes the host wait for the GPU
+                    pos[first] = torch.where(accept[:, None], prop, s)
+                    lnp[first] = torch.where(accept, new_lnp, lnp[first])
+                    self.naccepted[first] += accept.to(torch.int64)
                 self.iterations += 1
             self.pos, self.lnp = pos, lnp
         self.stream.synchronize()

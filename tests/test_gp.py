@@ -38,17 +38,19 @@ def hostgp(tmp_path_factory):
                    check=True)
     lib = C.CDLL(out)
     dp = C.POINTER(C.c_double)
-    lib.host_gp_loglike.restype = C.c_double
-    lib.host_gp_loglike.argtypes = [C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int, dp]
+    for fn in (lib.host_gp_loglike, lib.host_gp_loglike_two_sided):
+        fn.restype = C.c_double
+        fn.argtypes = [C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int, dp]
     lib.host_gp_changepoints.argtypes = [C.c_double] * 4 + [dp]
 
-    def loglike(x, ye, r, ampin, ampout, tau, gaps):
+    def loglike(x, ye, r, ampin, ampout, tau, gaps, two_sided=False):
         x, ye, r = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, ye, r))
         g = np.ascontiguousarray(np.asarray(gaps, dtype=np.float64).ravel())
         if g.size == 0:
             g = np.zeros(2)
-        return lib.host_gp_loglike(len(x), x.ctypes.data_as(dp), ye.ctypes.data_as(dp), r.ctypes.data_as(dp), ampin, ampout,
-                                   tau, len(gaps), g.ctypes.data_as(dp))
+        fn = lib.host_gp_loglike_two_sided if two_sided else lib.host_gp_loglike
+        return fn(len(x), x.ctypes.data_as(dp), ye.ctypes.data_as(dp), r.ctypes.data_as(dp), ampin, ampout, tau, len(gaps),
+                  g.ctypes.data_as(dp))
 
     def changepoints(xmin, xmax, dist, phi0):
         g = np.zeros(16)
@@ -60,7 +62,8 @@ def hostgp(tmp_path_factory):
 
 def random_case(rng, n=None):
     n = int(rng.integers(2, 300)) if n is None else n
-    x = np.sort(rng.uniform(-0.5, 0.5, n))
+    lo, hi = ((-0.5, 0.5), (-0.2, 0.3), (0.05, 0.45), (-1.2, 1.3))[int(rng.integers(4))]
+    x = np.sort(rng.uniform(lo, hi, n))
     ye = rng.uniform(0.002, 0.006, n)
     hyper = np.exp([rng.uniform(-12, -7), rng.uniform(-12, -7), rng.uniform(-8, -3)])
     gaps = O.gp_changepoints(x, rng.uniform(0.02, 0.08), rng.normal(0, 0.002))
@@ -116,6 +119,8 @@ def test_kalman_filter_equals_dense_cholesky(hostgp):
         a = O.gp_log_like(x, ye, r, *hyper, gaps)
         b = loglike(x, ye, r, *hyper, gaps)
         assert np.isfinite(a) and b == pytest.approx(a, rel=1e-10, abs=1e-9)
+        # two filters meeting in the middle (what the kernel runs on two lanes): in a gap or in eclipse
+        assert loglike(x, ye, r, *hyper, gaps, two_sided=True) == pytest.approx(a, rel=1e-10, abs=1e-9)
     x, ye, r, hyper, gaps = random_case(rng, n=1)
     assert loglike(x, ye, r, *hyper, gaps) == pytest.approx(O.gp_log_like(x, ye, r, *hyper, gaps), rel=1e-13)
     r[0] = np.inf
