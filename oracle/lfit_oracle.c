@@ -123,7 +123,8 @@ static void tileset_free(tileset *t)
 }
 
 /* Orbital phase is periodic and the solvers may return an interval that runs past +-0.5 (elements
- * on the far side of the donor, eclipsed around phase 0.5): test the neighbouring cycles too. */
+ * on the far side of the donor, eclipsed around phase 0.5): those -- has == 2, set by
+ * tileset_finish -- are tested against the neighbouring cycles too. */
 static inline double tileset_visible(const tileset *t, double ph)
 {
     double s = 0.0;
@@ -131,11 +132,18 @@ static inline double tileset_visible(const tileset *t, double ph)
         int ecl = 0;
         if (t->has[k]) {
             const double a = t->in[k], b = t->out[k];
-            ecl = (ph > a && ph < b) || (ph + 1.0 > a && ph + 1.0 < b) || (ph - 1.0 > a && ph - 1.0 < b);
+            ecl = ph > a && ph < b;
+            if (t->has[k] == 2 && !ecl) ecl = (ph + 1.0 > a && ph + 1.0 < b) || (ph - 1.0 > a && ph - 1.0 < b);
         }
         if (!ecl) s += t->w[k];
     }
     return s;
+}
+
+static void tileset_finish(tileset *t)
+{
+    for (int k = 0; k < t->n; ++k)
+        if (t->has[k]) t->has[k] = (t->in[k] < -0.5 || t->out[k] > 0.5) ? 2 : 1;
 }
 
 /* white dwarf: limb-darkened disc on the sky, 4*n^2 equal-area tiles */
@@ -355,6 +363,9 @@ int lfo_calc_flux(const lfo_config *cfg, const double *pars_in, int npars, int f
         beam_norm = fis + (1.0 - fis) * (cmax > 0.0 ? cmax : 0.0);
     }
     if (do_don && build_donor(cfg, &R, si, ci, &don)) { status = 9; goto fail; }
+    if (do_wd) tileset_finish(&wd);
+    if (do_disc) tileset_finish(&disc);
+    if (do_bs) tileset_finish(&bs);
 
     int K = cfg->n_quad;
     double off[16], wq[16];
