@@ -43,7 +43,10 @@ UNIT = "lightcurve evals/s"
 #   executed:    what the committed kernels issue today (the first Newton steps run in FP32).
 FLOPS_PER_LIGHTCURVE = {
     "r1": {"elements": 2.458e6, "all": 2.962e6, "source": "profiles/r01_launches_fp64solver.csv",
-           "executed": {"elements": 1.557e6, "all": 1.968e6, "source": "profiles/r01_launches.csv"}},
+           "executed": {"elements": 1.557e6, "all": 1.968e6, "source": "profiles/r01_launches.csv"},
+           # dram__bytes_read.sum + dram__bytes_write.sum of the four elements_kernel launches of one batch of
+           # 2048 light curves (ncu --set full, profiles/r01_elements_kernel.txt), per light curve
+           "dram_bytes_per_lightcurve": (1.19 + 1.88 + 1.04 + 0.78 + 0.19 + 0.0 + 1.18 + 0.94) * 1e6 / 2048},
 }
 
 
@@ -339,6 +342,7 @@ def run_gpu(args, rank, local_rank, world):
         if fl and wl.name.startswith("C2") and not args.n_ph and not wl.grid:
             per_rank = n * wl.n_ecl
             roof["flops_per_lightcurve"] = fl
+            roof["traffic"] = fl["dram_bytes_per_lightcurve"] * per_rank  # bytes per step of the elements stage (ncu)
             roof["achieved"] = fl["elements"] * per_rank / (el_ms * 1e-3) * 1e-12
             roof["frac"] = roof["achieved"] / fp64_peak
             roof["whole_pass"] = {"achieved": fl["all"] * per_rank / (k_ms * 1e-3) * 1e-12,

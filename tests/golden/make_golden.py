@@ -71,7 +71,25 @@ def main():
             ie.append([v, 84.0, *p0, *(r if r else (np.nan, np.nan))])
     np.savez_compressed(os.path.join(HERE, "roche.npz"), q=q, xl1=xl1, maxphi=maxphi, incl=inc, bspot=spot,
                         ingress_egress=np.asarray(ie))
-    print("wrote calc_flux.npz, log_prob.npz, roche.npz")
+    # 4. Gaussian-process likelihood (dense Cholesky statement of the reference's george kernel) and the
+    #    white-dwarf contact phases behind its change points
+    rng = np.random.default_rng(2024)
+    cases = []
+    for n, span in ((40, (-0.2, 0.3)), (150, (-0.5, 0.5)), (90, (0.05, 0.45)), (200, (-1.2, 1.3)), (1, (0.0, 0.0))):
+        x = np.sort(rng.uniform(span[0], span[1], n)) if n > 1 else np.array([0.01])
+        ye = rng.uniform(0.002, 0.006, n)
+        hyper = np.exp([rng.uniform(-12, -7), rng.uniform(-12, -7), rng.uniform(-8, -3)])
+        gaps = np.asarray(O.gp_changepoints(x, rng.uniform(0.02, 0.08), rng.normal(0, 0.002)), dtype=np.float64).reshape(-1, 2)
+        r = rng.normal(0.0, 0.006, n)
+        cases.append(dict(x=x, ye=ye, resid=r, hyper=hyper, gaps=gaps, lnl=O.gp_log_like(x, ye, r, *hyper, gaps.tolist())))
+    gp = {}
+    for i, c in enumerate(cases):
+        for k, v in c.items():
+            gp["%s_%d" % (k, i)] = v
+    wq = np.array([[0.1037, 0.0392, 0.0187], [0.3, 0.06, 0.012], [0.05, 0.03, 0.02], [0.7, 0.09, 0.01]])
+    wd = np.array([[O.findi(q_, d_), *O.wdphases(q_, O.findi(q_, d_), r_, 10), O.gp_dist_cp(q_, d_, r_, 10)] for q_, d_, r_ in wq])
+    np.savez_compressed(os.path.join(HERE, "gp.npz"), n_cases=len(cases), wd_in=wq, wd_out=wd, **gp)
+    print("wrote calc_flux.npz, log_prob.npz, roche.npz, gp.npz")
 
 
 if __name__ == "__main__":

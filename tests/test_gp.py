@@ -242,3 +242,35 @@ def test_driver_runs_end_to_end(tmp_path, monkeypatch, capsys, use_gp):
     chain = mcmc_utils.readchain(str(tmp_path / "chain_prod.txt"))
     assert chain.shape == (96, 4, ndim + 1)
     assert np.allclose(chain[:, -1, :ndim], sampler.chain[:, -1, :], rtol=1e-5, atol=1e-6)   # "%f"-style file precision
+
+
+def _gp_golden():
+    g = np.load(os.path.join(HERE, "golden", "gp.npz"))
+    return g, [dict((k, g["%s_%d" % (k, i)]) for k in ("x", "ye", "resid", "hyper", "gaps", "lnl")) for i in range(int(g["n_cases"]))]
+
+
+def test_gp_golden_vectors(hostgp):
+    """The committed numbers (tests/golden/make_golden.py): oracle today == oracle then, host build of the
+    device filter == both, one- and two-sided."""
+    loglike, _ = hostgp
+    g, cases = _gp_golden()
+    for c in cases:
+        want = float(c["lnl"])
+        assert O.gp_log_like(c["x"], c["ye"], c["resid"], *c["hyper"], c["gaps"].tolist()) == pytest.approx(want, rel=1e-12)
+        for two in (False, True):
+            assert loglike(c["x"], c["ye"], c["resid"], *c["hyper"], c["gaps"].tolist(), two_sided=two) == pytest.approx(want, rel=1e-10)
+    for (q, dphi, rwd), (inc, p3, p4, dist) in zip(g["wd_in"], g["wd_out"]):
+        assert O.findi(q, dphi) == pytest.approx(inc, rel=1e-12)
+        assert np.allclose(O.wdphases(q, inc, rwd, 10), (p3, p4), rtol=0, atol=1e-12)
+        assert O.gp_dist_cp(q, dphi, rwd, 10) == pytest.approx(dist, rel=1e-11)
+
+
+@pytest.mark.gpu
+def test_gpu_gp_golden_vectors(engine):
+    g, cases = _gp_golden()
+    for c in cases:
+        got = engine.gp_loglike(c["x"], c["ye"], c["resid"], c["hyper"], c["gaps"])
+        assert got[0] == pytest.approx(float(c["lnl"]), rel=1e-10)
+    for (q, dphi, rwd), (inc, p3, p4, dist) in zip(g["wd_in"], g["wd_out"]):
+        out, ok = engine.wdphases(q, inc, rwd, 10)
+        assert ok.all() and np.allclose(out[0], (p3, p4), rtol=0, atol=1e-10)
