@@ -605,16 +605,18 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
         cudaMemcpy(h->donor_off.p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
         return bail("donor ring table", cudaGetLastError());
     G.donor_ring_off = h->donor_off.as<int>();
-    // disc elements in order of their position along the line of centres, (m + 1/2) cos(az): elements
-    // next to each other in this order are eclipsed in the same way (deeply / barely / never), which
-    // keeps the 32 threads of a warp on the same branch of the solver
+    // disc elements in order of their distance from the donor (for a disc of typical size, 0.35 a):
+    // elements next to each other in this order are eclipsed in the same way (deeply / barely /
+    // never), which keeps the 32 threads of a warp on the same branch of the solver
     {
         const int hth = c.n_disc_th / 2;
         std::vector<int> order(G.n_disc_half);
         std::iota(order.begin(), order.end(), 0);
+        const double rtyp = 0.35;
         auto key = [&](int tile) {
             int m = tile / hth, j = tile % hth;
-            return (m + 0.5) * cos((j + 0.5) * kTwoPi / c.n_disc_th);
+            const double rho = rtyp * (m + 0.5) / c.n_disc_r, ca = cos((j + 0.5) * kTwoPi / c.n_disc_th);
+            return 2.0 * rho * ca - rho * rho;  // 1 - (distance to the donor)^2
         };
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) > key(b); });
         if (h->disc_order.reserve(order.size() * sizeof(int)) != cudaSuccess ||
