@@ -94,7 +94,9 @@ struct WalkerScal {
     Roche R;
     double si, ci;
     double lnprior;
+    Roots wd;    // grazing lines of sight of the white-dwarf centre: Newton starts for its tiles
     int status;  // 0: a model exists; else the parameters admit none
+    int wd_ok;   // wd is set
 };
 
 struct JobScal {
@@ -118,6 +120,7 @@ __global__ void walker_kernel(DevLayout L, int what, int flags, long long n, con
     const double* th = theta + w * L.ndim;
     WalkerScal W;
     W.status = 0;
+    W.wd_ok = 0;
     W.lnprior = 0.0;
     W.si = 1.0;
     W.ci = 0.0;
@@ -155,6 +158,26 @@ __global__ void walker_kernel(DevLayout L, int what, int flags, long long n, con
         W.lnprior = lnp;
     }
     ws[w] = W;
+}
+
+// ---------------------------------------------------------------- wdcentre_kernel
+// Thread per walker, beside the disc solves: the grazing lines of sight of the white-dwarf centre,
+// which the white-dwarf tiles (all within a few hundredths of it) take as their Newton starts.
+__global__ void wdcentre_kernel(int what, long long n, WalkerScal* __restrict__ ws)
+{
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    WalkerScal& W = ws[w];
+    if (W.status != 0 || (what != LFB_LN_LIKE && !(W.lnprior > -INFINITY))) return;
+    const Roche R = W.R;
+    const Point T = {0.0, 0.0, 0.0, 0.0, 0.0};
+    Roots r;
+    r.lam[0] = NAN;
+    double pin, pout;
+    if (ingress_egress(R, W.si, W.ci, T, &pin, &pout, nullptr, &r) && r.lam[0] == r.lam[0]) {
+        W.wd = r;
+        W.wd_ok = 1;
+    }
 }
 
 // ---------------------------------------------------------------- jobcheck_kernel / stream_kernel
@@ -346,7 +369,7 @@ __global__ void __launch_bounds__(kElemThreads, kElemBlocks) elements_kernel(con
         }
     }
     double pin, pout;
-    if (!ingress_egress(R, si, ci, T, &pin, &pout)) { pin = kBig; pout = -kBig; }
+    if (!ingress_egress(R, si, ci, T, &pin, &pout, (COMP == 0 && W.wd_ok) ? &W.wd : nullptr)) { pin = kBig; pout = -kBig; }
     if (COMP == 0) A.wd_io[unit * G.n_wd_half + t] = make_double2(pin, pout);
     else if (COMP == 1) A.disc_io[unit * G.n_disc_half + tile] = make_double2(pin, pout);
     else {

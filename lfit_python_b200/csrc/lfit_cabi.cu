@@ -83,8 +83,9 @@ enum { ST_WALKER = 0, ST_STREAM, ST_ELEMENTS, ST_FLUX, ST_FINISH, ST_COUNT };
 // Two lanes work on alternate batches so that one batch's FP64-bound element solves overlap
 // the other's shared-memory-bound flux stage.
 struct Lane {
-    cudaStream_t st = nullptr, side = nullptr;  // side: the serial stream ODE beside the element solves
-    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, done_ev = nullptr;
+    cudaStream_t st = nullptr, side = nullptr, side2 = nullptr;  // side: the serial stream ODE beside the element
+                                                                 // solves; side2: the white-dwarf centre's LOS
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, done_ev = nullptr, wd_ev = nullptr;
     cudaEvent_t ev[ST_COUNT + 1] = {};
     cudaEvent_t kev[LFB_K_COUNT + 1] = {}, sev[2] = {};  // per-kernel trace (lfb_set_trace), side-stream pair
     bool kev_set[LFB_K_COUNT + 1] = {};
@@ -94,9 +95,11 @@ struct Lane {
         cudaError_t e;
         if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return e;
         if ((e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&wd_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
         for (int i = 0; i <= ST_COUNT; ++i)
             if ((e = cudaEventCreate(&ev[i])) != cudaSuccess) return e;
         for (int i = 0; i <= LFB_K_COUNT; ++i)
@@ -118,7 +121,9 @@ struct Lane {
         if (fork_ev) cudaEventDestroy(fork_ev);
         if (join_ev) cudaEventDestroy(join_ev);
         if (done_ev) cudaEventDestroy(done_ev);
+        if (wd_ev) cudaEventDestroy(wd_ev);
         if (side) cudaStreamDestroy(side);
+        if (side2) cudaStreamDestroy(side2);
         if (st) cudaStreamDestroy(st);
     }
 };
@@ -393,6 +398,12 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
     // fork: the ballistic-stream ODE (one serial integration per job) runs beside the element solves
     CK(cudaEventRecord(ln.fork_ev, st));
     CK(cudaStreamWaitEvent(ln.side, ln.fork_ev, 0));
+    CK(cudaStreamWaitEvent(ln.side2, ln.fork_ev, 0));
+    if (what != LFB_LN_PRIOR && !(flags & LFB_FLAG_SKIP_WD)) {
+        wdcentre_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ln.side2>>>(what, n, ln.ws.as<WalkerScal>());
+        h->launches++;
+    }
+    CK(cudaEventRecord(ln.wd_ev, ln.side2));
     if (trace) CK(cudaEventRecord(ln.sev[0], ln.side));
     stream_kernel<<<(unsigned)((njobs + 63) / 64), 64, 0, ln.side>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
                                                                       ln.js.as<JobScal>());
@@ -426,6 +437,7 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
             h->launches++;
         }
         if (!(flags & LFB_FLAG_SKIP_WD)) {
+            CK(cudaStreamWaitEvent(st, ln.wd_ev, 0));  // the white-dwarf centre's lines of sight (side stream)
             KREC(LFB_K_ELEM_WD);
             elements_kernel<0><<<blocks(n, G.n_wd_half), kElemThreads, 0, st>>>(E);
             h->launches++;

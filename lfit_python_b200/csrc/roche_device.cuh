@@ -427,6 +427,72 @@ LFB_HD bool warm_root(float mu, float omu, float phic, float si, float ci, const
 constexpr int kMinIters = 12;   // deepest-LOS Newton (shallow elements only), early exit
 constexpr int kRootIters = 16;  // grazing-LOS Newton, early exit
 
+// The two grazing lines of sight of an element: orbital angle as (cos, sin) and distance along the LOS
+struct Roots {
+    double c[2], s[2], lam[2];
+};
+
+// 2-D Newton on (th, lam) for the grazing LOS (Phi = Phi_c, dPhi/dlam = 0) on either side of the
+// deepest LOS (cm, sm), from the given starts (FP32 warm-up, then FP64).  True if both converged to
+// grazing LOS of the right kind; res = their orbital angles (radians), ingress then egress.
+LFB_HD bool graze_roots(const Roche& R, double si, double ci, const Point& T, double cpsi, double spsi, double cm,
+                        double sm, const Roots& start, double res[2], Roots* roots)
+{
+    Derivs D;
+    Roots found;
+    const float muf = (float)R.mu, omuf = (float)R.omu, phicf = (float)R.phic, sif = (float)si, cif = (float)ci;
+    const PointF Tf = {(float)T.x, (float)T.y, (float)T.z, (float)T.xi, (float)T.eta};
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        const double sg = side ? 1.0 : -1.0;
+        double c = start.c[side], s = start.s[side], lam = start.lam[side];
+#ifndef LFB_NO_WARMUP
+        {
+            float cf = (float)c, sf = (float)s, lf = (float)lam;
+            if (warm_root(muf, omuf, phicf, sif, cif, Tf, (float)cm, (float)sm, (float)sg, cf, sf, lf)) {
+                const double cw = (double)cf, sw = (double)sf;
+                const double nrm = fast_rsqrt(cw * cw + sw * sw);
+                c = cw * nrm;
+                s = sw * nrm;
+                lam = (double)lf;
+            }
+        }
+#endif
+        bool conv = false;
+        for (int it = 0; it < kRootIters; ++it) {
+            ray_eval(R, si, ci, T, c, s, lam, D);
+            double F1 = D.S - R.phic, F2 = D.Sl;
+            double idet = fast_rcp(D.St * D.Sll - D.Sl * D.Stl);
+            double dth = clampd((-F1 * D.Sll + F2 * D.Sl) * idet, 0.2);
+            double dl = clampd((-D.St * F2 + D.Stl * F1) * idet, 0.2);
+            // stay on this side of the deepest LOS: sin(th + dth - thm) must keep the sign of sg
+            double cross = s * cm - c * sm;  // sin(th - thm)
+            if (!(sg * (cross + dth * (c * cm + s * sm)) > 0.0)) {
+                dth = -0.5 * asin(cross > 1.0 ? 1.0 : (cross < -1.0 ? -1.0 : cross));
+                dl *= 0.5;
+            }
+            rotate_cs(c, s, dth);
+            lam += dl;
+            // quadratic convergence: a step below 1e-9 leaves an error far below 1e-15
+            if (fabs(dth) < 1e-9 && fabs(dl) < 1e-7) { conv = true; break; }
+        }
+        // accept only a converged grazing LOS of the right kind (D is one tiny step old)
+        double xx = T.x - T.xi * s - T.eta * ci * c + lam * si * c - 1.0;
+        double yy = T.y - T.xi * c + T.eta * ci * s - lam * si * s;
+        double zz = T.z + T.eta * si + lam * ci;
+        bool ok = conv && D.Sll > 0.0 && lam > 0.0 && xx * xx + yy * yy + zz * zz <= R.rs * R.rs &&
+                  (side ? D.St > 0.0 : D.St < 0.0) && c * cpsi + s * spsi > 0.0;
+        if (!ok) return false;
+        res[side] = atan2(s, c);
+        found.c[side] = c;
+        found.s[side] = s;
+        found.lam[side] = lam;
+    }
+    if (!(res[0] < res[1])) return false;
+    if (roots) *roots = found;
+    return true;
+}
+
 // Ingress/egress phases (cycles) of one element; 0 if it is never eclipsed.
 // Fast path: 2-D Newton on (th, lam) for the two LOS that graze the critical surface
 // (Phi = Phi_c, dPhi/dlam = 0), started from the tangents to a sphere inscribed in the lobe
@@ -434,7 +500,11 @@ constexpr int kRootIters = 16;  // grazing-LOS Newton, early exit
 // orbital angle is carried as (cos, sin) and advanced by small rotations, so the loop has no
 // trigonometric calls; one atan2 per root at the end.  Every root is verified; anything
 // unverified goes to ingress_egress_robust.
-LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, double* ph_in, double* ph_out)
+// hint: grazing LOS of the element at the origin (the white-dwarf centre, for white-dwarf tiles): tried
+// first as the Newton starts when its eclipse is much wider than this element's offset; roots: where
+// the element's own end up (fast path only).
+LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, double* ph_in, double* ph_out,
+                          const Roots* hint = nullptr, Roots* roots = nullptr)
 {
     // conjunction: the LOS passes closest to the donor's centre
     const double X = 1.0 - T.x + T.eta * ci, Y = T.y - T.xi;
@@ -448,6 +518,19 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
     double lam = wx * ex + wy * ey + wz * ci;
     double w2 = wx * wx + wy * wy + wz * wz;
     if (w2 - lam * lam >= R.rs * R.rs || lam <= 0.0) return 0;
+    double res[2];
+    if (hint) {
+        // The hint's LOS graze the lobe where this element's do, give or take the element's offset; and
+        // the deepest LOS, which divides ingress from egress, is within that offset of conjunction.  When
+        // the hinted eclipse is several offsets wide none of this can be confused: solve from the hint.
+        const double off = sqrt(T.xi * T.xi + T.eta * T.eta + T.x * T.x + T.y * T.y + T.z * T.z);
+        if (-hint->s[0] > 4.0 * off && hint->s[1] > 4.0 * off && hint->c[0] > 0.0 && hint->c[1] > 0.0 &&
+            graze_roots(R, si, ci, T, cpsi, spsi, cpsi, spsi, *hint, res, roots)) {
+            *ph_in = res[0] * (1.0 / kTwoPi);
+            *ph_out = res[1] * (1.0 / kTwoPi);
+            return 1;
+        }
+    }
     double rxy = si * sqrt(wx * wx + wy * wy);
     double tang = sqrt(w2 - R.rin * R.rin);
     double cosd = (tang - wz * ci) / rxy;
@@ -501,55 +584,9 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         lam0 = lam - slope * del;
         lam1 = lam + slope * del;
     }
-    double res[2];
-    const float muf = (float)R.mu, omuf = (float)R.omu, phicf = (float)R.phic, sif = (float)si, cif = (float)ci;
-    const PointF Tf = {(float)T.x, (float)T.y, (float)T.z, (float)T.xi, (float)T.eta};
-#pragma unroll 1
-    for (int side = 0; side < 2; ++side) {
-        const double sg = side ? 1.0 : -1.0;
-        c = side ? c1 : c0;
-        s = side ? s1 : s0;
-        lam = side ? lam1 : lam0;
-#ifndef LFB_NO_WARMUP
-        {
-            float cf = (float)c, sf = (float)s, lf = (float)lam;
-            if (warm_root(muf, omuf, phicf, sif, cif, Tf, (float)cm, (float)sm, (float)sg, cf, sf, lf)) {
-                const double cw = (double)cf, sw = (double)sf;
-                const double nrm = fast_rsqrt(cw * cw + sw * sw);
-                c = cw * nrm;
-                s = sw * nrm;
-                lam = (double)lf;
-            }
-        }
-#endif
-        bool conv = false;
-        for (int it = 0; it < kRootIters; ++it) {
-            ray_eval(R, si, ci, T, c, s, lam, D);
-            double F1 = D.S - R.phic, F2 = D.Sl;
-            double idet = fast_rcp(D.St * D.Sll - D.Sl * D.Stl);
-            double dth = clampd((-F1 * D.Sll + F2 * D.Sl) * idet, 0.2);
-            double dl = clampd((-D.St * F2 + D.Stl * F1) * idet, 0.2);
-            // stay on this side of the deepest LOS: sin(th + dth - thm) must keep the sign of sg
-            double cross = s * cm - c * sm;  // sin(th - thm)
-            if (!(sg * (cross + dth * (c * cm + s * sm)) > 0.0)) {
-                dth = -0.5 * asin(cross > 1.0 ? 1.0 : (cross < -1.0 ? -1.0 : cross));
-                dl *= 0.5;
-            }
-            rotate_cs(c, s, dth);
-            lam += dl;
-            // quadratic convergence: a step below 1e-9 leaves an error far below 1e-15
-            if (fabs(dth) < 1e-9 && fabs(dl) < 1e-7) { conv = true; break; }
-        }
-        // accept only a converged grazing LOS of the right kind (D is one tiny step old)
-        double xx = T.x - T.xi * s - T.eta * ci * c + lam * si * c - 1.0;
-        double yy = T.y - T.xi * c + T.eta * ci * s - lam * si * s;
-        double zz = T.z + T.eta * si + lam * ci;
-        bool ok = conv && D.Sll > 0.0 && lam > 0.0 && xx * xx + yy * yy + zz * zz <= R.rs * R.rs &&
-                  (side ? D.St > 0.0 : D.St < 0.0) && c * cpsi + s * spsi > 0.0;
-        if (!ok) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
-        res[side] = atan2(s, c);
-    }
-    if (!(res[0] < res[1])) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
+    const Roots start = {{c0, c1}, {s0, s1}, {lam0, lam1}};
+    if (!graze_roots(R, si, ci, T, cpsi, spsi, cm, sm, start, res, roots))
+        return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
     *ph_in = res[0] * (1.0 / kTwoPi);
     *ph_out = res[1] * (1.0 / kTwoPi);
     return 1;
