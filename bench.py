@@ -40,13 +40,14 @@ UNIT = "lightcurve evals/s"
 # "all" = every kernel of a log-probability pass.
 #   algorithmic: the solver with every Newton step in FP64 -- the fixed per-unit figure that
 #                roofline.achieved is quoted on (it does not move when the kernels get cleverer);
-#   executed:    what the committed kernels issue today (the first Newton steps run in FP32).
+#   executed:    what the committed kernels issue today (the first Newton steps run in FP32, the
+#                white-dwarf tiles start from the centre's solution).
 FLOPS_PER_LIGHTCURVE = {
     "r1": {"elements": 2.458e6, "all": 2.962e6, "source": "profiles/r01_launches_fp64solver.csv",
-           "executed": {"elements": 1.557e6, "all": 1.968e6, "source": "profiles/r01_launches.csv"},
+           "executed": {"elements": 1.396e6, "all": 1.808e6, "source": "profiles/r01_launches.csv"},
            # dram__bytes_read.sum + dram__bytes_write.sum of the four elements_kernel launches of one batch of
            # 2048 light curves (ncu --set full, profiles/r01_elements_kernel.txt), per light curve
-           "dram_bytes_per_lightcurve": (1.19 + 1.88 + 1.04 + 0.78 + 0.19 + 0.0 + 1.18 + 0.94) * 1e6 / 2048},
+           "dram_bytes_per_lightcurve": 8.58e6 / 2048},
 }
 
 
