@@ -579,15 +579,30 @@ __device__ __forceinline__ int sample_search(const SampleAxis& X, double v, bool
     double gf = (v - X.s_first) * X.inv_binw;
     int b = gf <= 0.0 ? 0 : (gf >= (double)(M - 1) ? M - 1 : (int)gf);
     int p = __ldg(X.bins + b);
-    while (p < M) {
-        double s = __ldg(S + p);
-        if (!(strict ? (s <= v) : (s < v))) break;
-        ++p;
-    }
-    while (p > 0) {
-        double s = __ldg(S + p - 1);
-        if (strict ? (s <= v) : (s < v)) break;
+    // the answer is almost always within a few samples of the seed: fetch a window at once instead of
+    // walking load by load
+    const double inf = 1e300;
+    const double sm1 = p > 0 ? __ldg(S + p - 1) : -inf;
+    const double s0 = p < M ? __ldg(S + p) : inf, s1 = p + 1 < M ? __ldg(S + p + 1) : inf;
+    const double s2 = p + 2 < M ? __ldg(S + p + 2) : inf, s3 = p + 3 < M ? __ldg(S + p + 3) : inf;
+    const bool b0 = strict ? (s0 <= v) : (s0 < v), b1 = strict ? (s1 <= v) : (s1 < v);
+    const bool b2 = strict ? (s2 <= v) : (s2 < v), b3 = strict ? (s3 <= v) : (s3 < v);
+    const bool bm = strict ? (sm1 <= v) : (sm1 < v);
+    if (b0) {
+        p += b1 ? (b2 ? (b3 ? 4 : 3) : 2) : 1;
+        if (b1 && b2 && b3)
+            while (p < M) {
+                double s = __ldg(S + p);
+                if (!(strict ? (s <= v) : (s < v))) break;
+                ++p;
+            }
+    } else if (!bm && p > 0) {
         --p;
+        while (p > 0) {
+            double s = __ldg(S + p - 1);
+            if (strict ? (s <= v) : (s < v)) break;
+            --p;
+        }
     }
     return p;
 }
