@@ -910,9 +910,7 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
     if (!th_dev) {
         CK(h->theta.reserve(th_bytes));
         CK(h->h_in.reserve(th_bytes));
-        memcpy(h->h_in.p, theta, sizeof(double) * (size_t)n * h->ndim);
-        CK(cudaMemcpyAsync(h->theta.p, h->h_in.p, sizeof(double) * (size_t)n * h->ndim, cudaMemcpyHostToDevice, st));
-        d_theta = h->theta.as<double>();
+        d_theta = h->theta.as<double>();  // staged batch by batch below, so that a copy overlaps the batch before
     }
     double* d_out = out;
     if (!out_dev) {
@@ -951,6 +949,11 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
             used = (int)b + 1;
         }
         const long long nb = std::min(per, n - w0);
+        if (!th_dev) {
+            const size_t off = (size_t)w0 * h->ndim, cnt = sizeof(double) * (size_t)nb * h->ndim;
+            memcpy((double*)h->h_in.p + off, theta + off, cnt);
+            CK(cudaMemcpyAsync(h->theta.as<double>() + off, (double*)h->h_in.p + off, cnt, cudaMemcpyHostToDevice, ln.st));
+        }
         const bool last_on_lane0 = (b % h->n_lanes) == 0 && w0 + (long long)h->n_lanes * per >= n;
         int rc = run_batch(h, ln, L, h->lc, what, 0, 0, nb, d_theta + w0 * h->ndim, d_out + w0, d_chi + w0 * h->n_ecl,
                            nullptr, nullptr, last_on_lane0);
