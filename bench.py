@@ -334,7 +334,7 @@ def run_gpu(args, rank, local_rank, world):
         stages = {k: float(np.mean([d[k] for d in stage_ms])) for k in stage_ms[0]}
         serial = {k: float(np.mean([d[k] for d in serial_stage])) for k in serial_stage[0]}
         trace = {k: float(np.mean([d[k] for d in serial_trace])) for k in serial_trace[0]}
-        el_ms = serial["elements"]
+        el_ms = sum(v for k, v in trace.items() if k.startswith("elements_kernel"))  # the four stage-1 launches
         roof = {"bound": "fp64", "kernel": "elements_kernel<wd,disc,spot,donor> (stage 1: Roche ingress/egress solves)",
                 "kernel_ms": el_ms, "kernel_share_of_step": el_ms / serial["total"],
                 "stage_ms_serial": serial, "kernel_ms_serial": trace, "stage_ms_overlapped": stages, "pipeline_ms": k_ms,

@@ -25,7 +25,8 @@ EXPORTS = (
     "lfb_set_trace", "lfb_last_trace_ms", "lfb_set_gp", "lfb_gp_loglike", "lfb_wdphases", "lfb_ingress_egress",
 )
 TRACE_KERNELS = ("walker_kernel", "jobcheck_kernel", "elements_kernel<1> disc", "elements_kernel<0> white dwarf",
-                 "elements_kernel<3> donor", "elements_kernel<2> strip", "prep_kernel", "positions_kernel",
+                 "elements_kernel<3> donor", "prep_kernel", "positions_kernel", "elements_kernel<2> strip",
+                 "prep_strip_kernel + positions_kernel<1>",
                  "flux_kernel", "gp_kernel", "finish_kernel", "stream_kernel (side stream)")
 
 

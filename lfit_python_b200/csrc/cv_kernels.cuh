@@ -473,7 +473,6 @@ __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FluxA
     const double ulimb = par(P_ULIMB, 0.0), dexp = par(P_DEXP, 0.0);
     long long* wq_wd = A.wq + job * (G.n_wd_rings + G.n_disc_r + G.n_bs);
     long long* wq_disc = wq_wd + G.n_wd_rings;
-    long long* wq_bs = wq_disc + G.n_disc_r;
     // white dwarf rings: equal-area tiles, weight (1 - u) + u <mu>_ring
     double p = 0.0;
     for (int k = lane; k < G.n_wd_rings; k += 32) {
@@ -500,12 +499,7 @@ __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FluxA
         double r = rwd_a + (m + 0.5) * (rdisc_a - rwd_a) / G.n_disc_r;
         wq_disc[m] = do_disc ? llrint(pow(r, 1.0 - dexp) / tot_d * kFix) : 0;
     }
-    // bright-spot strip
-    const double* bsb = A.bs_b + job * G.n_bs;
-    p = 0.0;
-    if (do_bs) for (int t = lane; t < G.n_bs; t += 32) p += bsb[t];
-    const double tot_s = warp_sum(p);
-    for (int t = lane; t < G.n_bs; t += 32) wq_bs[t] = (do_bs && tot_s > 0.0) ? llrint(bsb[t] / tot_s * kFix) : 0;
+    // (the bright-spot strip's weights wait for the strip itself: prep_strip_kernel)
     // donor: normalised at quadrature (phase 0.25: c = 0, s = 1)
     const double4* don = A.don + w * G.n_donor_q;
     const double ud = G.donor_ulimb;
@@ -536,7 +530,7 @@ __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FluxA
         double beam_norm = fis + (1.0 - fis) * (cmax > 0.0 ? cmax : 0.0);
         C.f_wd = do_wd ? par(P_WDFLUX, 0.0) : 0.0;
         C.f_d = do_disc ? par(P_DFLUX, 0.0) : 0.0;
-        C.f_s = (do_bs && beam_norm > 0.0 && tot_s > 0.0) ? par(P_SFLUX, 0.0) / beam_norm : 0.0;
+        C.f_s = (do_bs && beam_norm > 0.0) ? par(P_SFLUX, 0.0) / beam_norm : 0.0;  // 0 if the strip is dark: prep_strip_kernel
         C.f_rs = do_don ? par(P_RSFLUX, 0.0) / tot_rs * (tot_rw * kInvFix) : 0.0;
         double phi0w = par(P_PHI0, 0.0);
         phi0w -= rint(phi0w);
@@ -665,12 +659,34 @@ __device__ __forceinline__ int rec_last_close(const EventRec& rec)
     return o2 != kNoEvent ? dec_pos(rec.y, 2) : (o1 != kNoEvent ? dec_pos(rec.y, 0) : dec_pos(rec.x, 1));
 }
 
+// prep_strip_kernel: warp per job, after the strip solve (which waits for the stream ODE): fixed-point
+// weights of the strip elements; a strip without light switches its component off.
+__global__ void __launch_bounds__(128) prep_strip_kernel(const __grid_constant__ FluxArgs A)
+{
+    const GridCfg& G = A.G;
+    const int lane = threadIdx.x & 31;
+    const long long job = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (job >= A.njobs) return;
+    const long long w = job / A.L.n_ecl;
+    if (!job_live(A, A.ws[w], A.js[job])) return;
+    const bool do_bs = !(A.flags & LFB_FLAG_SKIP_BS);
+    long long* wq_bs = A.wq + job * (G.n_wd_rings + G.n_disc_r + G.n_bs) + G.n_wd_rings + G.n_disc_r;
+    const double* bsb = A.bs_b + job * G.n_bs;
+    double p = 0.0;
+    if (do_bs) for (int t = lane; t < G.n_bs; t += 32) p += bsb[t];
+    const double tot_s = warp_sum(p);
+    for (int t = lane; t < G.n_bs; t += 32) wq_bs[t] = (do_bs && tot_s > 0.0) ? llrint(bsb[t] / tot_s * kFix) : 0;
+    if (lane == 0 && !(tot_s > 0.0)) A.jc[job].f_s = 0.0;
+}
+
 // positions_kernel: one thread per solved element (or donor quarter tile) of a job: where on the
 // job's sorted sample axis its eclipse (facing) intervals open and close.
+// PART 0: white dwarf, disc and donor (nothing here needs the stream ODE); PART 1: the bright-spot strip.
+template <int PART>
 __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ FluxArgs A)
 {
     const GridCfg& G = A.G;
-    const int per_job = G.n_wd_half + G.n_disc_half + G.n_bs + G.n_donor_q;
+    const int per_job = PART == 0 ? G.n_wd_half + G.n_disc_half + G.n_donor_q : G.n_bs;
     const int padded = (per_job + 31) & ~31;  // a warp never straddles two jobs
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long job = gid / padded;
@@ -688,24 +704,23 @@ __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ 
         EventRec* ivp = A.ivp + job * A.ni_total;
         const int n_half = G.n_wd_half + G.n_disc_half;
         const EventRec none = no_events();
-        if (t < n_half + G.n_bs) {
+        if (PART == 1 || t < n_half) {
             double2 io;
             int i0;
-            bool on, mirror = t < n_half;
-            if (t < G.n_wd_half) {
+            bool on, mirror = PART == 0;
+            if (PART == 1) {
+                on = !(A.flags & LFB_FLAG_SKIP_BS);
+                io = on ? A.bs_io[job * G.n_bs + t] : make_double2(kBig, -kBig);
+                i0 = G.n_wd + G.n_disc + t;
+            } else if (t < G.n_wd_half) {
                 on = !(A.flags & LFB_FLAG_SKIP_WD);
                 io = on ? A.wd_io[w * G.n_wd_half + t] : make_double2(kBig, -kBig);
                 i0 = 2 * t;
-            } else if (t < n_half) {
+            } else {
                 int h = t - G.n_wd_half;
                 on = !(A.flags & LFB_FLAG_SKIP_DISC);
                 io = on ? A.disc_io[job * G.n_disc_half + h] : make_double2(kBig, -kBig);
                 i0 = G.n_wd + 2 * h;
-            } else {
-                int h = t - n_half;
-                on = !(A.flags & LFB_FLAG_SKIP_BS);
-                io = on ? A.bs_io[job * G.n_bs + h] : make_double2(kBig, -kBig);
-                i0 = G.n_wd + G.n_disc + h;
             }
             const bool ecl = io.y > io.x;
             const EventRec r0 = ecl ? interval_pieces(X, io.x + phi0w, io.y + phi0w) : none;
@@ -721,7 +736,7 @@ __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ 
             }
         } else {
             // donor: every tile image faces the observer for |phase - centre| < half width
-            const int h = t - n_half - G.n_bs;
+            const int h = t - n_half;
             const bool on = !(A.flags & LFB_FLAG_SKIP_DONOR);
             double4 q = on ? A.don[w * G.n_donor_q + h] : make_double4(1.0, 0.0, 0.0, 0.0);
             double Aq = W.si * q.x, Bq = -W.si * q.y, Dq = W.ci * q.z;

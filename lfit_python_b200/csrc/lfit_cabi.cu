@@ -447,12 +447,6 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
             elements_kernel<3><<<blocks(n, G.n_donor_q), kElemThreads, 0, st>>>(E);
             h->launches++;
         }
-        CK(cudaStreamWaitEvent(st, ln.join_ev, 0));  // join: the strip needs the impact point
-        KREC(LFB_K_ELEM_BS);  // includes any wait for the stream ODE on the side stream
-        if (!(flags & LFB_FLAG_SKIP_BS)) {
-            elements_kernel<2><<<blocks(njobs, G.n_bs), kElemThreads, 0, st>>>(E);
-            h->launches++;
-        }
         if (record) CK(cudaEventRecord(ln.ev[ST_FLUX], st));
         FluxArgs A;
         A.L = L;
@@ -495,11 +489,24 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
             CK(ln.gp_resid.reserve(sizeof(double) * (size_t)ss.total * (size_t)n));
             A.gp_resid = ln.gp_resid.as<double>();
         }
+        // everything of the flux preparation that does not need the strip goes before the join with the
+        // stream ODE, so that the main stream has work while the ODE finishes
         KREC(LFB_K_PREP);
         prep_kernel<<<(unsigned)((njobs + 3) / 4), 128, 0, st>>>(A);
-        const long long per_job = ((G.n_wd_half + G.n_disc_half + G.n_bs + G.n_donor_q) + 31) & ~31;
+        const long long per_job0 = ((G.n_wd_half + G.n_disc_half + G.n_donor_q) + 31) & ~31;
+        const long long per_job1 = (G.n_bs + 31) & ~31;
         KREC(LFB_K_POSITIONS);
-        positions_kernel<<<(unsigned)((njobs * per_job + 127) / 128), 128, 0, st>>>(A);
+        positions_kernel<0><<<(unsigned)((njobs * per_job0 + 127) / 128), 128, 0, st>>>(A);
+        CK(cudaStreamWaitEvent(st, ln.join_ev, 0));  // join: the strip needs the impact point
+        KREC(LFB_K_ELEM_BS);  // includes any wait for the stream ODE on the side stream
+        if (!(flags & LFB_FLAG_SKIP_BS)) {
+            elements_kernel<2><<<blocks(njobs, G.n_bs), kElemThreads, 0, st>>>(E);
+            h->launches++;
+        }
+        KREC(LFB_K_PREP_BS);
+        prep_strip_kernel<<<(unsigned)((njobs + 3) / 4), 128, 0, st>>>(A);
+        positions_kernel<1><<<(unsigned)((njobs * per_job1 + 127) / 128), 128, 0, st>>>(A);
+        h->launches += 2;
         const int EC = Ms == 1280 ? 512 : Ms == 1024 ? 256 : Ms / 2;
         const size_t smem = flux_smem_bytes(G, Ms, EC, mode ? 4 : 1);
         if (smem > (size_t)h->max_smem - 2048)
