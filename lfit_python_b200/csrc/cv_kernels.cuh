@@ -226,10 +226,14 @@ __global__ void jobcheck_kernel(DevLayout L, int what, int flags, long long njob
 // stream: ballistic stream from L1 to the disc edge -> bright-spot impact point; the azimuth rule
 // of SimpleEclipse.ln_prior.  A serial ODE per job: launched on a side stream so that it overlaps
 // the element solves that do not need it.
+// LANES: eight lanes per job (bspot_lanes, a third of the latency, three times the issue slots) -- for
+// batches too small to hide the ODE behind the element solves; else one thread per job.
+template <bool LANES>
 __global__ void stream_kernel(DevLayout L, int what, int flags, long long njobs, const double* __restrict__ theta,
                               WalkerScal* ws, JobScal* js)
 {
-    long long job = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // (a group of lanes enters and leaves together)
+    long long job = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> (LANES ? 3 : 0);
     if (job >= njobs || (flags & LFB_FLAG_SKIP_BS)) return;
     if (js[job].status != 0) return;
     long long w = job / L.n_ecl;
@@ -239,7 +243,9 @@ __global__ void stream_kernel(DevLayout L, int what, int flags, long long njobs,
     const int* g = L.gather + e * LFB_NPAR;
     double rdisc_a = fetch(L, th, g[P_RDISC]) * R.xl1;
     double imp[4];
-    if (!bspot(R, rdisc_a, imp)) {
+    const bool hit = LANES ? bspot_lanes(R, rdisc_a, imp) : bspot(R, rdisc_a, imp);
+    if (LANES && (threadIdx.x & 7) != 0) return;  // one lane of the group writes
+    if (!hit) {
         js[job].status = 2;  // the stream misses the disc (roche.bspot raises, CVModel.py:309-316)
         if (what != LFB_LN_LIKE) ws[w].lnprior = -INFINITY;
         return;

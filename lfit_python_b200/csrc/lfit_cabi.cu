@@ -150,6 +150,7 @@ struct lfb_handle {
     int max_smem = 0;
     int Mc = 1280, Mc_flux = 1024;  // segment capacity of the flux kernel in samples: chi-squared mode / flux-curve mode
     long long max_jobs_per_batch = 131072;
+    long long stream_lanes_below = 1536;  // batches smaller than this spread each stream ODE over eight lanes
     int n_lanes = kLanes;  // LFB_LANES=1 serialises the batches (clean per-stage timings for profiling)
     // layout
     bool have_layout = false, have_lc = false;
@@ -405,7 +406,11 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
     }
     CK(cudaEventRecord(ln.wd_ev, ln.side2));
     if (trace) CK(cudaEventRecord(ln.sev[0], ln.side));
-    stream_kernel<<<(unsigned)((njobs + 63) / 64), 64, 0, ln.side>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
+    if (njobs < h->stream_lanes_below)
+        stream_kernel<true><<<(unsigned)((njobs * 8 + 63) / 64), 64, 0, ln.side>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
+                                                                      ln.js.as<JobScal>());
+    else
+        stream_kernel<false><<<(unsigned)((njobs + 63) / 64), 64, 0, ln.side>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
                                                                       ln.js.as<JobScal>());
     if (trace) CK(cudaEventRecord(ln.sev[1], ln.side));
     CK(cudaEventRecord(ln.join_ev, ln.side));
@@ -709,6 +714,7 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
         int v = atoi(env);
         if (v >= 1 && v <= kLanes) h->n_lanes = v;
     }
+    if (const char* env = getenv("LFB_STREAM_LANES_BELOW")) h->stream_lanes_below = atoll(env);
     if (const char* env = getenv("LFB_MS")) {
         int v = atoi(env);
         if (v == 1024 || v == 1280 || v == 1536 || v == 2048 || v == 3072) h->Mc = v;

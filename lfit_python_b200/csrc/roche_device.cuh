@@ -675,6 +675,85 @@ LFB_HD bool bspot(const Roche& R, double rad, double out[4])
     return false;
 }
 
+#ifdef __CUDACC__
+// ---- the same integrator with one job spread over eight neighbouring lanes ----
+// The six modified-midpoint sequences of a GBS step are independent: lane k of the group runs sequence k
+// (n = 2 k + 2 substeps; lanes 6 and 7 repeat sequence 5), the six results are exchanged by shuffles and
+// every lane finishes the extrapolation tableau in the order gbs_step uses -- same numbers, bit for bit,
+// a third of the latency.  All lanes of the group must call it together (their inputs are identical).
+__device__ __forceinline__ void gbs_step_lanes(const Roche& R, const double y0[4], double H, double yout[4])
+{
+    const int sub = threadIdx.x & 7, k_mine = sub < 6 ? sub : 5;
+    const unsigned mask = 0xffu << (threadIdx.x & 24);
+    double f0[4];
+    stream_rhs(R, y0, f0);
+    const int n = 2 * (k_mine + 1);
+    const double h = H / n;
+    double z0[4], z1[4], f[4], Tm[4];
+    for (int j = 0; j < 4; ++j) { z0[j] = y0[j]; z1[j] = y0[j] + h * f0[j]; }
+    for (int m = 1; m < n; ++m) {
+        stream_rhs(R, z1, f);
+        for (int j = 0; j < 4; ++j) {
+            double t = z0[j] + 2.0 * h * f[j];
+            z0[j] = z1[j];
+            z1[j] = t;
+        }
+    }
+    stream_rhs(R, z1, f);
+    for (int j = 0; j < 4; ++j) Tm[j] = 0.5 * (z0[j] + z1[j] + h * f[j]);
+    double T[6][4];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) T[k][j] = __shfl_sync(mask, Tm[j], k, 8);
+    // the tableau, in gbs_step's order: after sequence k, columns k - 1 .. 0
+#pragma unroll
+    for (int k = 1; k < 6; ++k) {
+#pragma unroll
+        for (int m = k - 1; m >= 0; --m) {
+            double ratio = (double)(k + 1) / (double)(m + 1);
+            double fac = 1.0 / (ratio * ratio - 1.0);
+            for (int j = 0; j < 4; ++j) T[m][j] = T[m + 1][j] + (T[m + 1][j] - T[m][j]) * fac;
+        }
+    }
+    for (int j = 0; j < 4; ++j) yout[j] = T[0][j];
+}
+
+// bspot with gbs_step_lanes: every lane of the group of eight returns the same answer
+__device__ __forceinline__ bool bspot_lanes(const Roche& R, double rad, double out[4])
+{
+    if (!(rad > 0.0) || !(rad < R.xl1 - 2.0 * kStreamEps)) return false;
+    double A = R.omu / (R.xl1 * R.xl1 * R.xl1) + R.mu / (R.rs * R.rs * R.rs);
+    double l2 = 0.5 * ((A - 2.0) + sqrt(A * (9.0 * A - 8.0)));
+    double l1 = sqrt(l2);
+    double m1 = (l2 - 2.0 * A - 1.0) / (2.0 * l1);
+    double y[4] = {R.xl1 - kStreamEps, -m1 * kStreamEps, -l1 * kStreamEps, -l1 * m1 * kStreamEps};
+    for (int step = 0; step < kStreamMaxSteps; ++step) {
+        double x2 = y[0] - 1.0, ysq = y[1] * y[1];
+        double r1sq = y[0] * y[0] + ysq, r2sq = x2 * x2 + ysq;
+        double w2 = R.omu / (r1sq * sqrt(r1sq)) + R.mu / (r2sq * sqrt(r2sq)) + 1.0;
+        double H = kStreamH0 / sqrt(w2);
+        double yn[4];
+        gbs_step_lanes(R, y, H, yn);
+        double r0 = sqrt(r1sq), rn = sqrt(yn[0] * yn[0] + yn[1] * yn[1]);
+        if (rn <= rad) {
+            double h = H * (r0 - rad) / (r0 - rn);
+            for (int it = 0; it < 8; ++it) {
+                gbs_step_lanes(R, y, h, yn);
+                rn = sqrt(yn[0] * yn[0] + yn[1] * yn[1]);
+                h -= (rn - rad) * rn / (yn[0] * yn[2] + yn[1] * yn[3]);
+            }
+            gbs_step_lanes(R, y, h, yn);
+            for (int j = 0; j < 4; ++j) out[j] = yn[j];
+            return true;
+        }
+        if (yn[0] * yn[2] + yn[1] * yn[3] >= 0.0) return false;
+        for (int j = 0; j < 4; ++j) y[j] = yn[j];
+    }
+    return false;
+}
+#endif
+
 // Radius of the critical surface from the donor's centre along unit vector d, plus the
 // potential gradient there.  Newton from inside the lobe (monotone), then one safeguarded polish.
 LFB_HD double donor_radius(const Roche& R, double dx, double dy, double dz, double g[3])
