@@ -81,8 +81,10 @@ LFB_HD bool roche_init(double q, Roche& R)
         double omx = 1.0 - x;
         double f = omu / (x * x) - mu / (omx * omx) - (x - mu);
         double fp = -2.0 * omu / (x * x * x) - 2.0 * mu / (omx * omx * omx) - 1.0;
-        x -= f / fp;
+        const double dx = f / fp;
+        x -= dx;
         x = x < 1e-4 ? 1e-4 : (x > 1.0 - 1e-4 ? 1.0 - 1e-4 : x);
+        if (fabs(dx) < 1e-16) break;  // converged (quadratically: the step before was ~1e-8)
     }
     R.mu = mu;
     R.omu = omu;
@@ -97,7 +99,9 @@ LFB_HD bool roche_init(double q, Roche& R)
         double r1sq = 1.0 + z * z, ir1 = 1.0 / sqrt(r1sq);
         double f = -omu * ir1 - mu / z - cst;
         double fp = omu * z * ir1 * ir1 * ir1 + mu / (z * z);
-        z -= f / fp;
+        const double dz = f / fp;
+        z -= dz;
+        if (fabs(dz) < 1e-16) break;
     }
     R.rin = 0.9 * z;
     return true;
@@ -133,8 +137,10 @@ LFB_HD double findphi90(const Roche& R)
         origin_pot(R, 1.0, c, lam, o);
         double F1 = o.P - R.phic, F2 = o.Pl;
         double det = o.Pc * o.Pll - o.Pl * o.Pcl;
-        c += (-F1 * o.Pll + F2 * o.Pl) / det;
-        lam += (-o.Pc * F2 + o.Pcl * F1) / det;
+        const double dc = (-F1 * o.Pll + F2 * o.Pl) / det, dl = (-o.Pc * F2 + o.Pcl * F1) / det;
+        c += dc;
+        lam += dl;
+        if (fabs(dc) < 1e-16 && fabs(dl) < 1e-15) break;
     }
     return acos(c) / kPi;
 }
@@ -150,8 +156,10 @@ LFB_HD bool findi(const Roche& R, double dphi, double maxphi, double& sini)
         origin_pot(R, u, c, lam, o);
         double F1 = o.P - R.phic, F2 = o.Pl;
         double det = o.Pu * o.Pll - o.Pl * o.Pul;
-        u += (-F1 * o.Pll + F2 * o.Pl) / det;
-        lam += (-o.Pu * F2 + o.Pul * F1) / det;
+        const double du = (-F1 * o.Pll + F2 * o.Pl) / det, dl = (-o.Pu * F2 + o.Pul * F1) / det;
+        u += du;
+        lam += dl;
+        if (fabs(du) < 1e-16 && fabs(dl) < 1e-15) break;
     }
     if (!(u > 0.0) || !(u <= 1.0)) return false;
     sini = u;
