@@ -274,3 +274,40 @@ def test_gpu_gp_golden_vectors(engine):
     for (q, dphi, rwd), (inc, p3, p4, dist) in zip(g["wd_in"], g["wd_out"]):
         out, ok = engine.wdphases(q, inc, rwd, 10)
         assert ok.all() and np.allclose(out[0], (p3, p4), rtol=0, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_gp_batched_path_with_unsorted_and_multi_cycle_phases(engine):
+    """lfb_set_gp + lfb_log_prob on light curves whose phases are shuffled / span several cycles: equal to
+    the per-eclipse lfb_gp_loglike of the residuals sorted by phase, with the reference's change points."""
+    from lfit_python_b200 import _cabi, workloads
+    wl = workloads.config(2, n_bands=1, ecl_per_band=3, n_ph=210)
+    rng = np.random.default_rng(17)
+    shapes = (np.linspace(-0.45, 0.48, 210), rng.permutation(np.linspace(-0.3, 0.4, 210)), np.linspace(-1.2, 1.3, 210))
+    for e, x in enumerate(shapes):
+        sl = slice(wl.lc_off[e], wl.lc_off[e + 1])
+        wl.lc_phase[sl] = x
+        wl.lc_width[sl] = 0.5 * (x.max() - x.min()) / 210
+    wl.make_data(lambda p, x, w: engine.calc_flux(p, x, w))
+    ln_hyper = (-9.5118, -9.0953, -5.0)
+    dist = wl.apply_gp(engine, ln_hyper)
+    theta = wl.walkers(24, scatter=0.01)
+    theta[0] = wl.p0
+    like, m2ll = engine.log_prob(theta, what=_cabi.LN_LIKE, return_chisq=True)
+    hyper = np.exp(ln_hyper)
+    for k in (0, 5, 23):
+        total = 0.0
+        for e in range(3):
+            sl = slice(wl.lc_off[e], wl.lc_off[e + 1])
+            x, ye = wl.lc_phase[sl], wl.lc_ye[sl]
+            pars = wl.cv_pars(theta[k], e)
+            resid = wl.lc_y[sl] - engine.calc_flux(pars, x, wl.lc_width[sl])
+            order = np.argsort(x, kind="stable")
+            gaps = O.gp_changepoints(x, dist, pars[13])
+            one = engine.gp_loglike(x[order], ye[order], resid[order], hyper, gaps)[0]
+            assert one == pytest.approx(O.gp_log_like(x[order], ye[order], resid[order], *hyper, gaps), rel=1e-9)
+            assert m2ll[k, e] == pytest.approx(-2.0 * one, rel=1e-9)
+            total += one
+        assert like[k] == pytest.approx(total, rel=1e-9)
+    wl.apply(engine)      # leave the shared engine in chi-squared mode
+    engine.set_gp()
