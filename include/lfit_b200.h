@@ -148,7 +148,8 @@ int lfb_ingress_egress(lfb_handle *h, long long n, const double *q, const double
 long long lfb_launch_count(const lfb_handle *h);
 /* Device time (ms) of the stages of the last lfb_log_prob (its last batch), from CUDA events
  * recorded on the stream the kernels ran on; valid once that stream is synchronised.
- * out = {walker, stream, elements (4 launches), flux, finish, total}. */
+ * out = {walker, stream, elements (4 launches), flux, finish, total}; the stages are -1 when the
+ * call replayed a CUDA graph (small ensembles, from the third identical call on). */
 int lfb_last_stage_ms(lfb_handle *h, float out[6]);
 /* elements + flux of the same call, <0 if none */
 float lfb_last_kernel_ms(lfb_handle *h);

@@ -20,6 +20,10 @@ using namespace lfb;
 
 namespace {
 
+// bumped whenever a buffer is (re)allocated or freed: a captured CUDA graph is only replayed while the
+// buffers it points into are the ones it was captured with
+unsigned long long g_alloc_generation = 0;
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -27,6 +31,7 @@ struct DevBuf {
     cudaError_t reserve(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
+        ++g_alloc_generation;
         release();
         size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
@@ -35,7 +40,10 @@ struct DevBuf {
     }
     void release()
     {
-        if (p) { if (pinned_host) cudaFreeHost(p); else cudaFree(p); }
+        if (p) {
+            ++g_alloc_generation;
+            if (pinned_host) cudaFreeHost(p); else cudaFree(p);
+        }
         p = nullptr;
         cap = 0;
     }
@@ -150,6 +158,20 @@ struct lfb_handle {
     int max_smem = 0;
     int Mc = 1280, Mc_flux = 1024;  // segment capacity of the flux kernel in samples: chi-squared mode / flux-curve mode
     long long max_jobs_per_batch = 131072;
+    // CUDA graphs for small, repeated calls (launch-bound): one captured pass per (what, n, pointers)
+    struct GraphEntry {
+        int what = -1;
+        long long n = 0;
+        const void *theta = nullptr, *out = nullptr, *chi = nullptr;
+        int seen = 0;            // identical calls so far (the second one is captured)
+        long long launches = 0;  // kernels inside
+        unsigned long long generation = 0;  // g_alloc_generation at capture
+        cudaGraphExec_t exec = nullptr;
+    };
+    GraphEntry graphs[4];
+    int graph_next = 0;
+    bool graphs_on = true, stages_valid = true;
+    long long graph_max_jobs = 1024;
     long long stream_lanes_below = 1536;  // batches smaller than this spread each stream ODE over eight lanes
     int n_lanes = kLanes;  // LFB_LANES=1 serialises the batches (clean per-stage timings for profiling)
     // layout
@@ -180,6 +202,14 @@ static int fail(lfb_handle* h, int code, const std::string& msg)
 {
     h->err = msg;
     return code;
+}
+
+static void drop_graphs(lfb_handle* h)
+{
+    for (auto& g : h->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = lfb_handle::GraphEntry();
+    }
 }
 
 static bool is_device_ptr(const void* p)
@@ -543,6 +573,7 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         CK(cudaStreamWaitEvent(st, ln.join_ev, 0));
         if (record) CK(cudaEventRecord(ln.ev[ST_FLUX], st));
     }
+    CK(cudaStreamWaitEvent(st, ln.wd_ev, 0));  // the second side stream always rejoins (stream capture needs it)
     if (record) CK(cudaEventRecord(ln.ev[ST_FINISH], st));
     KREC(LFB_K_FINISH);
     if (d_out || d_chi) {
@@ -715,6 +746,7 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
         if (v >= 1 && v <= kLanes) h->n_lanes = v;
     }
     if (const char* env = getenv("LFB_STREAM_LANES_BELOW")) h->stream_lanes_below = atoll(env);
+    if (const char* env = getenv("LFB_GRAPHS")) h->graphs_on = atoi(env) != 0;
     if (const char* env = getenv("LFB_MS")) {
         int v = atoi(env);
         if (v == 1024 || v == 1280 || v == 1536 || v == 2048 || v == 3072) h->Mc = v;
@@ -728,6 +760,7 @@ void lfb_destroy(lfb_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_graphs(h);
     DevBuf* bufs[] = {&h->gather, &h->consts, &h->psrc, &h->ptype, &h->pisvar, &h->pp1, &h->pp2, &h->pnorm,
                       &h->donor_off, &h->disc_order, &h->rec_widx, &h->rec_slot, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
                       &h->chisq, &h->h_in, &h->h_out, &h->h_chisq};
@@ -764,7 +797,7 @@ int lfb_last_stage_ms(lfb_handle* h, float out[6])
     // stages of the last batch that ran on lane 0 (they overlap the other lane's work);
     // total = the whole call on the caller's stream
     Lane& ln = h->lanes[0];
-    for (int i = 0; i < ST_COUNT; ++i)
+    for (int i = 0; i < ST_COUNT && h->stages_valid; ++i)  // a replayed CUDA graph has no stage events: total only
         if (cudaEventElapsedTime(&out[i], ln.ev[i], ln.ev[i + 1]) != cudaSuccess) {
             cudaGetLastError();
             return fail(h, LFB_ECUDA, "stage events not complete: synchronise the stream first");
@@ -779,6 +812,7 @@ int lfb_last_stage_ms(lfb_handle* h, float out[6])
 int lfb_set_trace(lfb_handle* h, int on)
 {
     if (!h) return LFB_EINVAL;
+    drop_graphs(h);  // captured passes hold the old tables / buffers
     h->trace = on != 0;
     return LFB_OK;
 }
@@ -817,6 +851,7 @@ int lfb_set_layout(lfb_handle* h, int ndim, int n_ecl, int npars, const int* gat
                    const double* consts)
 {
     if (!h) return LFB_EINVAL;
+    drop_graphs(h);  // captured passes hold the old tables / buffers
     if (ndim < 0 || n_ecl < 1 || (npars != 14 && npars != 18) || !gather || n_consts < 0 || (n_consts && !consts))
         return fail(h, LFB_EINVAL, "set_layout: need n_ecl >= 1, npars in {14, 18}, gather");
     for (int e = 0; e < n_ecl; ++e)
@@ -849,6 +884,7 @@ int lfb_set_priors(lfb_handle* h, int n_prior, const int* src, const int* type, 
                    const double* norm, const int* isvar)
 {
     if (!h) return LFB_EINVAL;
+    drop_graphs(h);  // captured passes hold the old tables / buffers
     if (!h->have_layout) return fail(h, LFB_ESTATE, "set_priors: call set_layout first");
     if (n_prior < 0 || (n_prior && (!src || !type || !p1 || !p2 || !norm || !isvar)))
         return fail(h, LFB_EINVAL, "set_priors: NULL array");
@@ -873,6 +909,7 @@ int lfb_set_lightcurves(lfb_handle* h, int n_ecl, const long long* off, const do
                         const double* y, const double* ye)
 {
     if (!h) return LFB_EINVAL;
+    drop_graphs(h);  // captured passes hold the old tables / buffers
     if (!h->have_layout) return fail(h, LFB_ESTATE, "set_lightcurves: call set_layout first");
     if (n_ecl != h->n_ecl || !off || !phase || !width || !y || !ye)
         return fail(h, LFB_EINVAL, "set_lightcurves: n_ecl must match the layout; arrays must be non-NULL");
@@ -951,6 +988,73 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
     const long long per = (n + nbatch - 1) / nbatch;
     int used = 0;
     long long b = 0;
+    h->stages_valid = true;
+    // A small ensemble is launch bound (a dozen dependent kernels of 10-30 us): the second identical call
+    // is captured into a CUDA graph and later ones replay it.
+    if (h->graphs_on && !h->trace && nbatch == 1 && njobs_all <= h->graph_max_jobs) {
+        lfb_handle::GraphEntry* ge = nullptr;
+        for (auto& g : h->graphs)
+            if (g.what == what && g.n == n && g.theta == (const void*)d_theta && g.out == (const void*)d_out &&
+                g.chi == (const void*)d_chi)
+                ge = &g;
+        if (!ge) {
+            ge = &h->graphs[h->graph_next];
+            h->graph_next = (h->graph_next + 1) % 4;
+            if (ge->exec) cudaGraphExecDestroy(ge->exec);
+            *ge = lfb_handle::GraphEntry();
+            ge->what = what;
+            ge->n = n;
+            ge->theta = d_theta;
+            ge->out = d_out;
+            ge->chi = d_chi;
+        }
+        if (ge->exec && ge->generation != g_alloc_generation) {  // some buffer moved since the capture
+            cudaGraphExecDestroy(ge->exec);
+            ge->exec = nullptr;
+            ge->seen = 0;  // this call runs plainly (and re-sizes the buffers), the next one captures again
+        }
+        ++ge->seen;
+        if (ge->seen >= 2) {
+            Lane& ln = h->lanes[0];
+            CK(cudaStreamWaitEvent(ln.st, h->enter_ev, 0));
+            if (!th_dev) {
+                memcpy(h->h_in.p, theta, sizeof(double) * (size_t)n * h->ndim);
+                CK(cudaMemcpyAsync(h->theta.p, h->h_in.p, sizeof(double) * (size_t)n * h->ndim, cudaMemcpyHostToDevice, ln.st));
+            }
+            bool ok = ge->exec != nullptr;
+            if (!ok) {
+                // buffers have their sizes from the first call: nothing inside allocates while capturing
+                const long long l0 = h->launches;
+                cudaGraph_t graph = nullptr;
+                if (cudaStreamBeginCapture(ln.st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const int rc = run_batch(h, ln, L, h->lc, what, 0, 0, n, d_theta, d_out, d_chi, nullptr, nullptr, false);
+                    const cudaError_t e = cudaStreamEndCapture(ln.st, &graph);
+                    if (rc == LFB_OK && e == cudaSuccess && graph &&
+                        cudaGraphInstantiate(&ge->exec, graph, 0) == cudaSuccess) {
+                        ge->launches = h->launches - l0;
+                        ge->generation = g_alloc_generation;
+                        ok = true;
+                    }
+                    if (graph) cudaGraphDestroy(graph);
+                }
+                h->launches = l0;
+                if (!ok) {
+                    cudaGetLastError();
+                    h->graphs_on = false;  // this driver / configuration cannot capture the pass: plain launches from now on
+                    ge->exec = nullptr;
+                }
+            }
+            if (ok) {
+                CK(cudaGraphLaunch(ge->exec, ln.st));
+                h->launches += ge->launches;
+                h->stages_valid = false;
+                CK(cudaEventRecord(ln.done_ev, ln.st));
+                CK(cudaStreamWaitEvent(st, ln.done_ev, 0));
+                goto finished;
+            }
+        }
+    }
+    {
     // one lane: run on the caller's own stream (no cross-stream hand-off)
     const bool inline_lane = h->n_lanes == 1;
     cudaStream_t lane0_st = h->lanes[0].st;
@@ -980,6 +1084,8 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
         CK(cudaEventRecord(h->lanes[i].done_ev, h->lanes[i].st));
         CK(cudaStreamWaitEvent(st, h->lanes[i].done_ev, 0));
     }
+    }
+finished:
     CK(cudaEventRecord(h->t1_ev, st));
     h->ev_valid = true;
     if (!out_dev || (chisq_out && !chi_dev)) {
@@ -1056,6 +1162,7 @@ int lfb_calc_flux(lfb_handle* h, long long n_sets, const double* pars, int npars
 int lfb_set_gp(lfb_handle* h, int enabled, const int gp_src[3], const double* dist_cp)
 {
     if (!h) return LFB_EINVAL;
+    drop_graphs(h);  // captured passes hold the old tables / buffers
     if (!enabled) {
         h->gp_on = false;
         return LFB_OK;

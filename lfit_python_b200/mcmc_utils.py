@@ -207,10 +207,11 @@ class DeviceEnsembleSampler:
         self.naccepted = torch.zeros(nwalkers, dtype=torch.int64, device=self.device)
         self.iterations = 0
 
-    def _log_prob(self, theta):
+    def _log_prob(self, theta, out=None):
         torch = self.torch
         theta = theta.contiguous()
-        out = torch.empty(theta.shape[0], dtype=torch.float64, device=self.device)
+        if out is None:
+            out = torch.empty(theta.shape[0], dtype=torch.float64, device=self.device)
         self.engine.log_prob_device(theta.data_ptr(), theta.shape[0], out.data_ptr(), what=self.what,
                                     stream=self.stream.cuda_stream)
         return out
@@ -224,6 +225,12 @@ class DeviceEnsembleSampler:
                 self.pos = torch.as_tensor(np.asarray(initial_state, dtype=np.float64)).to(self.device)
                 self.lnp = self._log_prob(self.pos)
             pos, lnp = self.pos, self.lnp
+            # proposals and their log-probabilities live in fixed buffers: identical calls, which the engine
+            # replays as a CUDA graph when the ensemble is small
+            if getattr(self, "_prop", None) is None:
+                self._prop = torch.empty((half, self.ndim), dtype=torch.float64, device=self.device)
+                self._new_lnp = torch.empty(half, dtype=torch.float64, device=self.device)
+            prop, new_lnp = self._prop, self._new_lnp
             for _ in range(nsteps):
                 perm = torch.randperm(self.nwalkers, device=self.device, generator=self.gen)
                 for first, second in ((perm[:half], perm[half:]), (perm[half:], perm[:half])):
@@ -231,8 +238,8 @@ class DeviceEnsembleSampler:
                     u = torch.rand(half, dtype=torch.float64, device=self.device, generator=self.gen)
                     zz = ((self.a - 1.0) * u + 1.0) ** 2 / self.a
                     partner = c[torch.randint(half, (half,), device=self.device, generator=self.gen)]
-                    prop = partner - (partner - s) * zz[:, None]
-                    new_lnp = self._log_prob(prop)
+                    torch.sub(partner, (partner - s) * zz[:, None], out=prop)
+                    self._log_prob(prop, out=new_lnp)
                     lnpdiff = (self.ndim - 1.0) * torch.log(zz) + new_lnp - lnp[first]
                     accept = lnpdiff > torch.log(torch.rand(half, dtype=torch.float64, device=self.device,
                                                             generator=self.gen))

@@ -287,3 +287,50 @@ def test_device_resident_sampler_keeps_its_books(engine):
     assert np.median(lnp) > np.median(lnp0) - 2 * wl.ndim      # relaxes from a tight ball to the posterior width, no further
     pos2, lnp2 = s.run_mcmc(None, 5)                           # continues from the resident state
     assert s.iterations == 20 and np.array_equal(lnp2, engine.log_prob(pos2))
+
+
+def test_small_repeated_calls_replay_a_cuda_graph_safely():
+    """From the second identical small call on, lfb_log_prob replays a captured CUDA graph: results must stay
+    bit-identical, follow new inputs in the same buffers, and survive re-allocation and re-configuration."""
+    import torch
+    eng = _cabi.Engine(0)
+    try:
+        wl = workloads.config(0, n_ph=150)
+        wl.make_data(lambda p, x, w: eng.calc_flux(p, x, w))
+        wl.apply(eng)
+        theta = wl.walkers(64, scatter=0.02)
+        t = torch.from_numpy(theta).cuda()
+        out = torch.empty(64, dtype=torch.float64, device="cuda")
+        s = torch.cuda.Stream()
+
+        def call(n=64):
+            eng.log_prob_device(t.data_ptr(), n, out.data_ptr(), stream=s.cuda_stream)
+            s.synchronize()
+            return out[:n].cpu().numpy().copy()
+
+        first = call()
+        l0 = eng.launch_count
+        for _ in range(4):                                   # plain, captured, replayed, replayed
+            assert np.array_equal(call(), first)
+        per_call = (eng.launch_count - l0) // 4
+        assert per_call >= 10                                # the replayed kernels are counted too
+        assert eng.last_stage_ms()["total"] > 0 and eng.last_stage_ms()["flux"] == -1.0   # no stage events in a graph
+        t.copy_(torch.from_numpy(theta[::-1].copy()))        # new walkers in the same buffer
+        assert np.array_equal(call(), first[::-1])
+        big = wl.walkers(3000, scatter=0.02)                 # a large call re-allocates the lane buffers
+        ref_big = eng.log_prob(big)
+        assert np.array_equal(call(), first[::-1])
+        assert np.array_equal(call(), first[::-1])
+        assert np.array_equal(eng.log_prob(big), ref_big)
+        wl2 = workloads.config(0, n_ph=90)                   # new light curves: captured passes are dropped
+        wl2.make_data(lambda p, x, w: eng.calc_flux(p, x, w))
+        wl2.apply(eng)
+        a = call()
+        assert not np.array_equal(a, first[::-1])
+        for _ in range(3):
+            assert np.array_equal(call(), a)
+        assert np.array_equal(call(17), a[:17])              # another size is another graph
+        assert np.array_equal(call(17), a[:17])
+        assert np.array_equal(call(17), a[:17])
+    finally:
+        eng.close()
