@@ -144,6 +144,51 @@ int lfb_wdphases(lfb_handle *h, long long n, const double *q, const double *incl
 int lfb_ingress_egress(lfb_handle *h, long long n, const double *q, const double *incl_deg, const double *pts,
                        double *out, int *ok);
 
+/* ---- Stretch-move sampler with the ensemble resident in HBM ----
+ * Replaces emcee.EnsembleSampler(nwalkers, npars, ln_prob, args=(model,), pool=pool) (mcmcfit.py:283-288)
+ * and the sampler.sample() loops of run_burnin / run_mcmc_save (mcmc_utils.py:114-183) for the model set on
+ * the handle.  emcee is third-party and not vendored; the move is the published stretch move (a = 2 by
+ * default), first half of the ensemble then second half (emcee 2.x).  Random numbers are Philox4x32-10
+ * counted by (step, half, walker): an ensemble sharded over N GPUs follows the 1-GPU chain bit for bit.
+ * what = LFB_LN_PROB normally.  nwalkers even and >= 2 ndim (mcmcfit.py:195-196). */
+typedef struct lfb_sampler lfb_sampler;
+int lfb_sampler_create(lfb_handle *h, long long nwalkers, double a, unsigned long long seed, int what,
+                       lfb_sampler **out);
+void lfb_sampler_destroy(lfb_sampler *s);
+/* Start positions pos[n][ndim] (host or device) and optionally their log-probabilities (NULL: evaluated). */
+int lfb_sampler_set_state(lfb_sampler *s, const double *pos, const double *lnp, void *stream);
+/* nsteps full steps on this GPU (nothing crosses PCIe; small ensembles replay one CUDA graph per step).
+ * Asynchronous: lfb_sampler_get_state synchronises. */
+int lfb_sampler_run(lfb_sampler *s, long long nsteps, void *stream);
+/* Sharded ensemble (one process per GPU, the ensemble replicated): this rank proposes, evaluates and
+ * accepts rows [lo, hi) of half `half` (0 or 1) into packed[hi - lo][ndim + 2] = (position, ln_prob,
+ * accepted) on the device (NULL: the sampler's own buffer, lfb_sampler_packed); the caller all-gathers
+ * the packed rows of all ranks (NCCL), then lfb_sampler_half_end writes gathered[world][slot][ndim + 2]
+ * (rank r's rows at gathered[r][0..]; balanced contiguous shards, lower ranks one row longer) into the
+ * ensemble.  The second half's half_end ends the step. */
+int lfb_sampler_half_begin(lfb_sampler *s, int half, long long lo, long long hi, double *packed, void *stream);
+int lfb_sampler_half_end(lfb_sampler *s, int half, const double *gathered, int world, long long slot, void *stream);
+double *lfb_sampler_packed(lfb_sampler *s);    /* device, [nwalkers / 2][ndim + 2] */
+double *lfb_sampler_positions(lfb_sampler *s); /* device, [nwalkers][ndim] */
+double *lfb_sampler_log_prob(lfb_sampler *s);  /* device, [nwalkers] */
+/* Ensemble, log-probabilities, per-walker acceptance counts and the step count to the host (any NULL). */
+int lfb_sampler_get_state(lfb_sampler *s, double *pos, double *lnp, long long *naccepted, long long *iterations);
+/* Record the ensemble after every step into a device buffer of `steps` steps (0: off); read_chain copies
+ * the steps recorded since the last read to out[steps][n][ndim + 1] (position, ln_prob; host) and empties it. */
+int lfb_sampler_set_chain(lfb_sampler *s, long long steps);
+int lfb_sampler_read_chain(lfb_sampler *s, double *out, long long *n_steps);
+/* The move's draws on the host (tests): out[cnt][3] = (z, partner row, ln u') of rows [0, cnt) of one half. */
+int lfb_stretch_draws(unsigned long long seed, unsigned long long step, int half, long long half_n, double a,
+                      long long cnt, double *out);
+
+/* ---- Chain file (mcmc_utils.py:157-164; reader mcmc_utils.py:252-272) ----
+ * rows[n_steps][n][ndim + 1] (position, ln_prob; host) as the reference's lines
+ * "{0:4d} {1:s} {2:f}\n".format(k, " ".join(map(str, pos[k])), prob[k]) -- byte for byte, formatted in
+ * parallel and appended with ONE write per call instead of one open() per walker per step.
+ * lfb_chain_format returns the size of the text and copies it to out when cap holds it. */
+long long lfb_chain_format(long long n_steps, long long n, int ndim, const double *rows, char *out, long long cap);
+int lfb_chain_append(const char *path, long long n_steps, long long n, int ndim, const double *rows);
+
 /* counters for bench.py: kernels launched by this handle since creation */
 long long lfb_launch_count(const lfb_handle *h);
 /* Device time (ms) of the stages of the last lfb_log_prob (its last batch), from CUDA events

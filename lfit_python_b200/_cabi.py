@@ -23,6 +23,10 @@ EXPORTS = (
     "lfb_set_priors", "lfb_set_lightcurves", "lfb_log_prob", "lfb_calc_flux", "lfb_roche",
     "lfb_launch_count", "lfb_last_kernel_ms", "lfb_last_stage_ms", "lfb_measure_fp64_peak",
     "lfb_set_trace", "lfb_last_trace_ms", "lfb_set_gp", "lfb_gp_loglike", "lfb_wdphases", "lfb_ingress_egress",
+    "lfb_sampler_create", "lfb_sampler_destroy", "lfb_sampler_set_state", "lfb_sampler_run", "lfb_sampler_half_begin",
+    "lfb_sampler_half_end", "lfb_sampler_packed", "lfb_sampler_positions", "lfb_sampler_log_prob",
+    "lfb_sampler_get_state", "lfb_sampler_set_chain", "lfb_sampler_read_chain", "lfb_stretch_draws",
+    "lfb_chain_format", "lfb_chain_append",
 )
 TRACE_KERNELS = ("walker_kernel", "jobcheck_kernel", "elements_kernel<1> disc", "elements_kernel<0> white dwarf",
                  "elements_kernel<3> donor", "prep_kernel", "positions_kernel", "elements_kernel<2> strip",
@@ -84,6 +88,24 @@ def load():
     lib.lfb_gp_loglike.argtypes = [vp, C.c_longlong, C.c_int, dp, dp, dp, dp, C.c_int, dp, dp]
     lib.lfb_wdphases.argtypes = [vp, C.c_longlong, dp, dp, dp, C.c_int, dp, ip]
     lib.lfb_ingress_egress.argtypes = [vp, C.c_longlong, dp, dp, dp, dp, ip]
+    ll, lp = C.c_longlong, C.POINTER(C.c_longlong)
+    lib.lfb_sampler_create.argtypes = [vp, ll, C.c_double, C.c_ulonglong, C.c_int, C.POINTER(vp)]
+    lib.lfb_sampler_destroy.argtypes = [vp]
+    lib.lfb_sampler_destroy.restype = None
+    lib.lfb_sampler_set_state.argtypes = [vp, vp, vp, vp]
+    lib.lfb_sampler_run.argtypes = [vp, ll, vp]
+    lib.lfb_sampler_half_begin.argtypes = [vp, C.c_int, ll, ll, vp, vp]
+    lib.lfb_sampler_half_end.argtypes = [vp, C.c_int, vp, C.c_int, ll, vp]
+    for name in ("lfb_sampler_packed", "lfb_sampler_positions", "lfb_sampler_log_prob"):
+        getattr(lib, name).argtypes = [vp]
+        getattr(lib, name).restype = vp
+    lib.lfb_sampler_get_state.argtypes = [vp, vp, vp, vp, lp]
+    lib.lfb_sampler_set_chain.argtypes = [vp, ll]
+    lib.lfb_sampler_read_chain.argtypes = [vp, vp, lp]
+    lib.lfb_stretch_draws.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_int, ll, C.c_double, ll, dp]
+    lib.lfb_chain_format.argtypes = [ll, ll, C.c_int, dp, C.c_char_p, ll]
+    lib.lfb_chain_format.restype = ll
+    lib.lfb_chain_append.argtypes = [C.c_char_p, ll, ll, C.c_int, dp]
     _lib = lib
     return lib
 
@@ -295,6 +317,41 @@ class Engine:
         self._check(self._lib.lfb_roche(self._h, int(which), a.shape[0], _dp(a), _dp(b), _dp(out), _ip(ok)),
                     "lfb_roche")
         return out, ok.astype(bool)
+
+
+def chain_text(rows):
+    """rows (n_steps, n, ndim + 1) -> the reference's chain lines (mcmc_utils.py:163-164) as bytes."""
+    rows = _f64(rows)
+    if rows.ndim != 3:
+        raise ValueError("chain_text: rows must be (n_steps, n_walkers, ndim + 1)")
+    lib = load()
+    steps, n, w = rows.shape
+    size = lib.lfb_chain_format(steps, n, w - 1, _dp(rows), None, 0)
+    if size < 0:
+        raise EngineError("lfb_chain_format failed")
+    buf = C.create_string_buffer(int(size) + 1)
+    lib.lfb_chain_format(steps, n, w - 1, _dp(rows), buf, size)
+    return buf.raw[:size]
+
+
+def chain_append(path, rows):
+    """Append rows (n_steps, n, ndim + 1) to the chain file with one write."""
+    rows = _f64(rows)
+    if rows.ndim != 3:
+        raise ValueError("chain_append: rows must be (n_steps, n_walkers, ndim + 1)")
+    steps, n, w = rows.shape
+    rc = load().lfb_chain_append(os.fsencode(path), steps, n, w - 1, _dp(rows))
+    if rc != 0:
+        raise EngineError("lfb_chain_append(%r) failed (%d)" % (path, rc))
+
+
+def stretch_draws(seed, step, half, half_n, a, cnt):
+    """(z, partner row, ln u') of rows [0, cnt) of one half at one step -- the sampler kernels' random stream."""
+    out = np.empty((int(cnt), 3))
+    rc = load().lfb_stretch_draws(int(seed), int(step), int(half), int(half_n), float(a), int(cnt), _dp(out))
+    if rc != 0:
+        raise EngineError("lfb_stretch_draws failed (%d)" % rc)
+    return out
 
 
 _default_engines = {}

@@ -20,18 +20,18 @@ using namespace lfb;
 
 namespace {
 
-// bumped whenever a buffer is (re)allocated or freed: a captured CUDA graph is only replayed while the
-// buffers it points into are the ones it was captured with
-unsigned long long g_alloc_generation = 0;
-
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     bool pinned_host = false;
+    // Generation counter of the owning handle (null: a buffer no captured CUDA graph points into).  Bumped
+    // whenever the buffer is (re)allocated or freed: a graph is only replayed while the buffers it was
+    // captured with are still the ones in use.
+    unsigned long long* gen = nullptr;
     cudaError_t reserve(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
-        ++g_alloc_generation;
+        if (gen) ++*gen;
         release();
         size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
@@ -41,7 +41,7 @@ struct DevBuf {
     void release()
     {
         if (p) {
-            ++g_alloc_generation;
+            if (gen) ++*gen;
             if (pinned_host) cudaFreeHost(p); else cudaFree(p);
         }
         p = nullptr;
@@ -56,6 +56,7 @@ struct SampleSet {
     DevBuf gp_x, gp_var, gp_slot, gp_span;  // GP likelihood: points in ascending raw phase
     int max_chunks = 1;
     int max_nph = 0;
+    int max_gaps = 0;  // GP likelihood: the most change-point gaps any of the light curves spans
     long long total = 0;
     void release()
     {
@@ -98,6 +99,11 @@ struct Lane {
     cudaEvent_t kev[LFB_K_COUNT + 1] = {}, sev[2] = {};  // per-kernel trace (lfb_set_trace), side-stream pair
     bool kev_set[LFB_K_COUNT + 1] = {};
     DevBuf ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, qmom, ivp, chi_part, gp_resid;
+    void track(unsigned long long* gen)
+    {
+        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &qmom, &ivp, &chi_part, &gp_resid};
+        for (DevBuf* x : b) x->gen = gen;
+    }
     cudaError_t create()
     {
         cudaError_t e;
@@ -165,7 +171,7 @@ struct lfb_handle {
         const void *theta = nullptr, *out = nullptr, *chi = nullptr;
         int seen = 0;            // identical calls so far (the second one is captured)
         long long launches = 0;  // kernels inside
-        unsigned long long generation = 0;  // g_alloc_generation at capture
+        unsigned long long generation = 0;  // alloc_generation at capture
         cudaGraphExec_t exec = nullptr;
     };
     GraphEntry graphs[4];
@@ -184,7 +190,16 @@ struct lfb_handle {
     // work
     DevBuf theta, out, chisq;
     DevBuf h_in, h_out, h_chisq;
-    lfb_handle() { h_in.pinned_host = h_out.pinned_host = h_chisq.pinned_host = true; }
+    DevBuf scratch[6];  // device staging of the scalar helpers (lfb_roche, lfb_wdphases, ...): kept between calls
+    bool h2d_pending = false;  // the last call staged theta through h_in and returned without synchronising
+    // bumped when a buffer a captured graph may point into moves (the lanes' buffers, theta / out / chisq staging)
+    unsigned long long alloc_generation = 0;
+    lfb_handle()
+    {
+        h_in.pinned_host = h_out.pinned_host = h_chisq.pinned_host = true;
+        for (int i = 0; i < kLanes; ++i) lanes[i].track(&alloc_generation);
+        theta.gen = out.gen = chisq.gen = h_in.gen = &alloc_generation;
+    }
 };
 
 static std::string g_create_error;
@@ -253,7 +268,7 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const 
     std::vector<double2> gp_span((size_t)std::max(n_ecl, 1));
     std::vector<long long> chunk_off(n_ecl + 1, 0);
     std::vector<int4> chunks;
-    int max_nph = 0, max_chunks = 1;
+    int max_nph = 0, max_chunks = 1, max_gaps = 0;
     std::vector<int> order, pt;
     std::vector<double> raw, wph;
     for (int e = 0; e < n_ecl; ++e) {
@@ -358,6 +373,13 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const 
         }
         for (int jj = 0; jj < n_ph; ++jj) gp_slot[o + jj] = (int)wph[pt_index[o + jj]];
         gp_span[e] = n_ph ? make_double2(gp_x[o], gp_x[o + n_ph - 1]) : make_double2(0.0, 0.0);
+        {
+            // one gap per cycle number c with x_min < c < 1 + x_max (gp_changepoints)
+            int ngap = 0;
+            for (int c = (int)floor(gp_span[e].x); n_ph && c <= (int)ceil(gp_span[e].y); ++c)
+                if ((double)c > gp_span[e].x && (double)c < 1.0 + gp_span[e].y) ++ngap;
+            max_gaps = std::max(max_gaps, ngap);
+        }
         chunk_off[e + 1] = chunk_off[e] + nch;
         max_chunks = std::max(max_chunks, nch);
     }
@@ -381,6 +403,7 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const 
     CK(cudaStreamSynchronize(h->stream));  // the host vectors die here
     ss.max_nph = max_nph;
     ss.max_chunks = max_chunks;
+    ss.max_gaps = max_gaps;
     ss.total = total;
     return LFB_OK;
 }
@@ -765,6 +788,8 @@ void lfb_destroy(lfb_handle* h)
                       &h->donor_off, &h->disc_order, &h->rec_widx, &h->rec_slot, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
                       &h->chisq, &h->h_in, &h->h_out, &h->h_chisq};
     for (DevBuf* b : bufs) b->release();
+    for (DevBuf& b : h->scratch) b.release();
+    h->gp_dist.release();
     h->lc.release();
     h->cf_lc.release();
     for (int i = 0; i < kLanes; ++i) {
@@ -889,7 +914,8 @@ int lfb_set_priors(lfb_handle* h, int n_prior, const int* src, const int* type, 
     if (n_prior < 0 || (n_prior && (!src || !type || !p1 || !p2 || !norm || !isvar)))
         return fail(h, LFB_EINVAL, "set_priors: NULL array");
     for (int k = 0; k < n_prior; ++k) {
-        if (src[k] >= h->ndim) return fail(h, LFB_EINVAL, "set_priors: source column out of range");
+        if (src[k] >= h->ndim || src[k] < -h->n_consts)
+            return fail(h, LFB_EINVAL, "set_priors: source column / constant slot out of range");
         if (type[k] < 0 || type[k] > LFB_PRIOR_MODJEFF) return fail(h, LFB_EINVAL, "set_priors: unknown prior type");
     }
     CK(cudaSetDevice(h->device));
@@ -920,6 +946,11 @@ int lfb_set_lightcurves(lfb_handle* h, int n_ecl, const long long* off, const do
     int rc = build_samples(h, h->lc, h->Mc, n_ecl, off, phase, width, y, ye);
     if (rc) return rc;
     h->have_lc = true;
+    if (h->gp_on && h->lc.max_gaps > kMaxGaps) {
+        h->gp_on = false;
+        return fail(h, LFB_EINVAL, "set_lightcurves: a light curve spans more than 8 orbital cycles; the GP likelihood "
+                                   "holds at most 8 change-point gaps (GP switched off)");
+    }
     return LFB_OK;
 }
 
@@ -941,6 +972,28 @@ static DevLayout make_layout(lfb_handle* h)
     return L;
 }
 
+}  // extern "C"
+
+// One pass over n walkers (device pointers) enqueued on st with plain launches on lane 0: no CUDA graph of its
+// own, no timing events, nothing allocated once the buffers have their sizes -- safe inside a stream capture.
+static int enqueue_pass_inline(lfb_handle* h, int what, long long n, const double* d_theta, double* d_out, cudaStream_t st)
+{
+    if (what == LFB_LN_PRIOR) CK(h->lanes[0].chi_part.reserve(8));
+    DevLayout L = make_layout(h);
+    Lane& ln = h->lanes[0];
+    cudaStream_t keep = ln.st;
+    ln.st = st;
+    int rc = LFB_OK;
+    const long long per = std::max(1LL, h->max_jobs_per_batch / h->n_ecl);
+    for (long long w0 = 0; w0 < n && rc == LFB_OK; w0 += per)
+        rc = run_batch(h, ln, L, h->lc, what, 0, 0, std::min(per, n - w0), d_theta + w0 * h->ndim, d_out + w0, nullptr,
+                       nullptr, nullptr, false);
+    ln.st = keep;
+    return rc;
+}
+
+extern "C" {
+
 int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, double* out, double* chisq_out,
                  void* stream_v)
 {
@@ -958,6 +1011,10 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
     const bool chi_dev = chisq_out && is_device_ptr(chisq_out);
     const double* d_theta = theta;
     if (!th_dev) {
+        // the previous call may have returned with its copy out of h_in still in flight (host theta, device
+        // outputs): t1_ev was recorded behind it
+        if (h->h2d_pending) CK(cudaEventSynchronize(h->t1_ev));
+        h->h2d_pending = false;
         CK(h->theta.reserve(th_bytes));
         CK(h->h_in.reserve(th_bytes));
         d_theta = h->theta.as<double>();  // staged batch by batch below, so that a copy overlaps the batch before
@@ -1008,7 +1065,7 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
             ge->out = d_out;
             ge->chi = d_chi;
         }
-        if (ge->exec && ge->generation != g_alloc_generation) {  // some buffer moved since the capture
+        if (ge->exec && ge->generation != h->alloc_generation) {  // some buffer moved since the capture
             cudaGraphExecDestroy(ge->exec);
             ge->exec = nullptr;
             ge->seen = 0;  // this call runs plainly (and re-sizes the buffers), the next one captures again
@@ -1032,7 +1089,7 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
                     if (rc == LFB_OK && e == cudaSuccess && graph &&
                         cudaGraphInstantiate(&ge->exec, graph, 0) == cudaSuccess) {
                         ge->launches = h->launches - l0;
-                        ge->generation = g_alloc_generation;
+                        ge->generation = h->alloc_generation;
                         ok = true;
                     }
                     if (graph) cudaGraphDestroy(graph);
@@ -1098,6 +1155,8 @@ finished:
         CK(cudaStreamSynchronize(st));
         if (!out_dev) memcpy(out, h->h_out.p, sizeof(double) * (size_t)n);
         if (chisq_out && !chi_dev) memcpy(chisq_out, h->h_chisq.p, sizeof(double) * (size_t)njobs);
+    } else if (!th_dev) {
+        h->h2d_pending = true;
     }
     return LFB_OK;
 }
@@ -1168,11 +1227,16 @@ int lfb_set_gp(lfb_handle* h, int enabled, const int gp_src[3], const double* di
         return LFB_OK;
     }
     if (!h->have_layout || !gp_src || !dist_cp) return fail(h, LFB_ESTATE, "set_gp: set_layout first; need gp_src[3] and dist_cp[n_ecl]");
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 3; ++i)
         if (gp_src[i] >= h->ndim || gp_src[i] < -h->n_consts)
             return fail(h, LFB_EINVAL, "set_gp: hyper-parameter source out of range");
-        h->gp_src[i] = gp_src[i];
-    }
+    for (int e = 0; e < h->n_ecl; ++e)
+        if (!(dist_cp[e] > 0.0) || !(dist_cp[e] < 0.5))
+            return fail(h, LFB_EINVAL, "set_gp: dist_cp must lie in (0, 0.5): no change points otherwise");
+    if (h->have_lc && h->lc.max_gaps > kMaxGaps)
+        return fail(h, LFB_EINVAL, "set_gp: a light curve spans more than 8 orbital cycles; the GP likelihood holds at "
+                                   "most 8 change-point gaps");
+    for (int i = 0; i < 3; ++i) h->gp_src[i] = gp_src[i];
     CK(cudaSetDevice(h->device));
     int rc = upload(h, h->gp_dist, dist_cp, sizeof(double) * (size_t)h->n_ecl);
     if (rc) return rc;
@@ -1192,32 +1256,29 @@ int lfb_gp_loglike(lfb_handle* h, long long n_sets, int n, const double* x, cons
     for (int k = 1; k < n; ++k)
         if (!(x[k] >= x[k - 1])) return fail(h, LFB_EINVAL, "gp_loglike: x must ascend");
     CK(cudaSetDevice(h->device));
-    DevBuf dx, dye, dr, dh, dg, dout;
-    auto cleanup = [&]() { dx.release(); dye.release(); dr.release(); dh.release(); dg.release(); dout.release(); };
-    cudaError_t e = cudaSuccess;
+    DevBuf &dx = h->scratch[0], &dye = h->scratch[1], &dr = h->scratch[2], &dh = h->scratch[3], &dg = h->scratch[4],
+           &dout = h->scratch[5];
     const size_t nn = (size_t)std::max(n, 1), ng = (size_t)std::max(n_gaps, 1);
-    if ((e = dx.reserve(8 * nn)) != cudaSuccess || (e = dye.reserve(8 * nn)) != cudaSuccess ||
-        (e = dr.reserve(8 * nn * (size_t)n_sets)) != cudaSuccess || (e = dh.reserve(24 * (size_t)n_sets)) != cudaSuccess ||
-        (e = dg.reserve(16 * ng * (size_t)n_sets)) != cudaSuccess || (e = dout.reserve(8 * (size_t)n_sets)) != cudaSuccess) {
-        cleanup();
-        return fail(h, LFB_ECUDA, cudaGetErrorString(e));
-    }
+    CK(dx.reserve(8 * nn));
+    CK(dye.reserve(8 * nn));
+    CK(dr.reserve(8 * nn * (size_t)n_sets));
+    CK(dh.reserve(24 * (size_t)n_sets));
+    CK(dg.reserve(16 * ng * (size_t)n_sets));
+    CK(dout.reserve(8 * (size_t)n_sets));
     cudaStream_t st = h->stream;
     if (n) {
-        cudaMemcpyAsync(dx.p, x, 8 * (size_t)n, cudaMemcpyDefault, st);
-        cudaMemcpyAsync(dye.p, ye, 8 * (size_t)n, cudaMemcpyDefault, st);
-        cudaMemcpyAsync(dr.p, resid, 8 * (size_t)n * (size_t)n_sets, cudaMemcpyDefault, st);
+        CK(cudaMemcpyAsync(dx.p, x, 8 * (size_t)n, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(dye.p, ye, 8 * (size_t)n, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(dr.p, resid, 8 * (size_t)n * (size_t)n_sets, cudaMemcpyDefault, st));
     }
-    cudaMemcpyAsync(dh.p, hyper, 24 * (size_t)n_sets, cudaMemcpyDefault, st);
-    if (n_gaps) cudaMemcpyAsync(dg.p, gaps, 16 * (size_t)n_gaps * (size_t)n_sets, cudaMemcpyDefault, st);
+    CK(cudaMemcpyAsync(dh.p, hyper, 24 * (size_t)n_sets, cudaMemcpyDefault, st));
+    if (n_gaps) CK(cudaMemcpyAsync(dg.p, gaps, 16 * (size_t)n_gaps * (size_t)n_sets, cudaMemcpyDefault, st));
     gp_batch_kernel<<<(unsigned)((n_sets + 63) / 64), 64, 0, st>>>(n_sets, n, dx.as<double>(), dye.as<double>(), dr.as<double>(),
                                                                     dh.as<double>(), n_gaps, dg.as<double>(), dout.as<double>());
+    CK(cudaGetLastError());
     h->launches++;
-    cudaMemcpyAsync(out, dout.p, 8 * (size_t)n_sets, cudaMemcpyDefault, st);
-    e = cudaStreamSynchronize(st);
-    cleanup();
-    if (e != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
-    if ((e = cudaGetLastError()) != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    CK(cudaMemcpyAsync(out, dout.p, 8 * (size_t)n_sets, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
     return LFB_OK;
 }
 
@@ -1229,28 +1290,23 @@ int lfb_wdphases(lfb_handle* h, long long n, const double* q, const double* incl
         return fail(h, LFB_EINVAL, "wdphases: bad arguments");
     if (n == 0) return LFB_OK;
     CK(cudaSetDevice(h->device));
-    DevBuf dq, di, dr, dout, dok;
-    auto cleanup = [&]() { dq.release(); di.release(); dr.release(); dout.release(); dok.release(); };
-    cudaError_t e;
-    if ((e = dq.reserve(8 * (size_t)n)) != cudaSuccess || (e = di.reserve(8 * (size_t)n)) != cudaSuccess ||
-        (e = dr.reserve(8 * (size_t)n)) != cudaSuccess || (e = dout.reserve(16 * (size_t)n)) != cudaSuccess ||
-        (e = dok.reserve(4 * (size_t)n)) != cudaSuccess) {
-        cleanup();
-        return fail(h, LFB_ECUDA, cudaGetErrorString(e));
-    }
+    DevBuf &dq = h->scratch[0], &di = h->scratch[1], &dr = h->scratch[2], &dout = h->scratch[3], &dok = h->scratch[4];
+    CK(dq.reserve(8 * (size_t)n));
+    CK(di.reserve(8 * (size_t)n));
+    CK(dr.reserve(8 * (size_t)n));
+    CK(dout.reserve(16 * (size_t)n));
+    CK(dok.reserve(4 * (size_t)n));
     cudaStream_t st = h->stream;
-    cudaMemcpyAsync(dq.p, q, 8 * (size_t)n, cudaMemcpyDefault, st);
-    cudaMemcpyAsync(di.p, incl_deg, 8 * (size_t)n, cudaMemcpyDefault, st);
-    cudaMemcpyAsync(dr.p, r1, 8 * (size_t)n, cudaMemcpyDefault, st);
+    CK(cudaMemcpyAsync(dq.p, q, 8 * (size_t)n, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(di.p, incl_deg, 8 * (size_t)n, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(dr.p, r1, 8 * (size_t)n, cudaMemcpyDefault, st));
     wdphases_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, dq.as<double>(), di.as<double>(), dr.as<double>(), ntheta,
                                                               dout.as<double>(), dok.as<int>());
+    CK(cudaGetLastError());
     h->launches++;
-    cudaMemcpyAsync(out, dout.p, 16 * (size_t)n, cudaMemcpyDefault, st);
-    cudaMemcpyAsync(ok, dok.p, 4 * (size_t)n, cudaMemcpyDefault, st);
-    e = cudaStreamSynchronize(st);
-    cleanup();
-    if (e != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
-    if ((e = cudaGetLastError()) != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    CK(cudaMemcpyAsync(out, dout.p, 16 * (size_t)n, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(ok, dok.p, 4 * (size_t)n, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
     return LFB_OK;
 }
 
@@ -1261,28 +1317,23 @@ int lfb_ingress_egress(lfb_handle* h, long long n, const double* q, const double
     if (n < 0 || (n && (!q || !incl_deg || !pts || !out || !ok))) return fail(h, LFB_EINVAL, "ingress_egress: bad arguments");
     if (n == 0) return LFB_OK;
     CK(cudaSetDevice(h->device));
-    DevBuf dq, di, dp, dout, dok;
-    auto cleanup = [&]() { dq.release(); di.release(); dp.release(); dout.release(); dok.release(); };
-    cudaError_t e;
-    if ((e = dq.reserve(8 * (size_t)n)) != cudaSuccess || (e = di.reserve(8 * (size_t)n)) != cudaSuccess ||
-        (e = dp.reserve(40 * (size_t)n)) != cudaSuccess || (e = dout.reserve(16 * (size_t)n)) != cudaSuccess ||
-        (e = dok.reserve(4 * (size_t)n)) != cudaSuccess) {
-        cleanup();
-        return fail(h, LFB_ECUDA, cudaGetErrorString(e));
-    }
+    DevBuf &dq = h->scratch[0], &di = h->scratch[1], &dp = h->scratch[2], &dout = h->scratch[3], &dok = h->scratch[4];
+    CK(dq.reserve(8 * (size_t)n));
+    CK(di.reserve(8 * (size_t)n));
+    CK(dp.reserve(40 * (size_t)n));
+    CK(dout.reserve(16 * (size_t)n));
+    CK(dok.reserve(4 * (size_t)n));
     cudaStream_t st = h->stream;
-    cudaMemcpyAsync(dq.p, q, 8 * (size_t)n, cudaMemcpyDefault, st);
-    cudaMemcpyAsync(di.p, incl_deg, 8 * (size_t)n, cudaMemcpyDefault, st);
-    cudaMemcpyAsync(dp.p, pts, 40 * (size_t)n, cudaMemcpyDefault, st);
+    CK(cudaMemcpyAsync(dq.p, q, 8 * (size_t)n, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(di.p, incl_deg, 8 * (size_t)n, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(dp.p, pts, 40 * (size_t)n, cudaMemcpyDefault, st));
     ingress_egress_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, dq.as<double>(), di.as<double>(), dp.as<double>(),
                                                                       dout.as<double>(), dok.as<int>());
+    CK(cudaGetLastError());
     h->launches++;
-    cudaMemcpyAsync(out, dout.p, 16 * (size_t)n, cudaMemcpyDefault, st);
-    cudaMemcpyAsync(ok, dok.p, 4 * (size_t)n, cudaMemcpyDefault, st);
-    e = cudaStreamSynchronize(st);
-    cleanup();
-    if (e != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
-    if ((e = cudaGetLastError()) != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    CK(cudaMemcpyAsync(out, dout.p, 16 * (size_t)n, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(ok, dok.p, 4 * (size_t)n, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
     return LFB_OK;
 }
 
@@ -1294,26 +1345,22 @@ int lfb_roche(lfb_handle* h, int which, long long n, const double* a, const doub
         return fail(h, LFB_EINVAL, "roche: bad arguments");
     if (n == 0) return LFB_OK;
     CK(cudaSetDevice(h->device));
-    DevBuf da, db, dout, dok;
-    auto cleanup = [&]() { da.release(); db.release(); dout.release(); dok.release(); };
-    cudaError_t e;
-    if ((e = da.reserve(sizeof(double) * n)) != cudaSuccess || (e = db.reserve(sizeof(double) * n)) != cudaSuccess ||
-        (e = dout.reserve(sizeof(double) * 4 * n)) != cudaSuccess || (e = dok.reserve(sizeof(int) * n)) != cudaSuccess) {
-        cleanup();
-        return fail(h, LFB_ECUDA, cudaGetErrorString(e));
-    }
-    cudaMemcpyAsync(da.p, a, sizeof(double) * n, cudaMemcpyDefault, h->stream);
-    if (b) cudaMemcpyAsync(db.p, b, sizeof(double) * n, cudaMemcpyDefault, h->stream);
-    else cudaMemsetAsync(db.p, 0, sizeof(double) * n, h->stream);
-    roche_kernel<<<(unsigned)((n + 63) / 64), 64, 0, h->stream>>>(which, n, da.as<double>(), db.as<double>(),
-                                                                  dout.as<double>(), dok.as<int>());
+    DevBuf &da = h->scratch[0], &db = h->scratch[1], &dout = h->scratch[2], &dok = h->scratch[3];
+    CK(da.reserve(sizeof(double) * n));
+    CK(db.reserve(sizeof(double) * n));
+    CK(dout.reserve(sizeof(double) * 4 * n));
+    CK(dok.reserve(sizeof(int) * n));
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(da.p, a, sizeof(double) * n, cudaMemcpyDefault, st));
+    if (b) CK(cudaMemcpyAsync(db.p, b, sizeof(double) * n, cudaMemcpyDefault, st));
+    else CK(cudaMemsetAsync(db.p, 0, sizeof(double) * n, st));
+    roche_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(which, n, da.as<double>(), db.as<double>(), dout.as<double>(),
+                                                           dok.as<int>());
+    CK(cudaGetLastError());
     h->launches++;
-    cudaMemcpyAsync(out, dout.p, sizeof(double) * 4 * n, cudaMemcpyDefault, h->stream);
-    cudaMemcpyAsync(ok, dok.p, sizeof(int) * n, cudaMemcpyDefault, h->stream);
-    e = cudaStreamSynchronize(h->stream);
-    cleanup();
-    if (e != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
-    if ((e = cudaGetLastError()) != cudaSuccess) return fail(h, LFB_ECUDA, cudaGetErrorString(e));
+    CK(cudaMemcpyAsync(out, dout.p, sizeof(double) * 4 * n, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(ok, dok.p, sizeof(int) * n, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
     return LFB_OK;
 }
 
@@ -1350,3 +1397,5 @@ int lfb_measure_fp64_peak(lfb_handle* h, int iters, double* tflops)
 }
 
 }  // extern "C"
+
+#include "sampler.cuh"

@@ -145,22 +145,43 @@ def run_burnin(sampler, startPos, nSteps, storechain=False, progress=False):
 
 def format_step(pos, prob):
     """One step of every walker in the reference's chain format: "{k:4d} {pos...} {lnprob:f}"
-    (mcmc_utils.py:163-164)."""
+    (mcmc_utils.py:163-164), formatted natively (lfb_chain_format) in one call."""
+    from . import _cabi
+    rows = np.concatenate([np.asarray(pos, dtype=np.float64), np.asarray(prob, dtype=np.float64)[:, None]], axis=1)
+    return _cabi.chain_text(rows[None]).decode()
+
+
+def format_step_python(pos, prob):
+    """The same lines with the reference's own expression (the checker of the native formatter)."""
     return "".join("{0:4d} {1:s} {2:f}\n".format(k, " ".join(map(str, pos[k])), prob[k]) for k in range(pos.shape[0]))
 
 
-def run_mcmc_save(sampler, startPos, nSteps, rState, file, col_names='', progress=False, **kwargs):
-    """Run nSteps storing the chain; append every step to `file` (one write per step instead of
-    the reference's one open() per walker per step, mcmc_utils.py:157-164; same bytes)."""
+def run_mcmc_save(sampler, startPos, nSteps, rState, file, col_names='', progress=False, flush_every=16, **kwargs):
+    """Run nSteps storing the chain and append it to `file` (mcmc_utils.py:135-183): the steps are
+    formatted natively and appended `flush_every` steps at a time with one write, instead of the
+    reference's one open() per walker per step (mcmc_utils.py:157-164); same bytes.  A DeviceSampler
+    keeps the chain on the GPU between flushes (run_mcmc_save_device)."""
+    from . import _cabi
+    if hasattr(sampler, "run_block"):
+        run_mcmc_save_device(sampler, startPos, nSteps, file, col_names=col_names, block=max(flush_every, 1), keep=False)
+        return sampler
     if file:
         with open(file, "w") as f:
             f.write(col_names)
             if col_names:
                 f.write("\n")
+    pending = []
+
+    def flush():
+        if file and pending:
+            _cabi.chain_append(file, np.asarray(pending))
+        pending.clear()
+
     for pos, prob, state in sampler.sample(startPos, iterations=nSteps, store=True, **kwargs):
-        if file:
-            with open(file, 'a') as f:
-                f.write(format_step(pos, prob))
+        pending.append(np.concatenate([pos, np.asarray(prob)[:, None]], axis=1))
+        if len(pending) >= flush_every:
+            flush()
+    flush()
     return sampler
 
 
@@ -184,74 +205,143 @@ def readchain(file, nskip=0, thin=1):
     return np.swapaxes(chain, 0, 1)[:, nskip::thin, :]
 
 
-class DeviceEnsembleSampler:
-    """The same stretch move with the ensemble resident in GPU memory.
+class DeviceSampler:
+    """emcee's stretch move with the ensemble resident in GPU memory:
+    hand-written kernels (csrc/sampler.cuh: Philox draws + proposals, accept / update, chain record) around
+    the engine's log-probability pass, through the C ABI's lfb_sampler_*.  A step moves nothing across PCIe;
+    a small ensemble replays one captured CUDA graph per step.  Replaces emcee.EnsembleSampler + pool
+    (/root/reference/mcmcfit.py:283-288) for the model set on `engine` (an _cabi.Engine or anything with
+    `.engine`, e.g. a flatten.VectorModel)."""
 
-    Positions, log-probabilities, proposals and the accept/reject step live in torch CUDA tensors
-    (plumbing only); the log-probability is the CUDA engine called through raw device pointers, so
-    a step moves nothing across PCIe.  `vec` is a flatten.VectorModel (or anything with `.engine`
-    and `.ndim`)."""
+    def __init__(self, engine, nwalkers, a=2.0, seed=0, what=2):
+        import ctypes as C
+        from . import _cabi
+        self._C, self._cabi = C, _cabi
+        self.engine = getattr(engine, "engine", engine)
+        self._lib = _cabi.load()
+        self.nwalkers, self.ndim, self.a = int(nwalkers), int(self.engine.ndim), float(a)
+        h = C.c_void_p()
+        rc = self._lib.lfb_sampler_create(self.engine._h, self.nwalkers, self.a, int(seed) & (2 ** 64 - 1), int(what),
+                                          C.byref(h))
+        self.engine._check(rc, "lfb_sampler_create")
+        self._s = h
+        self._chain_cap = 0
 
-    def __init__(self, nwalkers, vec, a=2.0, seed=None, what=2):
-        import torch
-        if nwalkers % 2 or nwalkers < 2 * vec.ndim:
-            raise ValueError("need an even number of walkers, at least twice the number of dimensions")
-        self.torch = torch
-        self.engine, self.ndim, self.nwalkers, self.a, self.what = vec.engine, vec.ndim, nwalkers, float(a), what
-        self.device = torch.device("cuda", self.engine.device)
-        self.gen = torch.Generator(device=self.device)
-        if seed is not None:
-            self.gen.manual_seed(int(seed))
-        self.stream = torch.cuda.Stream(device=self.device)
-        self.pos = self.lnp = None
-        self.naccepted = torch.zeros(nwalkers, dtype=torch.int64, device=self.device)
-        self.iterations = 0
+    def close(self):
+        if getattr(self, "_s", None):
+            self._lib.lfb_sampler_destroy(self._s)
+            self._s = None
 
-    def _log_prob(self, theta, out=None):
-        torch = self.torch
-        theta = theta.contiguous()
-        if out is None:
-            out = torch.empty(theta.shape[0], dtype=torch.float64, device=self.device)
-        self.engine.log_prob_device(theta.data_ptr(), theta.shape[0], out.data_ptr(), what=self.what,
-                                    stream=self.stream.cuda_stream)
-        return out
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
-    def run_mcmc(self, initial_state, nsteps):
-        """Advance nsteps; returns (positions, log-probabilities) as host arrays."""
-        torch = self.torch
-        half = self.nwalkers // 2
-        with torch.cuda.stream(self.stream):
-            if initial_state is not None:
-                self.pos = torch.as_tensor(np.asarray(initial_state, dtype=np.float64)).to(self.device)
-                self.lnp = self._log_prob(self.pos)
-            pos, lnp = self.pos, self.lnp
-            # proposals and their log-probabilities live in fixed buffers: identical calls, which the engine
-            # replays as a CUDA graph when the ensemble is small
-            if getattr(self, "_prop", None) is None:
-                self._prop = torch.empty((half, self.ndim), dtype=torch.float64, device=self.device)
-                self._new_lnp = torch.empty(half, dtype=torch.float64, device=self.device)
-            prop, new_lnp = self._prop, self._new_lnp
-            for _ in range(nsteps):
-                perm = torch.randperm(self.nwalkers, device=self.device, generator=self.gen)
-                for first, second in ((perm[:half], perm[half:]), (perm[half:], perm[:half])):
-                    s, c = pos[first], pos[second]
-                    u = torch.rand(half, dtype=torch.float64, device=self.device, generator=self.gen)
-                    zz = ((self.a - 1.0) * u + 1.0) ** 2 / self.a
-                    partner = c[torch.randint(half, (half,), device=self.device, generator=self.gen)]
-                    torch.sub(partner, (partner - s) * zz[:, None], out=prop)
-                    self._log_prob(prop, out=new_lnp)
-                    lnpdiff = (self.ndim - 1.0) * torch.log(zz) + new_lnp - lnp[first]
-                    accept = lnpdiff > torch.log(torch.rand(half, dtype=torch.float64, device=self.device,
-                                                            generator=self.gen))
-                    # masked updates with fixed shapes: nothing here makes the host wait for the GPU
-                    pos[first] = torch.where(accept[:, None], prop, s)
-                    lnp[first] = torch.where(accept, new_lnp, lnp[first])
-                    self.naccepted[first] += accept.to(torch.int64)
-                self.iterations += 1
-            self.pos, self.lnp = pos, lnp
-        self.stream.synchronize()
-        return pos.cpu().numpy(), lnp.cpu().numpy()
+    def set_state(self, pos, lnp=None):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        if pos.shape != (self.nwalkers, self.ndim):
+            raise ValueError("incompatible input dimensions")
+        lnp = None if lnp is None else np.ascontiguousarray(lnp, dtype=np.float64)
+        rc = self._lib.lfb_sampler_set_state(self._s, pos.ctypes.data, None if lnp is None else lnp.ctypes.data, None)
+        self.engine._check(rc, "lfb_sampler_set_state")
+
+    def run(self, nsteps, stream=None):
+        """Enqueue nsteps full steps (asynchronous; get_state / read_chain synchronise)."""
+        self.engine._check(self._lib.lfb_sampler_run(self._s, int(nsteps), stream), "lfb_sampler_run")
+
+    def _state(self, want_pos=True):
+        C = self._C
+        pos = np.empty((self.nwalkers, self.ndim)) if want_pos else None
+        lnp = np.empty(self.nwalkers)
+        acc = np.empty(self.nwalkers, dtype=np.int64)
+        it = C.c_longlong()
+        rc = self._lib.lfb_sampler_get_state(self._s, pos.ctypes.data if want_pos else None, lnp.ctypes.data,
+                                             acc.ctypes.data, C.byref(it))
+        self.engine._check(rc, "lfb_sampler_get_state")
+        return pos, lnp, acc, int(it.value)
+
+    def get_state(self):
+        pos, lnp, _, _ = self._state()
+        return pos, lnp
+
+    @property
+    def naccepted(self):
+        return self._state(False)[2]
+
+    @property
+    def iterations(self):
+        return self._state(False)[3]
 
     @property
     def acceptance_fraction(self):
-        return self.naccepted.cpu().numpy() / max(self.iterations, 1)
+        _, _, acc, it = self._state(False)
+        return acc / max(it, 1)
+
+    def set_chain(self, steps):
+        """Record the ensemble after every step in a device buffer holding `steps` steps (0: off)."""
+        self.engine._check(self._lib.lfb_sampler_set_chain(self._s, int(steps)), "lfb_sampler_set_chain")
+        self._chain_cap = int(steps)
+
+    def read_chain(self):
+        """The steps recorded since the last read, (steps, nwalkers, ndim + 1); empties the buffer."""
+        C = self._C
+        out = np.empty((max(self._chain_cap, 1), self.nwalkers, self.ndim + 1))
+        n = C.c_longlong()
+        self.engine._check(self._lib.lfb_sampler_read_chain(self._s, out.ctypes.data, C.byref(n)), "lfb_sampler_read_chain")
+        return out[: int(n.value)]
+
+    # -- the emcee call shape the reference's loops use (mcmc_utils.py:114-183) --
+    def reset(self):
+        pass
+
+    def run_mcmc(self, initial_state, nsteps, log_prob0=None, **_):
+        if initial_state is not None:
+            self.set_state(initial_state, log_prob0)
+        self.run(nsteps)
+        pos, lnp = self.get_state()
+        return pos, lnp, None
+
+    def sample(self, initial_state, iterations=1, log_prob0=None, **_):
+        """Step by step (one device -> host copy per step); run_block / run_mcmc_save are the fast paths."""
+        if initial_state is not None:
+            self.set_state(initial_state, log_prob0)
+        for _ in range(iterations):
+            self.run(1)
+            pos, lnp = self.get_state()
+            yield pos, lnp, None
+
+    def run_block(self, nsteps, block=64):
+        """nsteps recorded steps, read back `block` at a time: yields (steps, nwalkers, ndim + 1) arrays."""
+        block = max(1, min(int(block), int(nsteps)))
+        self.set_chain(block)
+        done = 0
+        while done < nsteps:
+            k = min(block, nsteps - done)
+            self.run(k)
+            yield self.read_chain()
+            done += k
+        self.set_chain(0)
+
+
+def run_mcmc_save_device(sampler, startPos, nSteps, file, col_names='', block=64, keep=True):
+    """run_mcmc_save (mcmc_utils.py:135-183) for a DeviceSampler: the chain is recorded on the device,
+    read back `block` steps at a time and appended with one native write per block -- the same bytes as
+    the reference's one open() per walker per step.  Returns the chain (nwalkers, nsteps, ndim + 1) if keep."""
+    from . import _cabi
+    if file:
+        with open(file, "w") as f:
+            f.write(col_names)
+            if col_names:
+                f.write("\n")
+    if startPos is not None:
+        sampler.set_state(startPos)
+    blocks = []
+    for rows in sampler.run_block(nSteps, block):
+        if file:
+            _cabi.chain_append(file, rows)
+        if keep:
+            blocks.append(rows.copy())
+    if keep and blocks:
+        return np.swapaxes(np.concatenate(blocks, axis=0), 0, 1)
+    return None

@@ -48,3 +48,96 @@ class ShardedLogProb:
             a, b = shard_bounds(n, r, self.world)
             res[a:b] = out[r, : b - a]
         return res
+
+
+class ShardedDeviceSampler:
+    """The stretch move over an ensemble sharded across the GPUs of one box, device resident
+    (replaces the multiprocessing.Pool of /root/reference/mcmcfit.py:273-288).
+
+    Every rank holds the whole ensemble in its HBM.  Per half-step a rank proposes, evaluates and
+    accepts its contiguous slice of the half (lfb_sampler_half_begin) into a packed
+    [rows, ndim + 2] buffer (new position, ln_prob, accepted); ONE all-gather of the packed rows
+    (NCCL over NVLink on the device buffers; gloo on host tensors in the CPU tests) hands every rank
+    the whole half, and lfb_sampler_half_end writes it into the replicated ensemble.  Nothing touches
+    the host.  The draws are counter based (Philox keyed by seed, counted by step / half / walker), so
+    N ranks follow the 1-GPU chain bit for bit.
+
+    `ops` does the per-rank work: by default the CUDA sampler of `engine`; tests pass a host stand-in
+    with the same four methods (set_state, half_begin, half_end, get_state)."""
+
+    def __init__(self, engine, nwalkers, a=2.0, seed=0, what=2, group=None, ops=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.nwalkers, self.half = int(nwalkers), int(nwalkers) // 2
+        self.slot = -(-self.half // self.world)      # equal-sized slots serve ragged shards
+        self.lo, self.hi = shard_bounds(self.half, self.rank, self.world)
+        self.iterations = 0
+        if ops is not None:
+            self.ops, self.cuda = ops, False
+            self.ndim = ops.ndim
+            self._packed = torch.zeros((self.slot, self.ndim + 2), dtype=torch.float64)
+            self._gathered = torch.zeros((self.world, self.slot, self.ndim + 2), dtype=torch.float64)
+            return
+        from .mcmc_utils import DeviceSampler
+        self.ops, self.cuda = DeviceSampler(engine, nwalkers, a=a, seed=seed, what=what), True
+        self.ndim = self.ops.ndim
+        self.device = torch.device("cuda", self.ops.engine.device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._packed = torch.zeros((self.slot, self.ndim + 2), dtype=torch.float64, device=self.device)
+        self._gathered = torch.zeros((self.world, self.slot, self.ndim + 2), dtype=torch.float64, device=self.device)
+        torch.cuda.synchronize(self.device)     # the fills ran on torch's stream, the sampler has its own
+
+    def close(self):
+        if self.cuda:
+            self.ops.close()
+
+    def set_state(self, pos, lnp=None):
+        self.ops.set_state(pos, lnp)
+
+    def get_state(self):
+        if self.cuda:
+            self.stream.synchronize()
+        return self.ops.get_state()
+
+    @property
+    def naccepted(self):
+        if self.cuda:
+            self.stream.synchronize()
+        return self.ops.naccepted
+
+    def set_chain(self, steps):
+        self.ops.set_chain(steps)
+
+    def read_chain(self):
+        if self.cuda:
+            self.stream.synchronize()
+        return self.ops.read_chain()
+
+    def _half_step(self, half):
+        dist = self.dist
+        if self.cuda:
+            lib, s, st = self.ops._lib, self.ops._s, self.stream.cuda_stream
+            check = self.ops.engine._check
+            check(lib.lfb_sampler_half_begin(s, half, self.lo, self.hi, self._packed.data_ptr(), st), "lfb_sampler_half_begin")
+            dist.all_gather_into_tensor(self._gathered, self._packed, group=self.group)
+            check(lib.lfb_sampler_half_end(s, half, self._gathered.data_ptr(), self.world, self.slot, st), "lfb_sampler_half_end")
+        else:
+            rows = self.ops.half_begin(half, self.lo, self.hi)
+            self._packed[: self.hi - self.lo] = self.torch.from_numpy(rows)
+            dist.all_gather_into_tensor(self._gathered.view(-1), self._packed.view(-1), group=self.group)
+            self.ops.half_end(half, self._gathered.numpy(), self.world, self.slot)
+
+    def run(self, nsteps):
+        """nsteps full steps; asynchronous on the sampler's stream (get_state synchronises)."""
+        if self.cuda:
+            with self.torch.cuda.stream(self.stream):
+                for _ in range(nsteps):
+                    self._half_step(0)
+                    self._half_step(1)
+        else:
+            for _ in range(nsteps):
+                self._half_step(0)
+                self._half_step(1)
+        self.iterations += nsteps

@@ -270,23 +270,19 @@ def test_device_resident_buffers(engine):
 def test_device_resident_sampler_keeps_its_books(engine):
     from lfit_python_b200 import mcmc_utils
 
-    class Vec:
-        pass
-
     wl = workloads.config(1, n_ph=150)
     wl.make_data(lambda p, x, w: engine.calc_flux(p, x, w))
     wl.apply(engine)
-    vec = Vec()
-    vec.engine, vec.ndim = engine, wl.ndim
     p0 = wl.walkers(64, scatter=0.01, ln_prior_fn=lambda t: engine.log_prob(t, what=_cabi.LN_PRIOR))
-    s = mcmc_utils.DeviceEnsembleSampler(64, vec, seed=5)
+    s = mcmc_utils.DeviceSampler(engine, 64, seed=5)
     lnp0 = engine.log_prob(p0)
-    pos, lnp = s.run_mcmc(p0, 15)
+    pos, lnp, _ = s.run_mcmc(p0, 15)
     assert np.array_equal(lnp, engine.log_prob(pos))          # stored ln_prob belongs to the stored position
     assert np.isfinite(lnp).all() and 0.05 < s.acceptance_fraction.mean() < 0.95
     assert np.median(lnp) > np.median(lnp0) - 2 * wl.ndim      # relaxes from a tight ball to the posterior width, no further
-    pos2, lnp2 = s.run_mcmc(None, 5)                           # continues from the resident state
+    pos2, lnp2, _ = s.run_mcmc(None, 5)                        # continues from the resident state
     assert s.iterations == 20 and np.array_equal(lnp2, engine.log_prob(pos2))
+    s.close()
 
 
 def test_small_repeated_calls_replay_a_cuda_graph_safely():

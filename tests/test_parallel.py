@@ -65,3 +65,54 @@ def test_two_rank_gloo(tmp_path):
     assert np.array_equal(pos, p0)  # N ranks == 1 process, bit for bit
     c0 = np.load(tmp_path / "calls_0.npy")
     assert c0[0] == 4 and c0[1] == 5 and c0[2] == 1   # rank 0's share of 8, 9 and 1 rows
+
+
+# ---- the device-resident sharded sampler's orchestration, with the numpy stand-in doing each rank's work ----
+def _gauss(theta):
+    return -0.5 * np.sum(np.atleast_2d(theta) ** 2 / np.array([1.0, 4.0, 0.25]), axis=1)
+
+
+def _sharded_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from lfit_python_b200.parallel import ShardedDeviceSampler
+    from oracle.stretch import StretchOracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    calls = []
+
+    def fn(theta):
+        calls.append(len(theta))
+        return _gauss(theta)
+
+    for nw in (14, 16):          # ragged (7 rows of a half over 2 ranks) and even shards
+        ops = StretchOracle(fn, nw, 3, seed=21)
+        smp = ShardedDeviceSampler(None, nw, ops=ops)
+        smp.set_state(np.random.default_rng(3).standard_normal((nw, 3)))
+        calls.clear()
+        smp.run(25)
+        pos, lnp = smp.get_state()
+        np.save(os.path.join(out_dir, "spos_%d_%d.npy" % (nw, rank)), pos)
+        np.save(os.path.join(out_dir, "sacc_%d_%d.npy" % (nw, rank)), smp.naccepted)
+        lo, hi = smp.lo, smp.hi
+        assert calls == [hi - lo] * 50        # this rank evaluated only its slice of each half-step
+    dist.destroy_process_group()
+
+
+def test_sharded_device_sampler_orchestration_gloo(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    from oracle.stretch import StretchOracle
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for nw in (14, 16):
+        one = StretchOracle(_gauss, nw, 3, seed=21)
+        one.set_state(np.random.default_rng(3).standard_normal((nw, 3)))
+        one.run(25)
+        for r in range(2):
+            assert np.array_equal(np.load(tmp_path / ("spos_%d_%d.npy" % (nw, r))), one.pos)   # N ranks == 1, bit for bit
+            assert np.array_equal(np.load(tmp_path / ("sacc_%d_%d.npy" % (nw, r))), one.naccepted)
+        assert one.naccepted.sum() > 0

@@ -83,3 +83,65 @@ def test_chain_file_format_and_reader(tmp_path):
     chain = utils.readchain(str(path))
     assert chain.shape == (8, 5, 3)
     assert np.array_equal(chain[:, :, :2], s.chain)
+
+
+# ---- the stretch move of the device sampler: random stream, algebra, statistics (numpy restatement) ----
+def test_philox_known_answers():
+    """Random123's known-answer vectors for Philox4x32-10."""
+    from oracle.stretch import philox4x32_10
+    z = np.zeros(1, dtype=np.uint32)
+    out = [int(v[0]) for v in philox4x32_10(z, z, z, z, 0, 0)]
+    assert out == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = np.full(1, 0xffffffff, dtype=np.uint32)
+    out = [int(v[0]) for v in philox4x32_10(f, f, f, f, 0xffffffff, 0xffffffff)]
+    assert out == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    c = [np.full(1, v, dtype=np.uint32) for v in (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344)]
+    out = [int(v[0]) for v in philox4x32_10(*c, 0xa4093822, 0x299f31d0)]
+    assert out == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_native_draws_equal_the_numpy_restatement():
+    """lfb_stretch_draws (the kernels' Philox + z + partner, compiled for the host) against oracle/stretch.py."""
+    from lfit_python_b200 import _cabi
+    from oracle import stretch as S
+    for seed, step, half, hn in [(0, 0, 0, 25), (12345678901234567, 7, 1, 2048), (2 ** 63 + 5, 2 ** 33 + 1, 0, 32768)]:
+        d = _cabi.stretch_draws(seed, step, half, hn, 2.0, 500)
+        z, partner, lnu = S.draws(seed, step, half, hn, 2.0, np.arange(500))
+        assert np.array_equal(d[:, 0], z) and np.array_equal(d[:, 1], partner)
+        assert np.allclose(d[:, 2], lnu, rtol=1e-15, atol=0)
+        assert (z >= 0.5).all() and (z <= 2.0).all() and partner.min() >= 0 and partner.max() < hn
+    # g(z) ~ 1/sqrt(z) on [1/a, a]: E[z] = (a + 1 + 1/a) / 3
+    z, partner, lnu = S.draws(5, 3, 0, 1000, 2.0, np.arange(200000) % 1000 + 1000 * (np.arange(200000) // 1000))
+    assert abs(z.mean() - 3.5 / 3.0) < 3e-3 and abs(np.exp(lnu).mean() - 0.5) < 3e-3
+
+
+def test_stretch_oracle_samples_a_gaussian():
+    from oracle.stretch import StretchOracle
+    mu, sig = np.array([1.0, -2.0, 0.5, 3.0]), np.array([0.5, 2.0, 1.0, 0.1])
+    s = StretchOracle(lambda t: gauss_lnprob(t, mu, 1 / sig), 64, 4, seed=8)
+    s.set_state(mu + 0.1 * np.random.default_rng(3).standard_normal((64, 4)))
+    s.run(300)
+    s.run(1500, record=True)
+    flat = np.asarray(s.chain)[::5, :, :4].reshape(-1, 4)
+    assert np.allclose(flat.mean(axis=0), mu, atol=4 * sig / np.sqrt(300))
+    assert np.allclose(flat.std(axis=0), sig, rtol=0.15)
+    assert 0.2 < (s.naccepted / 1800).mean() < 0.9
+
+
+def test_native_chain_text_equals_the_reference_expression():
+    """lfb_chain_format against "{0:4d} {1:s} {2:f}".format(k, " ".join(map(str, pos)), prob) (mcmc_utils.py:163-164)."""
+    from lfit_python_b200 import _cabi
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([rng.standard_normal(40000) * 10.0 ** rng.integers(-30, 30, 40000),
+                           rng.standard_normal(20000), rng.uniform(0, 200, 20000),
+                           [0.0, -0.0, 1e16, 1e-4, 9.999e-5, 1e15, 123456789012345678.0, 0.1037, 120.0, 1e-5, 1.5e-5, 1e100,
+                            1e-100, 5e-324, 1.7976931348623157e308, np.inf, -np.inf, np.nan, 1e22, 1e21,
+                            9007199254740993.0, 0.1 + 0.2, 1 / 3, 2.5e-5]])
+    vals = vals[: len(vals) // 4 * 4]
+    rows = vals.reshape(2, -1, 4)
+    txt = _cabi.chain_text(rows).decode()
+    ref = "".join(utils.format_step_python(r[:, :3], r[:, 3]) for r in rows)
+    assert txt == ref
+    assert utils.format_step(rows[0, :, :3], rows[0, :, 3]) == utils.format_step_python(rows[0, :, :3], rows[0, :, 3])
+    with pytest.raises(ValueError):
+        _cabi.chain_text(np.zeros((3, 4)))
