@@ -52,13 +52,34 @@ def build(force=False):
 
 
 _lib = None
+_NATIVE_PATH = os.path.join(_HERE, "_native", "liblfit_oracle_native.so")
+_use_native = False
+
+
+def use_native():
+    """bench.py's CPU legs: compile the oracle on THIS machine with -O3 -march=native (no fused multiply-add
+    contraction, so the numbers do not change) and use that build from now on.  Returns False, keeping the
+    portable build, if the compiler is missing.  Must be called before the first lib()."""
+    global _use_native
+    if _lib is not None:
+        return _use_native
+    try:
+        os.makedirs(os.path.dirname(_NATIVE_PATH), exist_ok=True)
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-fopenmp", "-std=c11", "-ffp-contract=off",
+                               "-shared", "-o", _NATIVE_PATH, os.path.join(_HERE, "lfit_oracle.c"), "-lm"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _use_native = True
+    except Exception:
+        _use_native = False
+    return _use_native
 
 
 def lib():
     global _lib
     if _lib is None:
-        build()
-        _lib = C.CDLL(_LIB_PATH)
+        if not _use_native:
+            build()
+        _lib = C.CDLL(_NATIVE_PATH if _use_native else _LIB_PATH)
         dp = C.POINTER(C.c_double)
         _lib.lfo_default_config.argtypes = [C.POINTER(Config)]
         _lib.lfo_roche_xl1.argtypes = [C.c_double, dp]

@@ -101,6 +101,11 @@ def test_device_sampler_samples_the_prior(engine):
     wl = setup(engine, cfg=0)
     nw = 64
     p0 = wl.walkers(nw, scatter=0.05, seed=1, ln_prior_fn=lambda t: engine.log_prob(t, what=_cabi.LN_PRIOR))
+    # (the ball is 1e-6 wide in ulimb, mcmcfit.py:220, and the stretch move widens a dimension only by a factor
+    # of order one per step: start these two margins at their prior width)
+    rng = np.random.default_rng(0)
+    p0[:, wl.names.index("ulimb_b0")] = 0.284 + 0.001 * rng.standard_normal(nw)
+    p0[:, wl.names.index("wdFlux_b0")] = rng.uniform(0.002, 0.199, nw)
     s = mcmc_utils.DeviceSampler(engine, nw, seed=12, what=_cabi.LN_PRIOR)
     s.set_state(p0)
     s.run(3000)

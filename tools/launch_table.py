@@ -1,14 +1,39 @@
 #!/usr/bin/env python
 """Tabulate an `ncu --csv --metrics ...` launch list: one row per kernel name (mean over launches).
 
-    python tools/launch_table.py gpurun_out/launches.csv [n_lightcurves_per_launch]
+    python tools/launch_table.py gpurun_out/launches.csv [n_lightcurves_per_launch] [--json out.json]
+
+With --json the per-kernel FP64 operation counts (FMA = 2, add = mul = 1; ncu counters
+smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on), DRAM bytes and shared-memory wavefronts per
+light curve are written next to a hash of the kernel sources they were measured on; bench.py quotes its
+roofline fractions on that file and says so when the sources have changed since.
 """
 import csv
+import hashlib
+import json
+import os
 import sys
 from collections import OrderedDict
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = ("cv_kernels.cuh", "roche_device.cuh", "gp_device.cuh", "lfit_cabi.cu", "sampler.cuh")
 
-def main(path, n_lc=None):
+
+def csrc_sha():
+    """Hash of the kernel sources (what the counters belong to)."""
+    h = hashlib.sha256()
+    for name in CSRC:
+        with open(os.path.join(ROOT, "lfit_python_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def short(name):
+    name = name.split('(')[0].replace("void ", "").replace("lfb::", "")
+    return name.strip()
+
+
+def main(path, n_lc=None, json_out=None):
     rows = list(csv.reader(open(path)))
     hdr_i = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
     H = rows[hdr_i]
@@ -20,14 +45,16 @@ def main(path, n_lc=None):
         per.setdefault(r[iid], {"name": r[ik]})[r[im]] = float(r[iv].replace(',', ''))
     agg = OrderedDict()
     for d in per.values():
-        a = agg.setdefault(d["name"].split('(')[0], {"n": 0})
+        a = agg.setdefault(short(d["name"]), {"n": 0})
         a["n"] += 1
         for k, v in d.items():
             if k != "name":
                 a[k] = a.get(k, 0.0) + v
     tot_t = sum(a.get('gpu__time_duration.sum', 0) / a["n"] for a in agg.values())
-    print("%-34s %4s %10s %6s %12s %9s %7s" % ("kernel", "n", "time_us", "share", "fp64_flop", "TFLOP/s", "lanes"))
+    print("%-34s %4s %10s %6s %12s %9s %7s %10s" % ("kernel", "n", "time_us", "share", "fp64_flop", "TFLOP/s", "lanes",
+                                                     "dram_MB"))
     tot_f = 0.0
+    kern = OrderedDict()
     for name, a in agg.items():
         n = a["n"]
         t = a.get('gpu__time_duration.sum', 0) / n * 1e-3
@@ -36,12 +63,47 @@ def main(path, n_lc=None):
               + a.get('smsp__sass_thread_inst_executed_op_dmul_pred_on.sum', 0)) / n
         tot_f += fl
         lanes = a.get('smsp__thread_inst_executed_per_inst_executed.ratio', 0) / n
-        print("%-34s %4d %10.1f %5.1f%% %12.4g %9.2f %7.1f" % (name[:34], n, t, 100 * t * 1e3 / tot_t, fl,
-                                                              fl / (t * 1e-6) * 1e-12 if t else 0, lanes))
+        dram = (a.get('dram__bytes_read.sum', 0) + a.get('dram__bytes_write.sum', 0)) / n
+        smem_wf = a.get('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 0) / n
+        kern[name] = {"launches": n, "time_us": t, "fp64_flop": fl, "dram_bytes": dram, "smem_wavefronts": smem_wf,
+                      "lanes": lanes}
+        print("%-34s %4d %10.1f %5.1f%% %12.4g %9.2f %7.1f %10.2f" % (name[:34], n, t, 100 * t * 1e3 / tot_t, fl,
+                                                                      fl / (t * 1e-6) * 1e-12 if t else 0, lanes,
+                                                                      dram * 1e-6))
     print("sum of kernel times %.1f us, FP64 flop per pass %.4g" % (tot_t * 1e-3, tot_f))
     if n_lc:
         print("FP64 flop per light curve: %.4g" % (tot_f / n_lc))
+    if json_out and n_lc:
+        def grp(pred, key):
+            return sum(k[key] for nm, k in kern.items() if pred(nm)) / n_lc
+        out = {
+            "csrc_sha": csrc_sha(), "source": os.path.basename(path), "lightcurves_per_launch": n_lc,
+            "convention": "FMA = 2, DADD = DMUL = 1 (executed, predicated-on thread instructions); per light curve",
+            "per_lightcurve": {
+                "elements_flop": grp(lambda nm: nm.startswith("elements_kernel") or nm.startswith("stage1_kernel"), "fp64_flop"),
+                "flux_flop": grp(lambda nm: nm.startswith("flux_kernel"), "fp64_flop"),
+                "all_flop": tot_f / n_lc,
+                "elements_dram_bytes": grp(lambda nm: nm.startswith("elements_kernel") or nm.startswith("stage1_kernel"), "dram_bytes"),
+                "flux_dram_bytes": grp(lambda nm: nm.startswith("flux_kernel"), "dram_bytes"),
+                "flux_smem_wavefronts": grp(lambda nm: nm.startswith("flux_kernel"), "smem_wavefronts"),
+                "all_dram_bytes": sum(k["dram_bytes"] for k in kern.values()) / n_lc,
+            },
+            "kernels": {nm: {k: (v / n_lc if k in ("fp64_flop", "dram_bytes", "smem_wavefronts") else v)
+                             for k, v in d.items()} for nm, d in kern.items()},
+        }
+        with open(json_out, "w") as f:
+            json.dump(out, f, indent=1)
+        print("wrote", json_out)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else None)
+    args = [a for a in sys.argv[1:]]
+    jo = None
+    if "--json" in args:
+        i = args.index("--json")
+        jo = args[i + 1]
+        del args[i:i + 2]
+    if "--sha" in args:
+        print(csrc_sha())
+        sys.exit(0)
+    main(args[0], float(args[1]) if len(args) > 1 else None, jo)
