@@ -209,8 +209,9 @@ enum {
     LFB_K_ELEM_DISC,   /* elements_kernel<1> */
     LFB_K_ELEM_WD,     /* elements_kernel<0> */
     LFB_K_ELEM_DONOR,  /* elements_kernel<3> */
+    LFB_K_DONOR_TABLE, /* donor_table_kernel: the donor curve's phase table, per walker */
     LFB_K_PREP,        /* prep_kernel */
-    LFB_K_POSITIONS,   /* positions_kernel<0>: white dwarf, disc, donor */
+    LFB_K_POSITIONS,   /* positions_kernel<0>: white dwarf, disc */
     LFB_K_ELEM_BS,     /* elements_kernel<2>, with any wait for the stream ODE */
     LFB_K_PREP_BS,     /* prep_strip_kernel, positions_kernel<1>: the strip's share of the flux preparation */
     LFB_K_FLUX,        /* flux_kernel */

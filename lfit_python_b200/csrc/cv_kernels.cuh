@@ -19,11 +19,13 @@
 //                    bright spot per job): ingress/egress phases from the Roche LOS solve /
 //                    donor surface tiles -> HBM (16-32 B per element)
 //   prep_kernel      warp per job: component totals, fixed-point element weights, constants
-//   positions_kernel thread per element: the element's eclipse / facing interval as events on the
-//                    job's sorted exposure-sample axis (16 B record), donor moment parts
-//   flux_kernel      CTA per job, in segments of the axis: tile events -> shared-memory atomics ->
-//                    block scan; donor events -> counting sort -> block scan of five trigonometric
-//                    moments; then component mix, exposure quadrature and the chi-squared reduction
+//   positions_kernel thread per element: the element's eclipse interval as events on the job's sorted
+//                    exposure-sample axis (16 B record)
+//   donor_table_kernel  CTA per walker: the donor's facing intervals sorted in phase, the five
+//                    trigonometric moments of the facing tiles after every interval end
+//   flux_kernel      CTA per job, in segments of the axis: tile events -> native 32-bit shared-memory
+//                    atomics -> block scan; donor moments looked up in the walker's table; then
+//                    component mix, exposure quadrature and the chi-squared reduction
 //   gp_kernel        (lfb_set_gp) thread per job: Kalman-filter GP likelihood of the residuals
 //   finish_kernel    thread per walker: ln_prior - chi^2/2 with the -inf rules
 #pragma once
@@ -48,10 +50,13 @@ constexpr int kElemThreads = 128;
 constexpr int kElemBlocks = LFB_ELEM_BLOCKS;  // resident CTAs per SM the element kernels are compiled for
 constexpr int kMaxDonorRings = 128;
 constexpr int kMaxQuad = 15;
-constexpr int kNumArr = 8;  // event arrays: white dwarf, disc, bright spot, 5 donor moments
 constexpr int kNoEventPos = 0x7fffffff;
-constexpr double kFix = 72057594037927936.0;         // 2^56: fixed-point scale of normalised weights
-constexpr double kInvFix = 1.0 / 72057594037927936.0;
+// Fixed-point scale of the normalised tile weights: 2^46, added into shared memory as a 30-bit high and a 16-bit
+// low limb (native 32-bit atomics; up to 32767 events of one running sum may meet in one cell)
+constexpr double kFix = 70368744177664.0;
+constexpr double kInvFix = 1.0 / 70368744177664.0;
+constexpr int kLimbBits = 16;
+constexpr long long kLimbMask = 0xFFFF;
 
 struct DevLayout {
     int ndim, n_ecl, npars, n_prior;
@@ -76,6 +81,8 @@ struct DevSamples {
     const double2* gp_span;      // [n_ecl] smallest and largest raw phase
     const long long* chunk_off;  // [n_ecl + 1] offsets into chunks
     const int4* chunks;          // per segment: first point, one past last point, first sample, last sample
+    const double* seg_tr;        // per segment [3][RP][NT]: phase, cos, sin of its samples in the flux kernel's
+                                 // thread-major order (sample t * RP + r of the segment at [r][t])
 };
 
 struct GridCfg {
@@ -384,7 +391,7 @@ __global__ void __launch_bounds__(kElemThreads, kElemBlocks) elements_kernel(con
     }
 }
 
-// ---------------------------------------------------------------- flux stage: prep / positions / flux
+// ---------------------------------------------------------------- flux stage: prep / positions / donor table / flux
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -412,10 +419,22 @@ constexpr int kAtStart = -1;          // event position: before the first sample
 
 // Per-job constants of the flux stage (written by prep_kernel)
 struct JobConst {
-    double f_wd, f_d, f_s, f_rs;        // flux scale of each component's running sum
+    double f_wd, f_d, f_s, f_rs;        // flux scale of each component
+    double F01;                         // |f_wd| + |f_d|: scale of the merged white-dwarf + disc running sum (chi-squared mode)
     double beam_a, beam_b, beam_d, fis; // bright-spot beaming: fis + (1-fis) max(0, a c + b s + d)
     double cphi, sphi, phi0w;           // phase offset wrapped to [-0.5, 0.5]
-    double don_sc;                      // 2^56 / sum of donor tile weights
+};
+
+// A walker's donor curve as a table over orbital phase (donor_table_kernel): every tile image faces the observer
+// on one phase interval, so the five trigonometric moments of the facing tiles are piecewise constant; the table
+// holds the sorted break points and the moments between them.
+struct DonorTable {
+    unsigned short* first;  // [n][kDonorBins + 1] break points in the phase bins before bin g
+    double* key;            // [n][nb_max]         sorted break points (an opening one is nudged up by one ulp:
+                            //                     break point k applies to phase x iff key[k] <= x)
+    double* mom;            // [n][nb_max + 1][6]  moments (1, c, s, c^2, c s; one pad) after k break points, normalised
+                            //                     "at maximum light" (quadrature)
+    int nb_max;             // 8 n_donor_q
 };
 
 struct FluxArgs {
@@ -423,8 +442,7 @@ struct FluxArgs {
     GridCfg G;
     DevSamples smp;
     int what, flags, mode;  // mode 0: chi-squared, 1: flux curves
-    int Ms;                 // capacity of a segment of the sample axis in samples
-    int ni_total;           // event records per job: n_wd + n_disc + n_bs + 4 n_donor_q
+    int ni_total;           // event records per job: n_wd + n_disc + n_bs
     long long njobs;
     const double* theta;
     const WalkerScal* ws;
@@ -436,8 +454,8 @@ struct FluxArgs {
     const double* bs_b;
     JobConst* jc;           // [njobs]
     long long* wq;          // [njobs][n_wd_rings + n_disc_r + n_bs] fixed-point element weights
-    long long* qmom;        // [njobs][n_donor_q][8] fixed-point donor moment parts of each quarter tile
-    ulonglong2* ivp;        // [njobs][ni_total] event records (EventRec) of every eclipse / facing interval
+    ulonglong2* ivp;        // [njobs][ni_total] event records (EventRec) of every eclipse interval
+    DonorTable dt;
     double* chisq_job;      // [njobs] chi-squared of each job (NaN: not evaluated)
     double* flux_tot;       // mode 1: [njobs][n_ph]
     double* flux_comp;      // mode 1 (optional): [4][njobs][n_ph]
@@ -457,7 +475,8 @@ __device__ __forceinline__ bool job_live(const FluxArgs& A, const WalkerScal& W,
 }
 
 // prep_kernel: one warp per job.  Component totals ("flux at maximum light", README.md:24-28),
-// fixed-point (2^-56) element weights, beaming and phase-offset constants.
+// fixed-point (2^-46) element weights, beaming and phase-offset constants.  In chi-squared mode the white
+// dwarf and the disc share one running sum: their weights carry f_wd / F01 and f_d / F01.
 __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FluxArgs A)
 {
     const GridCfg& G = A.G;
@@ -477,6 +496,11 @@ __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FluxA
     const double si = W.si, ci = W.ci, xl1 = W.R.xl1;
     const double rwd_a = par(P_RWD, 0.0) * xl1, rdisc_a = par(P_RDISC, 0.0) * xl1;
     const double ulimb = par(P_ULIMB, 0.0), dexp = par(P_DEXP, 0.0);
+    const double f_wd = do_wd ? par(P_WDFLUX, 0.0) : 0.0, f_d = do_disc ? par(P_DFLUX, 0.0) : 0.0;
+    const double F01 = fabs(f_wd) + fabs(f_d);
+    // weight of a white-dwarf / disc tile relative to its own component (flux-curve mode) or to both (chi-squared mode)
+    const double s_wd = A.mode ? (do_wd ? 1.0 : 0.0) : (F01 > 0.0 ? f_wd / F01 : 0.0);
+    const double s_d = A.mode ? (do_disc ? 1.0 : 0.0) : (F01 > 0.0 ? f_d / F01 : 0.0);
     long long* wq_wd = A.wq + job * (G.n_wd_rings + G.n_disc_r + G.n_bs);
     long long* wq_disc = wq_wd + G.n_wd_rings;
     // white dwarf rings: equal-area tiles, weight (1 - u) + u <mu>_ring
@@ -492,7 +516,7 @@ __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FluxA
         double inv = 1.0 / G.n_wd_rings, ra = k * inv, rb = (k + 1) * inv;
         double ua = 1.0 - ra * ra, ub = 1.0 - rb * rb;
         double mubar = (2.0 / 3.0) * (ua * sqrt(ua) - ub * sqrt(ub)) / (rb * rb - ra * ra);
-        wq_wd[k] = do_wd ? llrint(((1.0 - ulimb) + ulimb * mubar) / tot_wd * kFix) : 0;
+        wq_wd[k] = llrint(((1.0 - ulimb) + ulimb * mubar) / tot_wd * (s_wd * kFix));
     }
     // disc rings: brightness r^-dexp times area ~ r
     p = 0.0;
@@ -503,24 +527,10 @@ __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FluxA
     const double tot_d = warp_sum(p);
     for (int m = lane; m < G.n_disc_r; m += 32) {
         double r = rwd_a + (m + 0.5) * (rdisc_a - rwd_a) / G.n_disc_r;
-        wq_disc[m] = do_disc ? llrint(pow(r, 1.0 - dexp) / tot_d * kFix) : 0;
+        wq_disc[m] = llrint(pow(r, 1.0 - dexp) / tot_d * (s_d * kFix));
     }
-    // (the bright-spot strip's weights wait for the strip itself: prep_strip_kernel)
-    // donor: normalised at quadrature (phase 0.25: c = 0, s = 1)
-    const double4* don = A.don + w * G.n_donor_q;
-    const double ud = G.donor_ulimb;
-    double p_rs = 0.0, p_rw = 0.0;
-    if (do_don)
-        for (int t = lane; t < G.n_donor_q; t += 32) {
-            double4 q = don[t];
-            double b = si * q.y, d = ci * q.z, m;
-            m = -b + d; if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
-            m = b + d;  if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
-            m = -b - d; if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
-            m = b - d;  if (m > 0.0) p_rs += q.w * m * (1.0 - ud + ud * m);
-            p_rw += 4.0 * q.w;
-        }
-    const double tot_rs = warp_sum(p_rs), tot_rw = warp_sum(p_rw);
+    // (the bright-spot strip's weights wait for the strip itself: prep_strip_kernel; the donor's normalisation
+    // is in its table: donor_table_kernel)
     if (lane == 0) {
         JobConst C;
         // beamed part of the spot: polar angle tilt from +z, azimuth az - 90 + yaw
@@ -534,15 +544,15 @@ __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FluxA
         C.fis = fis;
         double cmax = si * st + ci * ct;  // cos(i - tilt): best alignment over an orbit
         double beam_norm = fis + (1.0 - fis) * (cmax > 0.0 ? cmax : 0.0);
-        C.f_wd = do_wd ? par(P_WDFLUX, 0.0) : 0.0;
-        C.f_d = do_disc ? par(P_DFLUX, 0.0) : 0.0;
+        C.f_wd = f_wd;
+        C.f_d = f_d;
+        C.F01 = F01;
         C.f_s = (do_bs && beam_norm > 0.0) ? par(P_SFLUX, 0.0) / beam_norm : 0.0;  // 0 if the strip is dark: prep_strip_kernel
-        C.f_rs = do_don ? par(P_RSFLUX, 0.0) / tot_rs * (tot_rw * kInvFix) : 0.0;
+        C.f_rs = do_don ? par(P_RSFLUX, 0.0) : 0.0;
         double phi0w = par(P_PHI0, 0.0);
         phi0w -= rint(phi0w);
         C.phi0w = phi0w;
         sincos_(kTwoPi * phi0w, &C.sphi, &C.cphi);
-        C.don_sc = do_don ? kFix / tot_rw : 0.0;
         A.jc[job] = C;
     }
 }
@@ -685,14 +695,14 @@ __global__ void __launch_bounds__(128) prep_strip_kernel(const __grid_constant__
     if (lane == 0 && !(tot_s > 0.0)) A.jc[job].f_s = 0.0;
 }
 
-// positions_kernel: one thread per solved element (or donor quarter tile) of a job: where on the
-// job's sorted sample axis its eclipse (facing) intervals open and close.
-// PART 0: white dwarf, disc and donor (nothing here needs the stream ODE); PART 1: the bright-spot strip.
+// positions_kernel: one thread per solved element of a job: where on the job's sorted sample axis its
+// eclipse intervals open and close.
+// PART 0: white dwarf and disc (nothing here needs the stream ODE); PART 1: the bright-spot strip.
 template <int PART>
 __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ FluxArgs A)
 {
     const GridCfg& G = A.G;
-    const int per_job = PART == 0 ? G.n_wd_half + G.n_disc_half + G.n_donor_q : G.n_bs;
+    const int per_job = PART == 0 ? G.n_wd_half + G.n_disc_half : G.n_bs;
     const int padded = (per_job + 31) & ~31;  // a warp never straddles two jobs
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long job = gid / padded;
@@ -708,77 +718,38 @@ __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ 
         const SampleAxis X = sample_axis(A.smp, e, G.n_quad);
         const double phi0w = A.jc[job].phi0w;
         EventRec* ivp = A.ivp + job * A.ni_total;
-        const int n_half = G.n_wd_half + G.n_disc_half;
         const EventRec none = no_events();
-        if (PART == 1 || t < n_half) {
-            double2 io;
-            int i0;
-            bool on, mirror = PART == 0;
-            if (PART == 1) {
-                on = !(A.flags & LFB_FLAG_SKIP_BS);
-                io = on ? A.bs_io[job * G.n_bs + t] : make_double2(kBig, -kBig);
-                i0 = G.n_wd + G.n_disc + t;
-            } else if (t < G.n_wd_half) {
-                on = !(A.flags & LFB_FLAG_SKIP_WD);
-                io = on ? A.wd_io[w * G.n_wd_half + t] : make_double2(kBig, -kBig);
-                i0 = 2 * t;
-            } else {
-                int h = t - G.n_wd_half;
-                on = !(A.flags & LFB_FLAG_SKIP_DISC);
-                io = on ? A.disc_io[job * G.n_disc_half + h] : make_double2(kBig, -kBig);
-                i0 = G.n_wd + 2 * h;
-            }
-            const bool ecl = io.y > io.x;
-            const EventRec r0 = ecl ? interval_pieces(X, io.x + phi0w, io.y + phi0w) : none;
-            ivp[__ldg(G.rec_slot + i0)] = r0;
-            lo = dec_pos(r0.x, 0);
-            hi = rec_last_close(r0);
-            // the y -> -y image is eclipsed from -egress to -ingress
-            if (mirror) {
-                const EventRec r1 = ecl ? interval_pieces(X, -io.y + phi0w, -io.x + phi0w) : none;
-                ivp[__ldg(G.rec_slot + i0 + 1)] = r1;
-                lo = min(lo, dec_pos(r1.x, 0));
-                hi = max(hi, rec_last_close(r1));
-            }
+        double2 io;
+        int i0;
+        bool on, mirror = PART == 0;
+        if (PART == 1) {
+            on = !(A.flags & LFB_FLAG_SKIP_BS);
+            io = on ? A.bs_io[job * G.n_bs + t] : make_double2(kBig, -kBig);
+            i0 = G.n_wd + G.n_disc + t;
+        } else if (t < G.n_wd_half) {
+            on = !(A.flags & LFB_FLAG_SKIP_WD);
+            io = on ? A.wd_io[w * G.n_wd_half + t] : make_double2(kBig, -kBig);
+            i0 = 2 * t;
         } else {
-            // donor: every tile image faces the observer for |phase - centre| < half width
-            const int h = t - n_half;
-            const bool on = !(A.flags & LFB_FLAG_SKIP_DONOR);
-            double4 q = on ? A.don[w * G.n_donor_q + h] : make_double4(1.0, 0.0, 0.0, 0.0);
-            double Aq = W.si * q.x, Bq = -W.si * q.y, Dq = W.ci * q.z;
-            double rho = sqrt(Aq * Aq + Bq * Bq);
-            double psi = atan2(Bq, Aq) * (1.0 / kTwoPi);
-            double ratio = rho > 0.0 ? Dq / rho : (Dq > 0.0 ? 2.0 : -2.0);
-            // image with +D faces the observer iff cos(th - psi) > -D/rho
-            double hp = ratio >= 1.0 ? 0.5 : (ratio <= -1.0 ? -1.0 : acos(-ratio) * (1.0 / kTwoPi));
-            double hm = ratio <= -1.0 ? 0.5 : (ratio >= 1.0 ? -1.0 : acos(ratio) * (1.0 / kTwoPi));
-            // W m (1 - u + u m), m = A c + B s + D, as moments of (1, c, s, c^2, c s): the four mirror
-            // images differ by the signs of B and D, so eight integers serve all of them
-            {
-                const double ud = G.donor_ulimb, sc = on ? q.w * A.jc[job].don_sc : 0.0;
-                const double Bp = W.si * q.y;
-                long long* m = A.qmom + (job * G.n_donor_q + h) * 8;
-                m[0] = llrint(sc * ud * (Dq * Dq + Bp * Bp));
-                m[1] = llrint(sc * (1.0 - ud) * Dq);
-                m[2] = llrint(sc * (1.0 - ud) * Aq);
-                m[3] = llrint(sc * 2.0 * ud * Aq * Dq);
-                m[4] = llrint(sc * (1.0 - ud) * Bp);
-                m[5] = llrint(sc * 2.0 * ud * Bp * Dq);
-                m[6] = llrint(sc * ud * (Aq * Aq - Bp * Bp));
-                m[7] = llrint(sc * 2.0 * ud * Aq * Bp);
-            }
-            EventRec* dnp = ivp + G.n_wd + G.n_disc + G.n_bs + 4 * h;
-#pragma unroll
-            for (int im = 0; im < 4; ++im) {
-                double cen = ((im & 1) ? -psi : psi) + phi0w, hw = (im & 2) ? hm : hp;
-                EventRec p = none;
-                if (on && hw >= 0.5) p.x = (p.x & ~(unsigned long long)kFieldNone) | enc_pos(kAtStart);  // always faces the observer
-                else if (on && hw >= 0.0) p = interval_pieces(X, cen - hw, cen + hw);
-                dnp[im] = p;
-            }
+            int h = t - G.n_wd_half;
+            on = !(A.flags & LFB_FLAG_SKIP_DISC);
+            io = on ? A.disc_io[job * G.n_disc_half + h] : make_double2(kBig, -kBig);
+            i0 = G.n_wd + 2 * h;
+        }
+        const bool ecl = io.y > io.x;
+        const EventRec r0 = ecl ? interval_pieces(X, io.x + phi0w, io.y + phi0w) : none;
+        ivp[__ldg(G.rec_slot + i0)] = r0;
+        lo = dec_pos(r0.x, 0);
+        hi = rec_last_close(r0);
+        // the y -> -y image is eclipsed from -egress to -ingress
+        if (mirror) {
+            const EventRec r1 = ecl ? interval_pieces(X, -io.y + phi0w, -io.x + phi0w) : none;
+            ivp[__ldg(G.rec_slot + i0 + 1)] = r1;
+            lo = min(lo, dec_pos(r1.x, 0));
+            hi = max(hi, rec_last_close(r1));
         }
     }
-    // span of the job's eclipse events (lets chunks far from the eclipse skip the tile records)
+    // span of the job's eclipse events (lets segments far from the eclipse skip the tile records)
     lo = __reduce_min_sync(0xffffffffu, lo);
     hi = __reduce_max_sync(0xffffffffu, hi);
     if ((threadIdx.x & 31) == 0 && lo != kNoEvent) {
@@ -787,48 +758,283 @@ __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ 
     }
 }
 
-// flux_kernel: one CTA per job -- stages (2)-(4) of the model, one pass over the job's sorted
-// exposure-sample axis in segments of at most Ms samples.
-//
-// Every eclipse / facing interval is a few events (+w where it opens, -w where it closes) on the
-// axis and the component curves are running sums of those events (2^-56 fixed point, so sums do
-// not depend on the order the events arrive in).  Per segment:
-//   * white-dwarf, disc and strip events are dense around the eclipse: shared-memory atomics add
-//     them into three per-sample delta arrays, a block scan turns the deltas into running sums;
-//   * donor events are sparse (one per ~5 samples): they are counting-sorted by sample, their
-//     moment contributions block-scanned in event order, and the running sums kept per event;
-//   * every sample then reads its three tile sums and the donor sums of the last event at or
-//     before it, evaluates the four components, and the exposure quadrature, residuals and a
-//     warp-shuffle + shared-memory chi-squared reduction follow.
-template <int Ms, int EC, int CTAS>
-__global__ void __launch_bounds__(kFluxThreads, CTAS) flux_kernel(const __grid_constant__ FluxArgs A)
+// donor_table_kernel: one CTA per walker.  Tile image im of quarter tile t shows the observer the projected
+// area W mu (1 - u + u mu), mu = A c + B s + D (c, s: cos, sin of the orbital angle), while mu > 0, i.e. on the
+// phase interval |phase - centre| < half width.  The donor curve is therefore
+//     yrs(phase) = m0 + m1 c + m2 s + m3 c^2 + m4 c s,   (m0..m4) = sum over the facing images,
+// with moments that change only at the 2 x 4 x n_donor_q interval ends.  The kernel sorts the ends in phase
+// (counting sort into kDonorBins uniform bins, then each short bin by insertion; ties by image, so the order is
+// unique and the double-precision running sums below are reproducible) and stores the moments after every end,
+// normalised "at maximum light" (quadrature, phase 0.25).  The table depends on (q, inclination) only: every
+// eclipse of the walker reads it, through its own phase offset.
+constexpr int kDonorThreads = 128;
+constexpr int kDonorBins = 1024;
+
+__host__ __device__ __forceinline__ int donor_bin(double phase)
 {
-    extern __shared__ __align__(16) unsigned char smraw[];
+    const double f = (phase + 0.5) * (double)kDonorBins;
+    return f <= 0.0 ? 0 : (f >= (double)(kDonorBins - 1) ? kDonorBins - 1 : (int)f);
+}
+
+// moments (1, c, s, c^2, c s) of image im (bit 0: sign of B, bit 1: sign of D) from the eight parts of its quarter tile
+__device__ __forceinline__ void donor_image_moments(const double* m, int im, double sgn, double* acc)
+{
+    const double sb = (im & 1) ? sgn : -sgn, sd = (im & 2) ? -1.0 : 1.0;
+    acc[0] += sgn * (m[0] + sd * m[1]);
+    acc[1] += sgn * (m[2] + sd * m[3]);
+    acc[2] += sb * (m[4] + sd * m[5]);
+    acc[3] += sgn * m[6];
+    acc[4] += sb * m[7];
+}
+
+__global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __grid_constant__ FluxArgs A)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
     const GridCfg& G = A.G;
-    constexpr int NW = kFluxThreads / 32;
-    constexpr int RP = Ms / kFluxThreads;  // samples per thread in the block scans
-    constexpr int EP = EC / kFluxThreads;  // donor events per thread (EC = events whose running sums fit at once)
-    constexpr int ND = kNumArr - 3;        // donor moment arrays
-    static_assert(Ms % kFluxThreads == 0 && EC % kFluxThreads == 0, "capacities: multiples of the block size");
+    const int NDQ = G.n_donor_q, NB = 8 * NDQ;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int nF = A.mode ? 4 : 1;
-    const int NDQ = G.n_donor_q;
-    long long* qmom = (long long*)smraw;                              // [NDQ][8] donor moment parts of a quarter tile
-    unsigned long long* Dt = (unsigned long long*)(qmom + 8 * NDQ);  // [3][Ms] tile deltas, then running sums (f64),
-    double* Dsum = (double*)Dt;                                       // then, sample by sample, ...
-    double* Fs = Dsum;                                                // [nF][Ms] flux per sample of the segment
-    double* P = Dsum + (size_t)(nF > 3 ? nF : 3) * Ms;                // [ND][EC] donor running sums after each event
-    int* S = (int*)(P + ND * EC);                                     // [Ms + 1] donor events per sample -> bucket ends
-    unsigned short* ev = (unsigned short*)(S + Ms + 1);               // [6 * 4 NDQ] donor events sorted by sample
-    __shared__ double red[NW];
-    __shared__ long long wtot[kNumArr][NW];
-    __shared__ long long s_carry[kNumArr], s_next[kNumArr];
+    constexpr int NW = kDonorThreads / 32;
+    double* qm = (double*)dsm;                         // [NDQ][8] moment parts of a quarter tile
+    double* ukey = qm + 8 * NDQ;                       // [NB] break points as found (+inf: none)
+    double* skey = ukey + NB;                          // [NB] sorted
+    int* cnt = (int*)(skey + NB);                      // [kDonorBins + 1]
+    unsigned short* uid = (unsigned short*)(cnt + kDonorBins + 1);  // [NB] image << 1 | (0: opens, 1: closes)
+    unsigned short* sid = uid + NB;                    // [NB] sorted
+    __shared__ double red[6][NW];
+    __shared__ double s_base[6];
     __shared__ int s_itot[NW];
+    const long long w = blockIdx.x;
+    const WalkerScal& W = A.ws[w];
+    if (W.status != 0 || (A.what != LFB_LN_LIKE && !(W.lnprior > -INFINITY))) return;
+    const double ud = G.donor_ulimb;
+    for (int q = tid; q < kDonorBins + 1; q += kDonorThreads) cnt[q] = 0;
+    // ---- 1. intervals of the four images of every quarter tile ----
+    double base[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // moments of the images facing at phase -0.5; [5]: normalisation
+    for (int t = tid; t < NDQ; t += kDonorThreads) {
+        const double4 q = A.don[w * NDQ + t];
+        const double Aq = W.si * q.x, Bq = -W.si * q.y, Dq = W.ci * q.z, Bp = W.si * q.y;
+        const double rho = sqrt(Aq * Aq + Bq * Bq);
+        const double psi = atan2(Bq, Aq) * (1.0 / kTwoPi);
+        const double ratio = rho > 0.0 ? Dq / rho : (Dq > 0.0 ? 2.0 : -2.0);
+        // image with +D faces the observer iff cos(th - psi) > -D/rho
+        const double hp = ratio >= 1.0 ? 0.5 : (ratio <= -1.0 ? -1.0 : acos(-ratio) * (1.0 / kTwoPi));
+        const double hm = ratio <= -1.0 ? 0.5 : (ratio >= 1.0 ? -1.0 : acos(ratio) * (1.0 / kTwoPi));
+        double* m = qm + 8 * t;
+        m[0] = q.w * ud * (Dq * Dq + Bp * Bp);
+        m[1] = q.w * (1.0 - ud) * Dq;
+        m[2] = q.w * (1.0 - ud) * Aq;
+        m[3] = q.w * 2.0 * ud * Aq * Dq;
+        m[4] = q.w * (1.0 - ud) * Bp;
+        m[5] = q.w * 2.0 * ud * Bp * Dq;
+        m[6] = q.w * ud * (Aq * Aq - Bp * Bp);
+        m[7] = q.w * 2.0 * ud * Aq * Bp;
+        // normalisation: the curve at quadrature (phase 0.25: c = 0, s = 1)
+        {
+            const double b = W.si * q.y, d = W.ci * q.z;
+            double mu;
+            mu = -b + d; if (mu > 0.0) base[5] += q.w * mu * (1.0 - ud + ud * mu);
+            mu = b + d;  if (mu > 0.0) base[5] += q.w * mu * (1.0 - ud + ud * mu);
+            mu = -b - d; if (mu > 0.0) base[5] += q.w * mu * (1.0 - ud + ud * mu);
+            mu = b - d;  if (mu > 0.0) base[5] += q.w * mu * (1.0 - ud + ud * mu);
+        }
+#pragma unroll
+        for (int im = 0; im < 4; ++im) {
+            const double cen = (im & 1) ? -psi : psi, hw = (im & 2) ? hm : hp;
+            double ko = INFINITY, kc = INFINITY;
+            if (hw >= 0.5) {
+                donor_image_moments(m, im, 1.0, base);  // always faces the observer
+            } else if (hw > 0.0) {
+                double o = cen - hw, c2 = cen + hw;
+                o -= rint(o);
+                c2 -= rint(c2);
+                if (o >= 0.5) o -= 1.0;
+                if (c2 >= 0.5) c2 -= 1.0;
+                if (o > c2) donor_image_moments(m, im, 1.0, base);  // the interval holds phase -0.5: facing at the start
+                if (o != c2) {
+                    ko = nextafter(o, 1.0);  // opens just after o: applies to phase x iff o < x
+                    kc = c2;                 // closed from c2 on:  applies iff c2 <= x
+                }
+            }
+            const int slot = 2 * (4 * t + im);
+            ukey[slot] = ko;
+            ukey[slot + 1] = kc;
+            uid[slot] = (unsigned short)((4 * t + im) << 1);
+            uid[slot + 1] = (unsigned short)(((4 * t + im) << 1) | 1);
+        }
+    }
+    // base moments and the normalisation: fixed-order sums over the CTA
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        const double v = warp_sum(base[a]);
+        if (lane == 0) red[a][wid] = v;
+    }
+    __syncthreads();
+    if (tid < 6) {
+        double v = 0.0;
+        for (int i = 0; i < NW; ++i) v += red[tid][i];
+        s_base[tid] = v;
+    }
+    // ---- 2. counting sort by phase bin ----
+    for (int i = tid; i < NB; i += kDonorThreads) {
+        const double k = ukey[i];
+        if (k < 1e300) atomicAdd(&cnt[donor_bin(k) + 1], 1);
+    }
+    __syncthreads();
+    {
+        // exclusive scan of the bin counts: cnt[g + 1] <- break points in bins 0..g; every thread owns a run of bins
+        constexpr int RB = kDonorBins / kDonorThreads;
+        int c[RB], tot = 0;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            c[r] = cnt[1 + tid * RB + r];
+            tot += c[r];
+        }
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_itot[wid] = inc;
+        __syncthreads();
+        int run = inc - tot;
+        for (int i = 0; i < wid; ++i) run += s_itot[i];
+        unsigned short* first = A.dt.first + w * (kDonorBins + 1);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            first[tid * RB + r] = (unsigned short)run;  // break points in the bins before this one
+            cnt[1 + tid * RB + r] = run;                // fill cursor of the bin
+            run += c[r];
+        }
+        if (tid == kDonorThreads - 1) {
+            first[kDonorBins] = (unsigned short)run;
+            cnt[0] = run;  // the number of break points
+        }
+    }
+    __syncthreads();
+    const int nb = cnt[0];
+    __syncthreads();
+    for (int i = tid; i < NB; i += kDonorThreads) {
+        const double k = ukey[i];
+        if (k < 1e300) {
+            const int at = atomicAdd(&cnt[donor_bin(k) + 1], 1);
+            skey[at] = k;
+            sid[at] = uid[i];
+        }
+    }
+    __syncthreads();
+    // afterwards cnt[g + 1] = end of bin g; its start is the end of bin g - 1 (0 for bin 0): sort every bin
+    for (int g = tid; g < kDonorBins; g += kDonorThreads) {
+        const int b0 = g == 0 ? 0 : cnt[g], b1 = cnt[g + 1];
+        for (int i = b0 + 1; i < b1; ++i) {
+            const double k = skey[i];
+            const unsigned short id = sid[i];
+            int j = i - 1;
+            while (j >= b0 && (skey[j] > k || (skey[j] == k && sid[j] > id))) {
+                skey[j + 1] = skey[j];
+                sid[j + 1] = sid[j];
+                --j;
+            }
+            skey[j + 1] = k;
+            sid[j + 1] = id;
+        }
+    }
+    __syncthreads();
+    // ---- 3. moments after every break point: block scan in sorted order ----
+    const double inv_norm = 1.0 / s_base[5];
+    double* key_out = A.dt.key + w * A.dt.nb_max;
+    double* mom_out = A.dt.mom + w * (A.dt.nb_max + 1) * 6;
+    if (tid < 6) mom_out[tid] = tid < 5 ? s_base[tid] * inv_norm : 0.0;
+    double carry[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) carry[a] = s_base[a];
+    constexpr int EP = 8;  // break points per thread and round
+    for (int r0 = 0; r0 < nb; r0 += EP * kDonorThreads) {
+        // every thread owns EP consecutive break points: their sum first, the running sums in a second sweep
+        double tot[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+        for (int q = 0; q < EP; ++q) {
+            const int x = r0 + tid * EP + q;
+            if (x < nb) {
+                const int id = sid[x];
+                donor_image_moments(qm + 8 * (id >> 3), (id >> 1) & 3, (id & 1) ? -1.0 : 1.0, tot);
+            }
+        }
+        double run[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            double v = tot[a];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += u;
+            }
+            run[a] = v - tot[a];  // sum of the lanes before this one
+            if (lane == 31) red[a][wid] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            double before = carry[a], all = carry[a];
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                if (i < wid) before += red[a][i];
+                all += red[a][i];
+            }
+            run[a] += before;
+            carry[a] = all;
+        }
+#pragma unroll 1
+        for (int q = 0; q < EP; ++q) {
+            const int x = r0 + tid * EP + q;
+            if (x < nb) {
+                const int id = sid[x];
+                donor_image_moments(qm + 8 * (id >> 3), (id >> 1) & 3, (id & 1) ? -1.0 : 1.0, run);
+                key_out[x] = skey[x];
+                double2* row = (double2*)(mom_out + (size_t)(x + 1) * 6);
+                row[0] = make_double2(run[0] * inv_norm, run[1] * inv_norm);
+                row[1] = make_double2(run[2] * inv_norm, run[3] * inv_norm);
+                row[2] = make_double2(run[4] * inv_norm, 0.0);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// flux_kernel: one CTA per job -- stages (2)-(4) of the model, one pass over the job's sorted
+// exposure-sample axis in segments of at most Ms = NT * RP samples.
+//
+// Every eclipse interval of a tile is a few events (+w where it opens, -w where it closes) on the axis and the
+// component curves are running sums of those events.  Weights are 2^-46 fixed point, split in a high and a 16-bit
+// low limb, so that the events add into 32-bit shared-memory cells with native atomics and the sums do not depend
+// on the order the events arrive in.  Per segment:
+//   1. the cells are cleared; every tile record adds its events (chi-squared mode: white dwarf and disc share one
+//      sum, their weights carry the component fluxes; flux-curve mode: three sums);
+//   2. a block scan turns the cells into running sums: every thread owns RP consecutive samples, reads their
+//      phase, cos and sin (stored per segment in thread-major order: coalesced), looks the donor moments up in the
+//      walker's phase table (walking along it: consecutive samples mostly share a table row), evaluates the
+//      components and leaves the flux in the sample's cell;
+//   3. exposure quadrature, residuals, and the warp-shuffle + shared-memory chi-squared reduction.
+// MODE 0: chi-squared (16 B cell per sample); MODE 1: the four component curves (32 B cell).
+template <int MODE, int NT, int RP, int CTAS>
+__global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ FluxArgs A)
+{
+    extern __shared__ __align__(16) int cells[];  // [Ms][CW]: limbs (hi, lo) of every running sum, then the flux
+    const GridCfg& G = A.G;
+    constexpr int Ms = NT * RP;
+    constexpr int NW = NT / 32;
+    constexpr int NA = MODE ? 3 : 2;  // running sums of tile events
+    constexpr int CW = MODE ? 8 : 4;  // 32-bit words of a cell
+    constexpr int NF = MODE ? 4 : 1;  // flux values left in a cell
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ double red[NW];
+    __shared__ long long wtot[NA][NW];
+    __shared__ long long s_carry[NA], s_next[NA];
 
     const long long job = blockIdx.x;
     const long long w = job / A.L.n_ecl;
     const int egather = (int)(job - w * A.L.n_ecl);
-    const int e = A.mode ? 0 : egather;
+    const int e = MODE ? 0 : egather;
     const long long ch0 = A.smp.chunk_off[e];
     const int n_seg = (int)(A.smp.chunk_off[e + 1] - ch0);
     const long long lc0 = A.smp.lc_off[e];
@@ -838,10 +1044,10 @@ __global__ void __launch_bounds__(kFluxThreads, CTAS) flux_kernel(const __grid_c
     const JobScal& J = A.js[job];
     if (!job_live(A, W, J)) {
         const bool skipped = J.status == 4 || J.status == 0;
-        if (A.mode == 0) {
+        if (MODE == 0) {
             if (tid == 0) A.chisq_job[job] = skipped ? NAN : INFINITY;
         } else {
-            for (int j = tid; j < n_ph; j += kFluxThreads) {
+            for (int j = tid; j < n_ph; j += NT) {
                 A.flux_tot[job * n_ph + j] = NAN;
                 if (A.flux_comp)
                     for (int cidx = 0; cidx < 4; ++cidx) A.flux_comp[((long long)cidx * A.njobs + job) * n_ph + j] = NAN;
@@ -852,37 +1058,14 @@ __global__ void __launch_bounds__(kFluxThreads, CTAS) flux_kernel(const __grid_c
     const JobConst C = A.jc[job];
     const long long* wq_tab = A.wq + job * (G.n_wd_rings + G.n_disc_r + G.n_bs);
     const EventRec* ivp = A.ivp + job * A.ni_total;
-    const int n_tile_iv = G.n_wd + G.n_disc + G.n_bs;
-    const EventRec* dnp = ivp + n_tile_iv;
-    const bool do_don = !(A.flags & LFB_FLAG_SKIP_DONOR);
-    const int n_img = do_don ? 4 * NDQ : 0;
-
-    if (do_don) {
-        const longlong2* src = (const longlong2*)(A.qmom + job * NDQ * 8);
-        for (int i = tid; i < 4 * NDQ; i += kFluxThreads) ((longlong2*)qmom)[i] = __ldg(src + i);
-    }
-    // moments (1, c, s, c^2, c s) of donor tile image im: the mirror images of a quarter tile differ by the
-    // signs of B (bit 0 set: +) and D (bit 1 set: -)
-    auto add_image = [&](int im, long long sgn, long long* acc) {
-        const long long* m = qmom + 8 * (im >> 2);
-        const long long sb = (im & 1) ? sgn : -sgn, sd = (im & 2) ? -1 : 1;
-        acc[0] += sgn * (m[0] + sd * m[1]);
-        acc[1] += sgn * (m[2] + sd * m[3]);
-        acc[2] += sb * (m[4] + sd * m[5]);
-        acc[3] += sgn * m[6];
-        acc[4] += sb * m[7];
-    };
-    // inclusive warp scan of a 64-bit value
-    auto warp_incl = [&](long long v) {
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long u = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += u;
-        }
-        return v;
-    };
+    const int n_tile_iv = A.ni_total;
+    const bool do_don = C.f_rs != 0.0;
+    // the walker's donor table
+    const unsigned short* __restrict__ dfirst = A.dt.first + w * (kDonorBins + 1);
+    const double* __restrict__ dkey = A.dt.key + w * A.dt.nb_max;
+    const double* __restrict__ dmom = A.dt.mom + w * (A.dt.nb_max + 1) * 6;
+    const int nb = do_don ? (int)__ldg(dfirst + kDonorBins) : 0;
     double chi = 0.0;
-    __syncthreads();
 
     for (int seg = 0; seg < n_seg; ++seg) {
         const int4 ch = __ldg(A.smp.chunks + ch0 + seg);  // first point, one past last point, first sample, last sample
@@ -892,252 +1075,215 @@ __global__ void __launch_bounds__(kFluxThreads, CTAS) flux_kernel(const __grid_c
         // 1 <= m0n <= len); its running sums start from those after sample m0n - 1
         const int m0n = seg + 1 < n_seg ? __ldg(&A.smp.chunks[ch0 + seg + 1].z) - m0 : -1;
 
-        // ---- 1. events of the segment: tile deltas, donor counts, sums already open at sample 0 ----
-        if (tiles_matter)
-            for (int q = tid; q < 3 * Ms; q += kFluxThreads) Dt[q] = 0ull;
-        for (int q = tid; q < Ms + 1; q += kFluxThreads) S[q] = 0;
+        // ---- 1. events of the segment into the cells; sums already open at sample 0 ----
+        if (tiles_matter) {
+            int4* c4 = (int4*)cells;
+            for (int q = tid; q < Ms * CW / 4; q += NT) c4[q] = make_int4(0, 0, 0, 0);
+        }
         __syncthreads();
-        long long base[kNumArr];
+        if (tiles_matter || seg == 0) {
+            long long base[NA];
 #pragma unroll
-        for (int a = 0; a < kNumArr; ++a) base[a] = 0;
-        if (tiles_matter || seg == 0)
-            for (int i0 = tid; i0 < n_tile_iv; i0 += 4 * kFluxThreads) {
+            for (int a = 0; a < NA; ++a) base[a] = 0;
+            for (int i0 = tid; i0 < n_tile_iv; i0 += 4 * NT) {
                 // (records are stored shuffled -- rec_slot -- so that the lanes of a warp hold tiles eclipsed at
                 // different samples and their shared-memory atomics rarely meet)
                 EventRec recs[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * kFluxThreads;
+                    const int i = i0 + u * NT;
                     recs[u] = i < n_tile_iv ? ivp[i] : no_events();
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * kFluxThreads;
+                    const int i = i0 + u * NT;
                     const EventRec rec = recs[u];
                     const int first = dec_pos(rec.x, 0);
                     if (first == kNoEvent || first >= m1) continue;
                     const int widx = __ldg(G.rec_widx + i);
                     const long long wq = __ldg(wq_tab + widx);  // the job's weight table: WD rings, disc rings, strip
-                    const int arr = (widx >= G.n_wd_rings) + (widx >= G.n_wd_rings + G.n_disc_r);
+                    const int arr = MODE ? (widx >= G.n_wd_rings) + (widx >= G.n_wd_rings + G.n_disc_r)
+                                         : (widx >= G.n_wd_rings + G.n_disc_r);
+                    const long long nq = -wq;
+                    const int hi_p = (int)(wq >> kLimbBits), lo_p = (int)(wq & kLimbMask);
+                    const int hi_n = (int)(nq >> kLimbBits), lo_n = (int)(nq & kLimbMask);
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
                         const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
                         if (p == kAtStart) {
                             if (seg == 0) base[arr] += wq;
                         } else if (p >= m0 && p < m1) {
-                            atomicAdd(Dt + arr * Ms + (p - m0), (unsigned long long)((k & 1) ? -wq : wq));
+                            int* cell = cells + (p - m0) * CW + 2 * arr;
+                            atomicAdd(cell, (k & 1) ? hi_n : hi_p);
+                            atomicAdd(cell + 1, (k & 1) ? lo_n : lo_p);
                         }
                     }
                 }
             }
-        for (int i = tid; i < n_img; i += kFluxThreads) {
-            const EventRec rec = dnp[i];
+            if (seg == 0) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
-                if (p == kNoEvent) break;  // positions ascend, empty fields come last
-                if (p == kAtStart) {
-                    if (seg == 0) add_image(i, 1, base + 3);
-                } else if (p >= m0 && p < m1) {
-                    atomicAdd(&S[p - m0 + 1], 1);
+                for (int a = 0; a < NA; ++a) {
+                    long long v = base[a];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) wtot[a][wid] = v;
                 }
             }
         }
-        if (seg == 0) {
-#pragma unroll
-            for (int a = 0; a < kNumArr; ++a) {
-                long long v = base[a];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) wtot[a][wid] = v;
-            }
-        }
         __syncthreads();
-        if (seg == 0 && tid < kNumArr) {
+        if (seg == 0 && tid < NA) {
             long long v = 0;
             for (int i = 0; i < NW; ++i) v += wtot[tid][i];
             s_carry[tid] = v;  // running sums just before sample 0
         }
-        // ---- 2. donor bucket offsets: exclusive scan of the counts (S[x + 1] = events before sample x) ----
-        {
-            int cnt[RP], tot = 0;
-#pragma unroll
-            for (int r = 0; r < RP; ++r) {
-                cnt[r] = S[1 + tid * RP + r];
-                tot += cnt[r];
-            }
-            int inc = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int u = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += u;
-            }
-            if (lane == 31) s_itot[wid] = inc;
-            __syncthreads();
-            int run = inc - tot;
-#pragma unroll
-            for (int i = 0; i < NW; ++i) run += i < wid ? s_itot[i] : 0;
-#pragma unroll
-            for (int r = 0; r < RP; ++r) {
-                const int c2 = cnt[r];
-                S[1 + tid * RP + r] = run;  // start of sample (tid*RP + r)'s bucket, used as fill cursor
-                run += c2;
-            }
-        }
         __syncthreads();
-        // ---- 3. fill the donor buckets; afterwards S[x + 1] = number of events at or before sample x ----
-        for (int i = tid; i < n_img; i += kFluxThreads) {
-            const EventRec rec = dnp[i];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
-                if (p == kNoEvent) break;
-                if (p >= m0 && p < m1) ev[atomicAdd(&S[p - m0 + 1], 1)] = (unsigned short)((i << 1) | (k & 1));
-            }
-        }
-        // ---- 4. tile deltas -> running sums after every sample (block scan, in place, as f64) ----
+        // ---- 2. cells -> running sums (block scan); every thread evaluates its RP consecutive samples ----
+        long long run[NA];
         if (tiles_matter) {
-            long long loc[3][RP], tot[3], inc[3];
+            long long tot[NA], inc[NA];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                long long t = 0;
+            for (int a = 0; a < NA; ++a) tot[a] = 0;
 #pragma unroll
-                for (int r = 0; r < RP; ++r) {
-                    t += (long long)Dt[a * Ms + tid * RP + r];
-                    loc[a][r] = t;
+            for (int r = 0; r < RP; ++r) {
+                const int* cell = cells + (tid * RP + r) * CW;
+                if (MODE == 0) {
+                    const int4 v = *(const int4*)cell;
+                    tot[0] += ((long long)v.x << kLimbBits) + v.y;
+                    tot[1] += ((long long)v.z << kLimbBits) + v.w;
+                } else {
+                    const int4 v = *(const int4*)cell;
+                    const int2 u = *(const int2*)(cell + 4);
+                    tot[0] += ((long long)v.x << kLimbBits) + v.y;
+                    tot[1] += ((long long)v.z << kLimbBits) + v.w;
+                    tot[2] += ((long long)u.x << kLimbBits) + u.y;
                 }
-                tot[a] = t;
-                inc[a] = warp_incl(t);
-                if (lane == 31) wtot[a][wid] = inc[a];
+            }
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                long long v = tot[a];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long u = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += u;
+                }
+                inc[a] = v;
+                if (lane == 31) wtot[a][wid] = v;
             }
             __syncthreads();
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
+            for (int a = 0; a < NA; ++a) {
                 long long before = s_carry[a] + inc[a] - tot[a];
 #pragma unroll
                 for (int i = 0; i < NW - 1; ++i) before += i < wid ? wtot[a][i] : 0;
-#pragma unroll
-                for (int r = 0; r < RP; ++r) {
-                    const long long v = before + loc[a][r];
-                    if (tid * RP + r == m0n - 1) s_next[a] = v;
-                    Dsum[a * Ms + tid * RP + r] = (double)v;
-                }
+                run[a] = before;
             }
-        } else if (tid < 3) {
-            s_next[tid] = s_carry[tid];
+        } else {
+#pragma unroll
+            for (int a = 0; a < NA; ++a) run[a] = s_carry[a];
+            if (tid < NA) s_next[tid] = s_carry[tid];
+        }
+        {
+            // phase, cos, sin of the segment's samples, thread-major: sample (tid, r) at [r][tid]
+            const double* __restrict__ seg_tr = A.smp.seg_tr + (size_t)(ch0 + seg) * 3 * Ms + tid;
+            int kd = -1;              // donor table row in dm
+            double knext = -INFINITY;  // the first break point after that row (+inf: none): nothing changes below it
+            double xprev = 2.0;
+            double dm[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            double x0 = __ldg(seg_tr), c0 = __ldg(seg_tr + Ms), s0 = __ldg(seg_tr + 2 * Ms);
+#pragma unroll 1
+            for (int r = 0; r < RP; ++r) {
+                const int p = tid * RP + r;
+                int* cell = cells + p * CW;
+                // the next sample's phase, cos and sin travel while this one is evaluated
+                const int rn = r + 1 < RP ? r + 1 : r;
+                const double x0n = __ldg(seg_tr + rn * NT), c0n = __ldg(seg_tr + Ms + rn * NT);
+                const double s0n = __ldg(seg_tr + 2 * Ms + rn * NT);
+                if (tiles_matter) {
+                    const int4 v = *(const int4*)cell;
+                    run[0] += ((long long)v.x << kLimbBits) + v.y;
+                    run[1] += ((long long)v.z << kLimbBits) + v.w;
+                    if (MODE) {
+                        const int2 u = *(const int2*)(cell + 4);
+                        run[2] += ((long long)u.x << kLimbBits) + u.y;
+                    }
+                    if (p == m0n - 1) {
+#pragma unroll
+                        for (int a = 0; a < NA; ++a) s_next[a] = run[a];
+                    }
+                }
+                if (p < len) {
+                    const double cc = c0 * C.cphi + s0 * C.sphi, ss = s0 * C.cphi - c0 * C.sphi;
+                    double f3 = 0.0;
+                    if (do_don) {
+                        // the donor's moments at this sample: table row = number of break points at or before its phase
+                        double x = x0 - C.phi0w;
+                        x -= rint(x);
+                        if (x >= 0.5) x -= 1.0;
+                        if (x >= knext || x < xprev) {
+                            int k2 = kd + 1;
+                            if (kd < 0 || x < xprev || x - xprev > 2.0 / kDonorBins)
+                                k2 = (int)__ldg(dfirst + donor_bin(x));  // first sample / the phase wrapped / a long jump
+                            double kn = INFINITY;
+                            while (k2 < nb && (kn = __ldg(dkey + k2)) <= x) ++k2;
+                            knext = k2 < nb ? kn : INFINITY;
+                            const double2* row = (const double2*)(dmom + (size_t)k2 * 6);
+                            const double2 a01 = __ldg(row), a23 = __ldg(row + 1), a45 = __ldg(row + 2);
+                            dm[0] = a01.x; dm[1] = a01.y; dm[2] = a23.x; dm[3] = a23.y; dm[4] = a45.x;
+                            kd = k2;
+                        }
+                        xprev = x;
+                        f3 = C.f_rs * (dm[0] + dm[1] * cc + dm[2] * ss + dm[3] * (cc * cc) + dm[4] * (cc * ss));
+                    }
+                    const double bm = C.beam_a * cc + C.beam_b * ss + C.beam_d;
+                    const double beam = C.fis + (1.0 - C.fis) * (bm > 0.0 ? bm : 0.0);
+                    if (MODE == 0) {
+                        const double f01 = (C.f_wd + C.f_d) - C.F01 * ((double)run[0] * kInvFix);
+                        const double f2 = C.f_s * beam * (1.0 - (double)run[1] * kInvFix);
+                        *(double*)cell = f01 + f2 + f3;
+                    } else {
+                        double* out = (double*)cell;
+                        out[0] = C.f_wd * (1.0 - (double)run[0] * kInvFix);
+                        out[1] = C.f_d * (1.0 - (double)run[1] * kInvFix);
+                        out[2] = C.f_s * beam * (1.0 - (double)run[2] * kInvFix);
+                        out[3] = f3;
+                    }
+                }
+                x0 = x0n;
+                c0 = c0n;
+                s0 = s0n;
+            }
         }
         __syncthreads();
-        // ---- 5. donor events -> running sums after every event, EC events at a time; 6. the samples ----
-        const int n_ev = S[len];
-        const int ev_next = m0n > 0 ? S[m0n] : 0;  // events at or before sample m0n - 1
-        if (tid < ND && ev_next == 0) s_next[3 + tid] = s_carry[3 + tid];
-        long long dcar[ND];  // donor sums before the first event of the round
+        if (tid < NA && seg + 1 < n_seg) s_carry[tid] = s_next[tid];
+        // ---- 3. exposure quadrature (Simpson over phase +- width), residuals / output ----
+        for (int j = j0 + tid; j < j1; j += NT) {
+            double acc[NF];
 #pragma unroll
-        for (int a = 0; a < ND; ++a) dcar[a] = s_carry[3 + a];
-        for (int r0 = 0; r0 == 0 || r0 < n_ev; r0 += EC) {
-            if (r0 < n_ev) {
-                long long loc[ND][EP], tot[ND], inc[ND];
-#pragma unroll
-                for (int a = 0; a < ND; ++a) tot[a] = 0;
-#pragma unroll
-                for (int q = 0; q < EP; ++q) {
-                    const int x = r0 + tid * EP + q;
-                    if (x < n_ev) {
-                        const int word = ev[x];
-                        add_image(word >> 1, (word & 1) ? -1 : 1, tot);
-                    }
-#pragma unroll
-                    for (int a = 0; a < ND; ++a) loc[a][q] = tot[a];
-                }
-#pragma unroll
-                for (int a = 0; a < ND; ++a) {
-                    inc[a] = warp_incl(tot[a]);
-                    if (lane == 31) wtot[3 + a][wid] = inc[a];
-                }
-                __syncthreads();
-#pragma unroll
-                for (int a = 0; a < ND; ++a) {
-                    long long before = dcar[a] + inc[a] - tot[a], all = dcar[a];
-#pragma unroll
-                    for (int i = 0; i < NW; ++i) {
-                        const long long t = wtot[3 + a][i];
-                        before += i < wid ? t : 0;
-                        all += t;
-                    }
-#pragma unroll
-                    for (int q = 0; q < EP; ++q) {
-                        const int x = r0 + tid * EP + q;
-                        const long long v = before + loc[a][q];
-                        if (x < n_ev) {
-                            P[a * EC + tid * EP + q] = (double)v;
-                            if (x == ev_next - 1) s_next[3 + a] = v;
-                        }
-                    }
-                    dcar[a] = all;
-                }
-                __syncthreads();
-            }
-            // ---- 6. components at every sample whose last event lies in this round ----
-            for (int p = tid; p < len; p += kFluxThreads) {
-                const int idx = S[p + 1];
-                if (!((idx > r0 && idx <= r0 + EC) || (idx == 0 && r0 == 0))) continue;
-                double t3[3], dm[ND];
-#pragma unroll
-                for (int a = 0; a < 3; ++a) t3[a] = tiles_matter ? Dsum[a * Ms + p] : (double)s_carry[a];
-#pragma unroll
-                for (int a = 0; a < ND; ++a) dm[a] = idx == 0 ? (double)s_carry[3 + a] : P[a * EC + idx - r0 - 1];
-                const int m = m0 + p;
-                const double c0 = __ldg(A.smp.cosS + lc0 * K + m), s0 = __ldg(A.smp.sinS + lc0 * K + m);
-                const double cc = c0 * C.cphi + s0 * C.sphi, ss = s0 * C.cphi - c0 * C.sphi;
-                const double bm = C.beam_a * cc + C.beam_b * ss + C.beam_d;
-                const double beam = C.fis + (1.0 - C.fis) * (bm > 0.0 ? bm : 0.0);
-                const double dn = dm[0] + dm[1] * cc + dm[2] * ss + dm[3] * (cc * cc) + dm[4] * (cc * ss);
-                const double f0 = C.f_wd * (1.0 - t3[0] * kInvFix);
-                const double f1 = C.f_d * (1.0 - t3[1] * kInvFix);
-                const double f2 = C.f_s * beam * (1.0 - t3[2] * kInvFix);
-                const double f3 = C.f_rs * dn;
-                if (A.mode == 0) {
-                    Fs[p] = f0 + f1 + f2 + f3;
-                } else {
-                    Fs[p] = f0;
-                    Fs[Ms + p] = f1;
-                    Fs[2 * Ms + p] = f2;
-                    Fs[3 * Ms + p] = f3;
-                }
-            }
-            __syncthreads();
-        }
-        if (tid < kNumArr && seg + 1 < n_seg) s_carry[tid] = s_next[tid];
-        // ---- 7. exposure quadrature (Simpson over phase +- width), residuals / output ----
-        for (int j = j0 + tid; j < j1; j += kFluxThreads) {
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int f = 0; f < NF; ++f) acc[f] = 0.0;
             for (int k = 0; k < K; ++k) {
                 const int q = __ldg(A.smp.pos + (lc0 + j) * K + k) - m0;
                 const double qw = G.quad_w[k];
-                acc[0] += qw * Fs[q];
-                if (A.mode) {
-                    acc[1] += qw * Fs[Ms + q];
-                    acc[2] += qw * Fs[2 * Ms + q];
-                    acc[3] += qw * Fs[3 * Ms + q];
-                }
+                const double* F = (const double*)(cells + q * CW);
+#pragma unroll
+                for (int f = 0; f < NF; ++f) acc[f] += qw * F[f];
             }
-            if (A.mode == 0) {
+            if (MODE == 0) {
                 const double dy = __ldg(A.smp.y + lc0 + j) - acc[0];
                 const double r = dy / __ldg(A.smp.ye + lc0 + j);
                 chi += r * r;
                 if (A.gp_resid) A.gp_resid[(lc0 + __ldg(A.smp.gp_slot + lc0 + j)) * A.n_walkers + w] = dy;
             } else {
                 const int jo = __ldg(A.smp.pt_index + lc0 + j);
-                A.flux_tot[job * n_ph + jo] = acc[0] + acc[1] + acc[2] + acc[3];
+                A.flux_tot[job * n_ph + jo] = acc[0] + acc[1 % NF] + acc[2 % NF] + acc[3 % NF];
                 if (A.flux_comp)
                     for (int cidx = 0; cidx < 4; ++cidx)
-                        A.flux_comp[((long long)cidx * A.njobs + job) * n_ph + jo] = acc[cidx];
+                        A.flux_comp[((long long)cidx * A.njobs + job) * n_ph + jo] = acc[cidx % NF];
             }
         }
         __syncthreads();
     }
-    if (A.mode == 0) {
-        chi = block_sum<kFluxThreads>(chi, red);
+    if (MODE == 0) {
+        chi = block_sum<NT>(chi, red);
         if (tid == 0) A.chisq_job[job] = chi;
     }
 }

@@ -52,7 +52,7 @@ struct DevBuf {
 
 // Sorted exposure samples of a set of light curves (device copies)
 struct SampleSet {
-    DevBuf lc_off, y, ye, S, cosS, sinS, bins, pos, pt_index, chunk_off, chunks;
+    DevBuf lc_off, y, ye, S, cosS, sinS, bins, pos, pt_index, chunk_off, chunks, seg_tr;
     DevBuf gp_x, gp_var, gp_slot, gp_span;  // GP likelihood: points in ascending raw phase
     int max_chunks = 1;
     int max_nph = 0;
@@ -60,7 +60,7 @@ struct SampleSet {
     long long total = 0;
     void release()
     {
-        DevBuf* b[] = {&lc_off, &y, &ye, &S, &cosS, &sinS, &bins, &pos, &pt_index, &chunk_off, &chunks,
+        DevBuf* b[] = {&lc_off, &y, &ye, &S, &cosS, &sinS, &bins, &pos, &pt_index, &chunk_off, &chunks, &seg_tr,
                        &gp_x, &gp_var, &gp_slot, &gp_span};
         for (DevBuf* x : b) x->release();
     }
@@ -82,6 +82,7 @@ struct SampleSet {
         v.gp_span = gp_span.as<double2>();
         v.chunk_off = chunk_off.as<long long>();
         v.chunks = chunks.as<int4>();
+        v.seg_tr = seg_tr.as<double>();
         return v;
     }
 };
@@ -98,10 +99,10 @@ struct Lane {
     cudaEvent_t ev[ST_COUNT + 1] = {};
     cudaEvent_t kev[LFB_K_COUNT + 1] = {}, sev[2] = {};  // per-kernel trace (lfb_set_trace), side-stream pair
     bool kev_set[LFB_K_COUNT + 1] = {};
-    DevBuf ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, qmom, ivp, chi_part, gp_resid;
+    DevBuf ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, ivp, chi_part, gp_resid, dt_first, dt_key, dt_mom;
     void track(unsigned long long* gen)
     {
-        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &qmom, &ivp, &chi_part, &gp_resid};
+        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &ivp, &chi_part, &gp_resid, &dt_first, &dt_key, &dt_mom};
         for (DevBuf* x : b) x->gen = gen;
     }
     cudaError_t create()
@@ -124,7 +125,7 @@ struct Lane {
     }
     void destroy()
     {
-        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &qmom, &ivp, &chi_part, &gp_resid};
+        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &ivp, &chi_part, &gp_resid, &dt_first, &dt_key, &dt_mom};
         for (DevBuf* x : b) x->release();
         for (int i = 0; i <= ST_COUNT; ++i)
             if (ev[i]) cudaEventDestroy(ev[i]);
@@ -162,7 +163,7 @@ struct lfb_handle {
     long long launches = 0;
     int sm_count = 148;
     int max_smem = 0;
-    int Mc = 1280, Mc_flux = 1024;  // segment capacity of the flux kernel in samples: chi-squared mode / flux-curve mode
+    int flux_variant = 0;  // shape of the chi-squared flux kernel (LFB_FLUX_VARIANT: 0 = 256 x 13, 1 = 512 x 13, 2 = 128 x 13)
     long long max_jobs_per_batch = 131072;
     // CUDA graphs for small, repeated calls (launch-bound): one captured pass per (what, n, pointers)
     struct GraphEntry {
@@ -203,6 +204,19 @@ struct lfb_handle {
 };
 
 static std::string g_create_error;
+
+// The flux kernel's shape per mode: threads, consecutive samples per thread (segment capacity = NT * RP samples),
+// resident CTAs per SM.  Chi-squared mode has a few variants for tuning (LFB_FLUX_VARIANT).
+struct FluxShape {
+    int NT, RP, CTAS;
+};
+static FluxShape flux_shape(const lfb_handle* h, int mode)
+{
+    if (mode) return {256, 6, 4};
+    if (h->flux_variant == 1) return {512, 13, 2};
+    if (h->flux_variant == 2) return {128, 13, 8};
+    return {256, 13, 4};
+}
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -254,9 +268,10 @@ static int donor_ring_count(int nth, int k)
 // by all walkers: order the points in (wrapped) phase, merge their K exposure samples, wrap to
 // [-0.5, 0.5], sort, record where each (point, node) landed, build the bin table of the sorted
 // axis, and cut the points into chunks whose samples span at most Mc consecutive sorted samples.
-static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const long long* off, const double* phase,
-                         const double* width, const double* y, const double* ye)
+static int build_samples(lfb_handle* h, SampleSet& ss, int NT, int RP, int n_ecl, const long long* off,
+                         const double* phase, const double* width, const double* y, const double* ye)
 {
+    const int Mc = NT * RP;  // capacity of a flux-kernel segment in samples
     const GridCfg& G = h->grid;
     const int K = G.n_quad;
     const long long total = off[n_ecl];
@@ -384,7 +399,27 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const 
         max_chunks = std::max(max_chunks, nch);
     }
     if (chunks.empty()) chunks.push_back(make_int4(0, 0, 0, -1));
+    // phase, cos, sin of every segment's samples in the flux kernel's thread-major order: thread t evaluates
+    // samples t * RP .. t * RP + RP - 1 of the segment and reads [r][t], coalesced
+    std::vector<double> seg_tr((size_t)chunks.size() * 3 * Mc, 0.0);
+    {
+        size_t ci = 0;
+        for (int e = 0; e < n_ecl; ++e) {
+            const size_t so = (size_t)off[e] * K;
+            for (long long c = chunk_off[e]; c < chunk_off[e + 1]; ++c, ++ci) {
+                const int4 ch = chunks[(size_t)c];
+                double* dst = seg_tr.data() + (size_t)c * 3 * Mc;
+                for (int p = 0; p <= ch.w - ch.z; ++p) {
+                    const size_t at = (size_t)(p % RP) * NT + (size_t)(p / RP);
+                    dst[at] = S[so + ch.z + p];
+                    dst[(size_t)Mc + at] = cS[so + ch.z + p];
+                    dst[2 * (size_t)Mc + at] = sS[so + ch.z + p];
+                }
+            }
+        }
+    }
     int rc;
+    if ((rc = upload(h, ss.seg_tr, seg_tr.data(), sizeof(double) * seg_tr.size()))) return rc;
     if ((rc = upload(h, ss.lc_off, off, sizeof(long long) * (size_t)(n_ecl + 1)))) return rc;
     if ((rc = upload(h, ss.y, ys.data(), sizeof(double) * (size_t)total))) return rc;
     if ((rc = upload(h, ss.ye, yes.data(), sizeof(double) * (size_t)total))) return rc;
@@ -406,15 +441,6 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int Mc, int n_ecl, const 
     ss.max_gaps = max_gaps;
     ss.total = total;
     return LFB_OK;
-}
-
-// shared memory of flux_kernel<Ms>: donor moment parts, three tile delta arrays, flux per sample,
-// donor bucket offsets and sorted donor events (worst case 6 per image)
-static size_t flux_smem_bytes(const GridCfg& G, int Ms, int EC, int nF)
-{
-    const size_t ndq = (size_t)G.n_donor_q;
-    size_t b = 64 * ndq + 8 * (size_t)std::max(nF, 3) * Ms + 8 * 5 * (size_t)EC + 4 * ((size_t)Ms + 1) + 2 * 6 * 4 * ndq;
-    return (b + 15) & ~(size_t)15;
 }
 
 // One pass of the pipeline over walkers [0, n) (device pointers, one batch).
@@ -513,9 +539,7 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         A.what = what;
         A.flags = flags;
         A.mode = mode;
-        const int Ms = mode ? h->Mc_flux : h->Mc;
-        A.Ms = Ms;
-        A.ni_total = G.n_wd + G.n_disc + G.n_bs + 4 * G.n_donor_q;
+        A.ni_total = G.n_wd + G.n_disc + G.n_bs;
         A.njobs = njobs;
         A.theta = d_theta;
         A.ws = E.ws;
@@ -526,15 +550,21 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         A.bs_io = E.bs_io;
         A.bs_b = E.bs_b;
         const size_t nwq = (size_t)G.n_wd_rings + G.n_disc_r + G.n_bs;
+        const size_t nb_max = 8 * (size_t)G.n_donor_q;
         CK(ln.jc.reserve(sizeof(JobConst) * (size_t)njobs));
         CK(ln.wq.reserve(sizeof(long long) * (size_t)njobs * nwq));
-        CK(ln.qmom.reserve(sizeof(long long) * (size_t)njobs * G.n_donor_q * 8));
         CK(ln.ivp.reserve(sizeof(EventRec) * (size_t)njobs * A.ni_total));
         CK(ln.chi_part.reserve(sizeof(double) * (size_t)njobs));
+        CK(ln.dt_first.reserve(sizeof(unsigned short) * (size_t)n * (kDonorBins + 1)));
+        CK(ln.dt_key.reserve(sizeof(double) * (size_t)n * nb_max));
+        CK(ln.dt_mom.reserve(sizeof(double) * (size_t)n * (nb_max + 1) * 6));
         A.jc = ln.jc.as<JobConst>();
         A.wq = ln.wq.as<long long>();
-        A.qmom = ln.qmom.as<long long>();
         A.ivp = ln.ivp.as<EventRec>();
+        A.dt.first = ln.dt_first.as<unsigned short>();
+        A.dt.key = ln.dt_key.as<double>();
+        A.dt.mom = ln.dt_mom.as<double>();
+        A.dt.nb_max = (int)nb_max;
         A.chisq_job = ln.chi_part.as<double>();
         A.flux_tot = d_tot;
         A.flux_comp = d_comp;
@@ -547,11 +577,21 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
             CK(ln.gp_resid.reserve(sizeof(double) * (size_t)ss.total * (size_t)n));
             A.gp_resid = ln.gp_resid.as<double>();
         }
+        if (!(flags & LFB_FLAG_SKIP_DONOR)) {
+            // the donor's curve as a table over phase, once per walker (every eclipse of the walker reads it)
+            if (8 * G.n_donor_q > 65535) return fail(h, LFB_EINVAL, "donor grid too dense (16-bit break-point index)");
+            const size_t dsm = 224 * (size_t)G.n_donor_q + 4 * (kDonorBins + 1) + 64;
+            if (dsm > (size_t)h->max_smem - 2048) return fail(h, LFB_EINVAL, "donor grid too dense for the table kernel's shared memory");
+            KREC(LFB_K_DONOR_TABLE);
+            CK(cudaFuncSetAttribute(donor_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+            donor_table_kernel<<<(unsigned)n, kDonorThreads, dsm, st>>>(A);
+            h->launches++;
+        }
         // everything of the flux preparation that does not need the strip goes before the join with the
         // stream ODE, so that the main stream has work while the ODE finishes
         KREC(LFB_K_PREP);
         prep_kernel<<<(unsigned)((njobs + 3) / 4), 128, 0, st>>>(A);
-        const long long per_job0 = ((G.n_wd_half + G.n_disc_half + G.n_donor_q) + 31) & ~31;
+        const long long per_job0 = ((G.n_wd_half + G.n_disc_half) + 31) & ~31;
         const long long per_job1 = (G.n_bs + 31) & ~31;
         KREC(LFB_K_POSITIONS);
         positions_kernel<0><<<(unsigned)((njobs * per_job0 + 127) / 128), 128, 0, st>>>(A);
@@ -565,26 +605,21 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         prep_strip_kernel<<<(unsigned)((njobs + 3) / 4), 128, 0, st>>>(A);
         positions_kernel<1><<<(unsigned)((njobs * per_job1 + 127) / 128), 128, 0, st>>>(A);
         h->launches += 2;
-        const int EC = Ms == 1280 ? 512 : Ms == 1024 ? 256 : Ms / 2;
-        const size_t smem = flux_smem_bytes(G, Ms, EC, mode ? 4 : 1);
-        if (smem > (size_t)h->max_smem - 2048)
-            return fail(h, LFB_EINVAL, "light curve too long / surface grid too dense for the flux kernel's shared memory");
-        if (4 * G.n_donor_q > 32767) return fail(h, LFB_EINVAL, "donor grid too dense (15-bit image index)");
+        const FluxShape fs = flux_shape(h, mode);
+        const size_t smem = (size_t)fs.NT * fs.RP * (mode ? 32 : 16);
+        if (G.n_wd + G.n_disc > 32767 || G.n_bs > 32767)
+            return fail(h, LFB_EINVAL, "surface grid too dense: at most 32767 tiles per running sum (16-bit low limb)");
         const dim3 fgrid((unsigned)njobs);
         KREC(LFB_K_FLUX);
-#define LFB_LAUNCH_FLUX(MS, EC_, CTAS)                                                                                 \
-    do {                                                                                                               \
-        CK(cudaFuncSetAttribute(flux_kernel<MS, EC_, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        flux_kernel<MS, EC_, CTAS><<<fgrid, kFluxThreads, smem, st>>>(A);                                              \
+#define LFB_LAUNCH_FLUX(MODE, NT, RP, CTAS)                                                                               \
+    do {                                                                                                                  \
+        CK(cudaFuncSetAttribute(flux_kernel<MODE, NT, RP, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        flux_kernel<MODE, NT, RP, CTAS><<<fgrid, NT, smem, st>>>(A);                                                      \
     } while (0)
-        switch (Ms) {
-        case 1024: LFB_LAUNCH_FLUX(1024, 256, 4); break;
-        case 1280: LFB_LAUNCH_FLUX(1280, 512, 3); break;
-        case 1536: LFB_LAUNCH_FLUX(1536, 768, 2); break;
-        case 2048: LFB_LAUNCH_FLUX(2048, 1024, 2); break;
-        case 3072: LFB_LAUNCH_FLUX(3072, 1536, 1); break;
-        default: return fail(h, LFB_EINVAL, "unsupported segment capacity");
-        }
+        if (mode) LFB_LAUNCH_FLUX(1, 256, 6, 4);
+        else if (fs.NT == 512) LFB_LAUNCH_FLUX(0, 512, 13, 2);
+        else if (fs.NT == 128) LFB_LAUNCH_FLUX(0, 128, 13, 8);
+        else LFB_LAUNCH_FLUX(0, 256, 13, 4);
 #undef LFB_LAUNCH_FLUX
         h->launches += 3;
         if (gp) {
@@ -761,19 +796,16 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
             G.quad_w[k] = cw / (3.0 * nint);
         }
     }
-    // capacity of a flux-kernel segment in samples (LFB_MS overrides the chi-squared one for tuning)
-    h->Mc = 1280;
-    h->Mc_flux = 1024;
+    if (const char* env = getenv("LFB_FLUX_VARIANT")) {
+        int v = atoi(env);
+        if (v >= 0 && v <= 2) h->flux_variant = v;
+    }
     if (const char* env = getenv("LFB_LANES")) {
         int v = atoi(env);
         if (v >= 1 && v <= kLanes) h->n_lanes = v;
     }
     if (const char* env = getenv("LFB_STREAM_LANES_BELOW")) h->stream_lanes_below = atoll(env);
     if (const char* env = getenv("LFB_GRAPHS")) h->graphs_on = atoi(env) != 0;
-    if (const char* env = getenv("LFB_MS")) {
-        int v = atoi(env);
-        if (v == 1024 || v == 1280 || v == 1536 || v == 2048 || v == 3072) h->Mc = v;
-    }
     *out = h;
     return LFB_OK;
 }
@@ -943,7 +975,8 @@ int lfb_set_lightcurves(lfb_handle* h, int n_ecl, const long long* off, const do
     for (int e = 0; e < n_ecl; ++e)
         if (off[e + 1] < off[e] || off[e + 1] - off[e] > 100000000LL) return fail(h, LFB_EINVAL, "set_lightcurves: offsets must ascend");
     CK(cudaSetDevice(h->device));
-    int rc = build_samples(h, h->lc, h->Mc, n_ecl, off, phase, width, y, ye);
+    const FluxShape fs = flux_shape(h, 0);
+    int rc = build_samples(h, h->lc, fs.NT, fs.RP, n_ecl, off, phase, width, y, ye);
     if (rc) return rc;
     h->have_lc = true;
     if (h->gp_on && h->lc.max_gaps > kMaxGaps) {
@@ -1175,7 +1208,8 @@ int lfb_calc_flux(lfb_handle* h, long long n_sets, const double* pars, int npars
     std::vector<int> gather(LFB_NPAR, 0);
     for (int k = 0; k < LFB_NPAR; ++k) gather[k] = k < npars ? k : 0;
     long long off[2] = {0, n_ph};
-    int rc = build_samples(h, h->cf_lc, h->Mc_flux, 1, off, phase, width, nullptr, nullptr);
+    const FluxShape fs = flux_shape(h, 1);
+    int rc = build_samples(h, h->cf_lc, fs.NT, fs.RP, 1, off, phase, width, nullptr, nullptr);
     if (rc) return rc;
     CK(h->cf_gather.reserve(sizeof(int) * LFB_NPAR));
     CK(cudaMemcpyAsync(h->cf_gather.p, gather.data(), sizeof(int) * LFB_NPAR, cudaMemcpyHostToDevice, st));

@@ -262,7 +262,7 @@ def test_device_resident_buffers(engine):
     try:
         assert np.array_equal(engine.log_prob(theta), ref)
         tr = engine.last_trace_ms()
-        assert tr["flux_kernel"] > 0 and tr["elements_kernel<1> disc"] > 0 and len(tr) == 12
+        assert tr["flux_kernel"] > 0 and tr["elements_kernel<1> disc"] > 0 and len(tr) == 13
     finally:
         engine.set_trace(False)
 
