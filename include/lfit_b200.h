@@ -191,6 +191,9 @@ int lfb_chain_append(const char *path, long long n_steps, long long n, int ndim,
 
 /* counters for bench.py: kernels launched by this handle since creation */
 long long lfb_launch_count(const lfb_handle *h);
+/* Diagnostics: element solves that needed the last-resort (scan + golden section + bisection) solver since
+ * the library was loaded, on this handle's device; -1 on error.  Synchronises the device. */
+long long lfb_robust_calls(lfb_handle *h);
 /* Device time (ms) of the stages of the last lfb_log_prob (its last batch), from CUDA events
  * recorded on the stream the kernels ran on; valid once that stream is synchronised.
  * out = {walker, stream, elements (4 launches), flux, finish, total}; the stages are -1 when the

@@ -26,7 +26,7 @@ EXPORTS = (
     "lfb_sampler_create", "lfb_sampler_destroy", "lfb_sampler_set_state", "lfb_sampler_run", "lfb_sampler_half_begin",
     "lfb_sampler_half_end", "lfb_sampler_packed", "lfb_sampler_positions", "lfb_sampler_log_prob",
     "lfb_sampler_get_state", "lfb_sampler_set_chain", "lfb_sampler_read_chain", "lfb_stretch_draws",
-    "lfb_chain_format", "lfb_chain_append",
+    "lfb_chain_format", "lfb_chain_append", "lfb_robust_calls",
 )
 TRACE_KERNELS = ("walker_kernel", "jobcheck_kernel", "elements_kernel<1> disc", "elements_kernel<0> white dwarf",
                  "elements_kernel<3> donor", "donor_table_kernel", "prep_kernel", "positions_kernel", "elements_kernel<2> strip",
@@ -78,6 +78,8 @@ def load():
     lib.lfb_roche.argtypes = [vp, C.c_int, C.c_longlong, dp, dp, dp, ip]
     lib.lfb_launch_count.argtypes = [vp]
     lib.lfb_launch_count.restype = C.c_longlong
+    lib.lfb_robust_calls.argtypes = [vp]
+    lib.lfb_robust_calls.restype = C.c_longlong
     lib.lfb_last_kernel_ms.argtypes = [vp]
     lib.lfb_last_kernel_ms.restype = C.c_float
     lib.lfb_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
@@ -168,6 +170,11 @@ class Engine:
     @property
     def launch_count(self):
         return int(self._lib.lfb_launch_count(self._h))
+
+    @property
+    def robust_calls(self):
+        """Element solves that fell through to the last-resort solver (device-wide, since load)."""
+        return int(self._lib.lfb_robust_calls(self._h))
 
     def last_kernel_ms(self):
         return float(self._lib.lfb_last_kernel_ms(self._h))

@@ -1398,6 +1398,20 @@ int lfb_roche(lfb_handle* h, int which, long long n, const double* a, const doub
     return LFB_OK;
 }
 
+// Diagnostics: element solves that fell through to the scan + golden-section + bisection solver since the
+// library was loaded (all handles of this device).
+long long lfb_robust_calls(lfb_handle* h)
+{
+    if (!h) return -1;
+    unsigned long long v = 0;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpyFromSymbol(&v, g_robust_calls, sizeof(v)) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (long long)v;
+}
+
 int lfb_measure_fp64_peak(lfb_handle* h, int iters, double* tflops)
 {
     if (!h || !tflops || iters <= 0) return LFB_EINVAL;

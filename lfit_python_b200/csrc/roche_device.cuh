@@ -31,6 +31,16 @@
 inline double rsqrt(double v) { return 1.0 / sqrt(v); }
 #endif
 
+// path counters of the element solve (host experiments only; nothing in a normal build)
+#ifndef LFB_CNT
+#define LFB_CNT(i)
+#endif
+
+#ifdef __CUDACC__
+// how often the last-resort solver ran on the device (diagnostics: lfb_robust_calls)
+__device__ unsigned long long g_robust_calls = 0ull;
+#endif
+
 namespace lfb {
 
 constexpr double kPi = 3.14159265358979323846264338327950288;
@@ -201,6 +211,7 @@ LFB_HD double fast_rcp(double x)
 // orbital angle whose cosine and sine are (c, s).
 LFB_HD void ray_eval(const Roche& R, double si, double ci, const Point& T, double c, double s, double lam, Derivs& D)
 {
+    LFB_CNT(9);
     double ex = si * c, ey = -si * s;
     double dx = fma(lam, ex, -T.xi * s - T.eta * ci * c);
     double dy = fma(lam, ey, -T.xi * c + T.eta * ci * s);
@@ -297,6 +308,10 @@ LFB_HD_NOINLINE double chord_min(const Roche& R, double si, double ci, const Poi
 LFB_HD_NOINLINE int ingress_egress_robust(const Roche& R, double si, double ci, const Point& T, double* ph_in,
                                           double* ph_out)
 {
+    LFB_CNT(8);
+#ifdef __CUDA_ARCH__
+    atomicAdd(&g_robust_calls, 1ull);
+#endif
     const int NSCAN = 384;
     double psi = atan2(T.y, 1.0 - T.x);
     double half = 0.5 * kPi, step = 2.0 * half / (NSCAN - 1), th_lo = psi - half;
@@ -354,7 +369,7 @@ LFB_HD_NOINLINE int ingress_egress_robust(const Roche& R, double si, double ci, 
 // the FP64 iteration converges to is unchanged -- FP32 only picks the starting point, and a
 // warm-up that misbehaves is dropped.
 struct DerivsF {
-    float S, St, Sl, Stl, Sll;
+    float S, St, Sl, Stt, Stl, Sll;
 };
 struct PointF {
     float x, y, z, xi, eta;
@@ -371,6 +386,7 @@ LFB_HD float rsqrt_f(float x)
 
 LFB_HD void ray_eval_f(float mu, float omu, float si, float ci, const PointF& T, float c, float s, float lam, DerivsF& D)
 {
+    LFB_CNT(10);
     float ex = si * c, ey = -si * s;
     float dx = fmaf(lam, ex, -T.xi * s - T.eta * ci * c);
     float dy = fmaf(lam, ey, -T.xi * c + T.eta * ci * s);
@@ -386,11 +402,12 @@ LFB_HD void ray_eval_f(float mu, float omu, float si, float ci, const PointF& T,
     float gx = a1 * x + a2 * x2 - xc, gy = a12 * y - y, gz = a12 * z;
     float x_e = x * ex + y * ey + z * ci, d_e = x_e - ex;
     float x_t = x * tx + y * ty, d_t = x_t - tx;
-    float e_t = ex * tx + ey * ty, e_xy = ex * ex + ey * ey;
+    float t_t = tx * tx + ty * ty, e_t = ex * tx + ey * ty, e_xy = ex * ex + ey * ey;
     D.S = -omu * ir1 - mu * ir2 - 0.5f * (xc * xc + y * y);
     D.St = gx * tx + gy * ty;
     D.Sl = gx * ex + gy * ey + gz * ci;
     D.Sll = a12 - b1 * x_e * x_e - b2 * d_e * d_e - e_xy;
+    D.Stt = (a12 - 1.0f) * t_t - b1 * x_t * x_t - b2 * d_t * d_t - (gx * dx + gy * dy);
     D.Stl = (a12 - 1.0f) * e_t - b1 * x_e * x_t - b2 * d_e * d_t + (gx * ey - gy * ex);
 }
 
@@ -432,6 +449,41 @@ LFB_HD bool warm_root(float mu, float omu, float phic, float si, float ci, const
     return false;
 }
 
+// FP32 search for the deepest LOS of an element (the minimum over (th, lam) of the potential along its lines of
+// sight), from the conjunction LOS: Newton on lam alone first, then on both.  1: settled, g0 = depth below the
+// critical potential there (single precision); 0: it did not settle -- the caller searches in FP64 from scratch.
+LFB_HD int warm_min(float mu, float omu, float phic, float si, float ci, const PointF& T, float& c, float& s, float& lam,
+                    float& g0)
+{
+    DerivsF D;
+    for (int it = 0; it < 5; ++it) {
+        ray_eval_f(mu, omu, si, ci, T, c, s, lam, D);
+        if (!(D.Sll > 0.0f)) return 0;
+        float dl = -D.Sl / D.Sll;
+        dl = dl > 0.1f ? 0.1f : (dl < -0.1f ? -0.1f : dl);
+        lam += dl;
+        if (fabsf(dl) < 1e-3f) break;
+    }
+    for (int it = 0; it < 12; ++it) {
+        ray_eval_f(mu, omu, si, ci, T, c, s, lam, D);
+        float det = D.Stt * D.Sll - D.Stl * D.Stl;
+        if (!(D.Sll > 0.0f) || !(det > 0.0f)) return 0;
+        float idet = 1.0f / det;
+        float dth = -(D.St * D.Sll - D.Sl * D.Stl) * idet, dl = -(D.Sl * D.Stt - D.St * D.Stl) * idet;
+        dth = dth > 0.1f ? 0.1f : (dth < -0.1f ? -0.1f : dth);
+        dl = dl > 0.1f ? 0.1f : (dl < -0.1f ? -0.1f : dl);
+        rotate_cs_f(c, s, dth);
+        lam += dl;
+        if (!(fabsf(dth) < 1.0f)) return 0;  // NaN
+        if (fabsf(dth) < 1e-4f && fabsf(dl) < 1e-4f) {
+            g0 = D.S - phic;  // one small step old: good to ~1e-6
+            return 1;
+        }
+    }
+    return 0;
+}
+
+constexpr float kWarmRejectMargin = 3e-4f;  // depth above which the FP32 search alone says "never eclipsed"
 constexpr int kMinIters = 12;   // deepest-LOS Newton (shallow elements only), early exit
 constexpr int kRootIters = 16;  // grazing-LOS Newton, early exit
 
@@ -525,7 +577,8 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
     double wz = -(T.z + T.eta * si);
     double lam = wx * ex + wy * ey + wz * ci;
     double w2 = wx * wx + wy * wy + wz * wz;
-    if (w2 - lam * lam >= R.rs * R.rs || lam <= 0.0) return 0;
+    LFB_CNT(0);
+    if (w2 - lam * lam >= R.rs * R.rs || lam <= 0.0) { LFB_CNT(1); return 0; }
     double res[2];
     if (hint) {
         // The hint's LOS graze the lobe where this element's do, give or take the element's offset; and
@@ -534,6 +587,7 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         const double off = sqrt(T.xi * T.xi + T.eta * T.eta + T.x * T.x + T.y * T.y + T.z * T.z);
         if (-hint->s[0] > 4.0 * off && hint->s[1] > 4.0 * off && hint->c[0] > 0.0 && hint->c[1] > 0.0 &&
             graze_roots(R, si, ci, T, cpsi, spsi, cpsi, spsi, *hint, res, roots)) {
+            LFB_CNT(2);
             *ph_in = res[0] * (1.0 / kTwoPi);
             *ph_out = res[1] * (1.0 / kTwoPi);
             return 1;
@@ -544,8 +598,14 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
     double cosd = (tang - wz * ci) / rxy;
     Derivs D;
     double c0, s0, c1, s1, lam0, lam1, cm = cpsi, sm = spsi;
+    // How the search for the starts ends: -1 starts found, 0 never eclipsed, 2 hand over to the robust solver.
+    // (No return inside the two branches: all lanes of a warp meet again before the grazing-LOS Newton, which is
+    // the expensive part and the same code for deep and shallow elements.)
+    int verdict = -1;
+    c0 = c1 = s0 = s1 = lam0 = lam1 = 0.0;
     if (cosd < 0.995) {
         // the conjunction LOS passes well inside the inscribed sphere: start at its tangents
+        LFB_CNT(3);
         cosd = cosd > -1.0 ? cosd : -1.0;
         double sind = sqrt(1.0 - cosd * cosd);
         c0 = cpsi * cosd + spsi * sind;  // psi - del
@@ -554,20 +614,47 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         s1 = spsi * cosd + cpsi * sind;
         lam0 = lam1 = tang;
     } else {
-        for (int it = 0; it < 5; ++it) {
+        LFB_CNT(4);
+        bool warmed = false;
+#ifndef LFB_NO_WARMUP
+        {
+            // the search for the deepest LOS runs in FP32 first: an element that clears the lobe by a wide margin
+            // is done, the others hand the FP64 iteration a start ~1e-4 from the minimum
+            const PointF Tf = {(float)T.x, (float)T.y, (float)T.z, (float)T.xi, (float)T.eta};
+            float cf = (float)c, sf = (float)s, lf = (float)lam, g0f = 0.0f;
+            if (warm_min((float)R.mu, (float)R.omu, (float)R.phic, (float)si, (float)ci, Tf, cf, sf, lf, g0f)) {
+                if (g0f > kWarmRejectMargin) {
+                    LFB_CNT(6);
+                    verdict = 0;
+                } else {
+                    const double cw = (double)cf, sw = (double)sf;
+                    const double nrm = fast_rsqrt(cw * cw + sw * sw);
+                    c = cw * nrm;
+                    s = sw * nrm;
+                    lam = (double)lf;
+                    warmed = true;
+                }
+            }
+        }
+#endif
+        for (int it = 0; it < 5 && !warmed && verdict < 0; ++it) {
             ray_eval(R, si, ci, T, c, s, lam, D);
-            if (!(D.Sll > 0.0)) return 0;  // no potential minimum along the closest LOS: out of reach
+            if (!(D.Sll > 0.0)) {  // no potential minimum along the closest LOS: out of reach
+                LFB_CNT(5);
+                verdict = 0;
+                break;
+            }
             double dl = clampd(-D.Sl * fast_rcp(D.Sll), 0.1);
             lam += dl;
             if (fabs(dl) < 1e-6) break;  // the 2-D Newton below finishes the job
         }
         bool conv = false;
-        for (int it = 0; it < kMinIters; ++it) {
+        for (int it = 0; it < kMinIters && verdict < 0; ++it) {
             ray_eval(R, si, ci, T, c, s, lam, D);
             double det = D.Stt * D.Sll - D.Stl * D.Stl;
             if (!(D.Sll > 0.0) || !(det > 0.0)) {
-                if (D.S >= R.phic) return 0;
-                return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
+                verdict = D.S >= R.phic ? 0 : 2;
+                break;
             }
             double dth = clampd(-(D.St * D.Sll - D.Sl * D.Stl) / det, 0.1);
             double dl = clampd(-(D.Sl * D.Stt - D.St * D.Stl) / det, 0.1);
@@ -575,29 +662,46 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
             lam += dl;
             if (fabs(dth) < 1e-7 && fabs(dl) < 1e-7) { conv = true; break; }
         }
-        if (!conv) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
-        ray_eval(R, si, ci, T, c, s, lam, D);
-        double g0 = D.S - R.phic;
-        if (!(g0 < 0.0)) return 0;  // the deepest LOS clears the lobe
-        double kappa = D.Stt - D.Stl * D.Stl / D.Sll;
-        if (!(D.Sll > 0.0) || !(kappa > 0.0)) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
-        double del = sqrt(-2.0 * g0 / kappa), slope = -D.Stl / D.Sll;
-        if (!(del < 0.25)) return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
-        cm = c;
-        sm = s;
-        c0 = c1 = c;
-        s0 = s1 = s;
-        rotate_cs(c0, s0, -del);
-        rotate_cs(c1, s1, del);
-        lam0 = lam - slope * del;
-        lam1 = lam + slope * del;
+        if (verdict < 0 && !conv) verdict = 2;
+        if (verdict < 0) {
+            ray_eval(R, si, ci, T, c, s, lam, D);
+            double g0 = D.S - R.phic;
+            double kappa = D.Stt - D.Stl * D.Stl / D.Sll;
+            if (!(g0 < 0.0)) {  // the deepest LOS clears the lobe
+                LFB_CNT(6);
+                verdict = 0;
+            } else if (!(D.Sll > 0.0) || !(kappa > 0.0)) {
+                verdict = 2;
+            } else {
+                LFB_CNT(7);
+                double del = sqrt(-2.0 * g0 / kappa), slope = -D.Stl / D.Sll;
+                if (!(del < 0.25)) {
+                    verdict = 2;
+                } else {
+                    cm = c;
+                    sm = s;
+                    c0 = c1 = c;
+                    s0 = s1 = s;
+                    rotate_cs(c0, s0, -del);
+                    rotate_cs(c1, s1, del);
+                    lam0 = lam - slope * del;
+                    lam1 = lam + slope * del;
+                }
+            }
+        }
     }
-    const Roots start = {{c0, c1}, {s0, s1}, {lam0, lam1}};
-    if (!graze_roots(R, si, ci, T, cpsi, spsi, cm, sm, start, res, roots))
-        return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
-    *ph_in = res[0] * (1.0 / kTwoPi);
-    *ph_out = res[1] * (1.0 / kTwoPi);
-    return 1;
+    if (verdict < 0) {
+        const Roots start = {{c0, c1}, {s0, s1}, {lam0, lam1}};
+        if (graze_roots(R, si, ci, T, cpsi, spsi, cm, sm, start, res, roots)) verdict = 1;
+        else verdict = 2;
+    }
+    if (verdict == 1) {
+        *ph_in = res[0] * (1.0 / kTwoPi);
+        *ph_out = res[1] * (1.0 / kTwoPi);
+        return 1;
+    }
+    if (verdict == 0) return 0;
+    return ingress_egress_robust(R, si, ci, T, ph_in, ph_out);
 }
 
 // ---- ballistic stream from L1 (roche.bspot): fixed-sequence Gragg-Bulirsch-Stoer ----
