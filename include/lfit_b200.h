@@ -211,8 +211,8 @@ enum {
     LFB_K_JOBCHECK,    /* jobcheck_kernel */
     LFB_K_ELEM_DISC,   /* elements_kernel<1> */
     LFB_K_ELEM_WD,     /* elements_kernel<0> */
-    LFB_K_ELEM_DONOR,  /* elements_kernel<3> */
-    LFB_K_DONOR_TABLE, /* donor_table_kernel: the donor curve's phase table, per walker */
+    LFB_K_ELEM_DONOR,  /* elements_kernel<3> (second side stream, beside the kernels of the main stream) */
+    LFB_K_DONOR_TABLE, /* donor_table_kernel: the donor curve's phase table, per walker (second side stream) */
     LFB_K_PREP,        /* prep_kernel */
     LFB_K_POSITIONS,   /* positions_kernel<0>: white dwarf, disc */
     LFB_K_ELEM_BS,     /* elements_kernel<2>, with any wait for the stream ODE */

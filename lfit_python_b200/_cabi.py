@@ -29,7 +29,7 @@ EXPORTS = (
     "lfb_chain_format", "lfb_chain_append", "lfb_robust_calls",
 )
 TRACE_KERNELS = ("walker_kernel", "jobcheck_kernel", "elements_kernel<1> disc", "elements_kernel<0> white dwarf",
-                 "elements_kernel<3> donor", "donor_table_kernel", "prep_kernel", "positions_kernel", "elements_kernel<2> strip",
+                 "elements_kernel<3> donor (side stream)", "donor_table_kernel (side stream)", "prep_kernel", "positions_kernel", "elements_kernel<2> strip",
                  "prep_strip_kernel + positions_kernel<1>",
                  "flux_kernel", "gp_kernel", "finish_kernel", "stream_kernel (side stream)")
 

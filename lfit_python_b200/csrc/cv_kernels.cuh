@@ -71,7 +71,7 @@ struct DevLayout {
 // the map from (point, quadrature node) to sorted position.
 struct DevSamples {
     const long long* lc_off;     // [n_ecl + 1] data-point offsets
-    const double *y, *ye;        // [total] in phase order
+    const double *y, *iye;       // [total] in phase order: flux, 1 / error
     const double *S, *cosS, *sinS;  // [K * total] sorted per eclipse
     const int* bins;             // [K * total + n_ecl] per eclipse M + 1 entries (see SampleAxis)
     const int* pos;              // [total * K] sorted position of each (point, node); points in phase order
@@ -776,15 +776,16 @@ __host__ __device__ __forceinline__ int donor_bin(double phase)
     return f <= 0.0 ? 0 : (f >= (double)(kDonorBins - 1) ? kDonorBins - 1 : (int)f);
 }
 
-// moments (1, c, s, c^2, c s) of image im (bit 0: sign of B, bit 1: sign of D) from the eight parts of its quarter tile
-__device__ __forceinline__ void donor_image_moments(const double* m, int im, double sgn, double* acc)
+// moments (1, c, s, c^2, c s) of image im (bit 0: sign of B, bit 1: sign of D) from the eight parts of its
+// quarter tile, m[part * stride]
+__device__ __forceinline__ void donor_image_moments(const double* m, int stride, int im, double sgn, double* acc)
 {
     const double sb = (im & 1) ? sgn : -sgn, sd = (im & 2) ? -1.0 : 1.0;
-    acc[0] += sgn * (m[0] + sd * m[1]);
-    acc[1] += sgn * (m[2] + sd * m[3]);
-    acc[2] += sb * (m[4] + sd * m[5]);
-    acc[3] += sgn * m[6];
-    acc[4] += sb * m[7];
+    acc[0] += sgn * (m[0] + sd * m[stride]);
+    acc[1] += sgn * (m[2 * stride] + sd * m[3 * stride]);
+    acc[2] += sb * (m[4 * stride] + sd * m[5 * stride]);
+    acc[3] += sgn * m[6 * stride];
+    acc[4] += sb * m[7 * stride];
 }
 
 __global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __grid_constant__ FluxArgs A)
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __g
     const int NDQ = G.n_donor_q, NB = 8 * NDQ;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = kDonorThreads / 32;
-    double* qm = (double*)dsm;                         // [NDQ][8] moment parts of a quarter tile
+    double* qm = (double*)dsm;                         // [8][NDQ] moment parts of the quarter tiles (part-major: no bank conflicts)
     double* ukey = qm + 8 * NDQ;                       // [NB] break points as found (+inf: none)
     double* skey = ukey + NB;                          // [NB] sorted
     int* cnt = (int*)(skey + NB);                      // [kDonorBins + 1]
@@ -819,15 +820,15 @@ __global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __g
         // image with +D faces the observer iff cos(th - psi) > -D/rho
         const double hp = ratio >= 1.0 ? 0.5 : (ratio <= -1.0 ? -1.0 : acos(-ratio) * (1.0 / kTwoPi));
         const double hm = ratio <= -1.0 ? 0.5 : (ratio >= 1.0 ? -1.0 : acos(ratio) * (1.0 / kTwoPi));
-        double* m = qm + 8 * t;
+        double* m = qm + t;
         m[0] = q.w * ud * (Dq * Dq + Bp * Bp);
-        m[1] = q.w * (1.0 - ud) * Dq;
-        m[2] = q.w * (1.0 - ud) * Aq;
-        m[3] = q.w * 2.0 * ud * Aq * Dq;
-        m[4] = q.w * (1.0 - ud) * Bp;
-        m[5] = q.w * 2.0 * ud * Bp * Dq;
-        m[6] = q.w * ud * (Aq * Aq - Bp * Bp);
-        m[7] = q.w * 2.0 * ud * Aq * Bp;
+        m[NDQ] = q.w * (1.0 - ud) * Dq;
+        m[2 * NDQ] = q.w * (1.0 - ud) * Aq;
+        m[3 * NDQ] = q.w * 2.0 * ud * Aq * Dq;
+        m[4 * NDQ] = q.w * (1.0 - ud) * Bp;
+        m[5 * NDQ] = q.w * 2.0 * ud * Bp * Dq;
+        m[6 * NDQ] = q.w * ud * (Aq * Aq - Bp * Bp);
+        m[7 * NDQ] = q.w * 2.0 * ud * Aq * Bp;
         // normalisation: the curve at quadrature (phase 0.25: c = 0, s = 1)
         {
             const double b = W.si * q.y, d = W.ci * q.z;
@@ -842,14 +843,14 @@ __global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __g
             const double cen = (im & 1) ? -psi : psi, hw = (im & 2) ? hm : hp;
             double ko = INFINITY, kc = INFINITY;
             if (hw >= 0.5) {
-                donor_image_moments(m, im, 1.0, base);  // always faces the observer
+                donor_image_moments(m, NDQ, im, 1.0, base);  // always faces the observer
             } else if (hw > 0.0) {
                 double o = cen - hw, c2 = cen + hw;
                 o -= rint(o);
                 c2 -= rint(c2);
                 if (o >= 0.5) o -= 1.0;
                 if (c2 >= 0.5) c2 -= 1.0;
-                if (o > c2) donor_image_moments(m, im, 1.0, base);  // the interval holds phase -0.5: facing at the start
+                if (o > c2) donor_image_moments(m, NDQ, im, 1.0, base);  // the interval holds phase -0.5: facing at the start
                 if (o != c2) {
                     ko = nextafter(o, 1.0);  // opens just after o: applies to phase x iff o < x
                     kc = c2;                 // closed from c2 on:  applies iff c2 <= x
@@ -957,7 +958,7 @@ __global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __g
             const int x = r0 + tid * EP + q;
             if (x < nb) {
                 const int id = sid[x];
-                donor_image_moments(qm + 8 * (id >> 3), (id >> 1) & 3, (id & 1) ? -1.0 : 1.0, tot);
+                donor_image_moments(qm + (id >> 3), NDQ, (id >> 1) & 3, (id & 1) ? -1.0 : 1.0, tot);
             }
         }
         double run[5];
@@ -989,7 +990,7 @@ __global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __g
             const int x = r0 + tid * EP + q;
             if (x < nb) {
                 const int id = sid[x];
-                donor_image_moments(qm + 8 * (id >> 3), (id >> 1) & 3, (id & 1) ? -1.0 : 1.0, run);
+                donor_image_moments(qm + (id >> 3), NDQ, (id >> 1) & 3, (id & 1) ? -1.0 : 1.0, run);
                 key_out[x] = skey[x];
                 double2* row = (double2*)(mom_out + (size_t)(x + 1) * 6);
                 row[0] = make_double2(run[0] * inv_norm, run[1] * inv_norm);
@@ -1030,6 +1031,7 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
     __shared__ double red[NW];
     __shared__ long long wtot[NA][NW];
     __shared__ long long s_carry[NA], s_next[NA];
+    __shared__ JobConst C;  // (in shared memory: a dozen doubles every thread reads but need not hold in registers)
 
     const long long job = blockIdx.x;
     const long long w = job / A.L.n_ecl;
@@ -1055,7 +1057,8 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
         }
         return;
     }
-    const JobConst C = A.jc[job];
+    if (tid < (int)(sizeof(JobConst) / sizeof(double))) ((double*)&C)[tid] = ((const double*)(A.jc + job))[tid];
+    __syncthreads();
     const long long* wq_tab = A.wq + job * (G.n_wd_rings + G.n_disc_r + G.n_bs);
     const EventRec* ivp = A.ivp + job * A.ni_total;
     const int n_tile_iv = A.ni_total;
@@ -1107,13 +1110,15 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
                     const long long nq = -wq;
                     const int hi_p = (int)(wq >> kLimbBits), lo_p = (int)(wq & kLimbMask);
                     const int hi_n = (int)(nq >> kLimbBits), lo_n = (int)(nq & kLimbMask);
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
+                    int* cell0 = cells + 2 * arr - m0 * CW;
+                    // (nearly every record is one piece: it opens once and closes once)
+                    const int nfld = dec_pos(rec.x, 2) == kNoEvent ? 2 : 6;
+                    for (int k = 0; k < nfld; ++k) {
                         const int p = dec_pos(k < 3 ? rec.x : rec.y, k % 3);
                         if (p == kAtStart) {
                             if (seg == 0) base[arr] += wq;
                         } else if (p >= m0 && p < m1) {
-                            int* cell = cells + (p - m0) * CW + 2 * arr;
+                            int* cell = cell0 + p * CW;
                             atomicAdd(cell, (k & 1) ? hi_n : hi_p);
                             atomicAdd(cell + 1, (k & 1) ? lo_n : lo_p);
                         }
@@ -1185,10 +1190,13 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
         {
             // phase, cos, sin of the segment's samples, thread-major: sample (tid, r) at [r][tid]
             const double* __restrict__ seg_tr = A.smp.seg_tr + (size_t)(ch0 + seg) * 3 * Ms + tid;
-            int kd = -1;              // donor table row in dm
-            double knext = -INFINITY;  // the first break point after that row (+inf: none): nothing changes below it
+            // Donor table state: dm = moments of row kd (the break points at or before the last sample's phase),
+            // knext = the next break point; row kd + 1 and the break point after it (dn, knext2) are fetched ahead,
+            // so that crossing a break point costs no memory latency.
+            int kd = -1;
+            double knext = -INFINITY, knext2 = INFINITY;
             double xprev = 2.0;
-            double dm[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            double dm[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, dn[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             double x0 = __ldg(seg_tr), c0 = __ldg(seg_tr + Ms), s0 = __ldg(seg_tr + 2 * Ms);
 #pragma unroll 1
             for (int r = 0; r < RP; ++r) {
@@ -1212,7 +1220,8 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
                     }
                 }
                 if (p < len) {
-                    const double cc = c0 * C.cphi + s0 * C.sphi, ss = s0 * C.cphi - c0 * C.sphi;
+                    const double cphi = C.cphi, sphi = C.sphi;
+                    const double cc = c0 * cphi + s0 * sphi, ss = s0 * cphi - c0 * sphi;
                     double f3 = 0.0;
                     if (do_don) {
                         // the donor's moments at this sample: table row = number of break points at or before its phase
@@ -1220,16 +1229,34 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
                         x -= rint(x);
                         if (x >= 0.5) x -= 1.0;
                         if (x >= knext || x < xprev) {
-                            int k2 = kd + 1;
-                            if (kd < 0 || x < xprev || x - xprev > 2.0 / kDonorBins)
-                                k2 = (int)__ldg(dfirst + donor_bin(x));  // first sample / the phase wrapped / a long jump
-                            double kn = INFINITY;
-                            while (k2 < nb && (kn = __ldg(dkey + k2)) <= x) ++k2;
-                            knext = k2 < nb ? kn : INFINITY;
-                            const double2* row = (const double2*)(dmom + (size_t)k2 * 6);
-                            const double2 a01 = __ldg(row), a23 = __ldg(row + 1), a45 = __ldg(row + 2);
-                            dm[0] = a01.x; dm[1] = a01.y; dm[2] = a23.x; dm[3] = a23.y; dm[4] = a45.x;
-                            kd = k2;
+                            bool fetch = true;
+                            if (kd >= 0 && x >= xprev && x < knext2) {
+                                // one break point crossed: the row fetched ahead
+                                ++kd;
+#pragma unroll
+                                for (int a = 0; a < 5; ++a) dm[a] = dn[a];
+                                knext = knext2;
+                            } else {
+                                // first sample / the phase wrapped / several break points at once: look the row up
+                                int k2 = kd + 1;
+                                if (kd < 0 || x < xprev || x - xprev > 2.0 / kDonorBins) k2 = (int)__ldg(dfirst + donor_bin(x));
+                                double kn = INFINITY;
+                                while (k2 < nb && (kn = __ldg(dkey + k2)) <= x) ++k2;
+                                knext = k2 < nb ? kn : INFINITY;
+                                const double2* row = (const double2*)(dmom + (size_t)k2 * 6);
+                                const double2 a01 = __ldg(row), a23 = __ldg(row + 1), a45 = __ldg(row + 2);
+                                dm[0] = a01.x; dm[1] = a01.y; dm[2] = a23.x; dm[3] = a23.y; dm[4] = a45.x;
+                                kd = k2;
+                                fetch = kd < nb;
+                                if (!fetch) knext2 = INFINITY;
+                            }
+                            if (fetch && kd < nb) {
+                                // row kd + 1 and the break point after it, for the next crossing
+                                knext2 = kd + 1 < nb ? __ldg(dkey + kd + 1) : INFINITY;
+                                const double2* row = (const double2*)(dmom + (size_t)(kd + 1) * 6);
+                                const double2 a01 = __ldg(row), a23 = __ldg(row + 1), a45 = __ldg(row + 2);
+                                dn[0] = a01.x; dn[1] = a01.y; dn[2] = a23.x; dn[3] = a23.y; dn[4] = a45.x;
+                            }
                         }
                         xprev = x;
                         f3 = C.f_rs * (dm[0] + dm[1] * cc + dm[2] * ss + dm[3] * (cc * cc) + dm[4] * (cc * ss));
@@ -1269,7 +1296,7 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
             }
             if (MODE == 0) {
                 const double dy = __ldg(A.smp.y + lc0 + j) - acc[0];
-                const double r = dy / __ldg(A.smp.ye + lc0 + j);
+                const double r = dy * __ldg(A.smp.iye + lc0 + j);
                 chi += r * r;
                 if (A.gp_resid) A.gp_resid[(lc0 + __ldg(A.smp.gp_slot + lc0 + j)) * A.n_walkers + w] = dy;
             } else {

@@ -69,7 +69,7 @@ struct SampleSet {
         DevSamples v;
         v.lc_off = lc_off.as<long long>();
         v.y = y.as<double>();
-        v.ye = ye.as<double>();
+        v.iye = ye.as<double>();
         v.S = S.as<double>();
         v.cosS = cosS.as<double>();
         v.sinS = sinS.as<double>();
@@ -95,7 +95,8 @@ enum { ST_WALKER = 0, ST_STREAM, ST_ELEMENTS, ST_FLUX, ST_FINISH, ST_COUNT };
 struct Lane {
     cudaStream_t st = nullptr, side = nullptr, side2 = nullptr;  // side: the serial stream ODE beside the element
                                                                  // solves; side2: the white-dwarf centre's LOS
-    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, done_ev = nullptr, wd_ev = nullptr;
+    cudaEvent_t fork_ev = nullptr, fork2_ev = nullptr, join_ev = nullptr, done_ev = nullptr, wd_ev = nullptr, don_ev = nullptr;
+    cudaEvent_t dev[3] = {};  // trace of the donor chain on the second side stream
     cudaEvent_t ev[ST_COUNT + 1] = {};
     cudaEvent_t kev[LFB_K_COUNT + 1] = {}, sev[2] = {};  // per-kernel trace (lfb_set_trace), side-stream pair
     bool kev_set[LFB_K_COUNT + 1] = {};
@@ -115,6 +116,10 @@ struct Lane {
         if ((e = cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&wd_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&don_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&fork2_ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        for (int i = 0; i < 3; ++i)
+            if ((e = cudaEventCreate(&dev[i])) != cudaSuccess) return e;
         for (int i = 0; i <= ST_COUNT; ++i)
             if ((e = cudaEventCreate(&ev[i])) != cudaSuccess) return e;
         for (int i = 0; i <= LFB_K_COUNT; ++i)
@@ -137,6 +142,10 @@ struct Lane {
         if (join_ev) cudaEventDestroy(join_ev);
         if (done_ev) cudaEventDestroy(done_ev);
         if (wd_ev) cudaEventDestroy(wd_ev);
+        if (don_ev) cudaEventDestroy(don_ev);
+        if (fork2_ev) cudaEventDestroy(fork2_ev);
+        for (int i = 0; i < 3; ++i)
+            if (dev[i]) cudaEventDestroy(dev[i]);
         if (side) cudaStreamDestroy(side);
         if (side2) cudaStreamDestroy(side2);
         if (st) cudaStreamDestroy(st);
@@ -311,7 +320,7 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int NT, int RP, int n_ecl
             const int j = pt[jj];
             pt_index[o + jj] = j;
             ys[o + jj] = y ? y[o + j] : 0.0;
-            yes[o + jj] = ye ? ye[o + j] : 1.0;
+            yes[o + jj] = ye ? 1.0 / ye[o + j] : 1.0;  // the kernel multiplies
             // the point is wrapped as a whole: its samples stay together on the axis
             for (int k = 0; k < K; ++k) raw[jj * K + k] = wph[j] + G.quad_off[k] * (width ? width[o + j] : 0.0);
         }
@@ -468,35 +477,11 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
             ln.kev_set[i] = true;                    \
         }                                            \
     } while (0)
-    if (record) CK(cudaEventRecord(ln.ev[ST_WALKER], st));
-    KREC(LFB_K_WALKER);
-    walker_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, what, flags, n, d_theta, ln.ws.as<WalkerScal>());
-    if (record) CK(cudaEventRecord(ln.ev[ST_STREAM], st));
-    KREC(LFB_K_JOBCHECK);
-    jobcheck_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, st>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
-                                                                      ln.js.as<JobScal>());
-    // fork: the ballistic-stream ODE (one serial integration per job) runs beside the element solves
-    CK(cudaEventRecord(ln.fork_ev, st));
-    CK(cudaStreamWaitEvent(ln.side, ln.fork_ev, 0));
-    CK(cudaStreamWaitEvent(ln.side2, ln.fork_ev, 0));
-    if (what != LFB_LN_PRIOR && !(flags & LFB_FLAG_SKIP_WD)) {
-        wdcentre_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ln.side2>>>(what, n, ln.ws.as<WalkerScal>());
-        h->launches++;
-    }
-    CK(cudaEventRecord(ln.wd_ev, ln.side2));
-    if (trace) CK(cudaEventRecord(ln.sev[0], ln.side));
-    if (njobs < h->stream_lanes_below)
-        stream_kernel<true><<<(unsigned)((njobs * 8 + 63) / 64), 64, 0, ln.side>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
-                                                                      ln.js.as<JobScal>());
-    else
-        stream_kernel<false><<<(unsigned)((njobs + 63) / 64), 64, 0, ln.side>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
-                                                                      ln.js.as<JobScal>());
-    if (trace) CK(cudaEventRecord(ln.sev[1], ln.side));
-    CK(cudaEventRecord(ln.join_ev, ln.side));
-    h->launches += 3;
-    if (record) CK(cudaEventRecord(ln.ev[ST_ELEMENTS], st));
+    // argument blocks of the element and flux stages (buffers sized before anything is launched)
+    ElemArgs E;
+    FluxArgs A;
+    const bool gp = h->gp_on && mode == 0;
     if (what != LFB_LN_PRIOR) {
-        ElemArgs E;
         E.L = L;
         E.G = G;
         E.what = what;
@@ -511,28 +496,6 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         E.disc_io = ln.disc_io.as<double2>();
         E.bs_io = ln.bs_io.as<double2>();
         E.bs_b = ln.bs_b.as<double>();
-        auto blocks = [&](long long units, int per_unit, bool whole_warps = false) {
-            const long long padded = whole_warps ? (per_unit + 31) & ~31 : per_unit;
-            return (unsigned)((units * padded + kElemThreads - 1) / kElemThreads);
-        };
-        if (!(flags & LFB_FLAG_SKIP_DISC)) {
-            KREC(LFB_K_ELEM_DISC);
-            elements_kernel<1><<<blocks(njobs, G.n_disc_half, true), kElemThreads, 0, st>>>(E);
-            h->launches++;
-        }
-        if (!(flags & LFB_FLAG_SKIP_WD)) {
-            CK(cudaStreamWaitEvent(st, ln.wd_ev, 0));  // the white-dwarf centre's lines of sight (side stream)
-            KREC(LFB_K_ELEM_WD);
-            elements_kernel<0><<<blocks(n, G.n_wd_half), kElemThreads, 0, st>>>(E);
-            h->launches++;
-        }
-        if (!(flags & LFB_FLAG_SKIP_DONOR)) {
-            KREC(LFB_K_ELEM_DONOR);
-            elements_kernel<3><<<blocks(n, G.n_donor_q), kElemThreads, 0, st>>>(E);
-            h->launches++;
-        }
-        if (record) CK(cudaEventRecord(ln.ev[ST_FLUX], st));
-        FluxArgs A;
         A.L = L;
         A.G = G;
         A.smp = ss.view();
@@ -568,7 +531,6 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         A.chisq_job = ln.chi_part.as<double>();
         A.flux_tot = d_tot;
         A.flux_comp = d_comp;
-        const bool gp = h->gp_on && mode == 0;
         A.gp_resid = nullptr;
         A.n_walkers = n;
         A.gp_dist = h->gp_dist.as<double>();
@@ -577,16 +539,70 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
             CK(ln.gp_resid.reserve(sizeof(double) * (size_t)ss.total * (size_t)n));
             A.gp_resid = ln.gp_resid.as<double>();
         }
-        if (!(flags & LFB_FLAG_SKIP_DONOR)) {
-            // the donor's curve as a table over phase, once per walker (every eclipse of the walker reads it)
-            if (8 * G.n_donor_q > 65535) return fail(h, LFB_EINVAL, "donor grid too dense (16-bit break-point index)");
-            const size_t dsm = 224 * (size_t)G.n_donor_q + 4 * (kDonorBins + 1) + 64;
-            if (dsm > (size_t)h->max_smem - 2048) return fail(h, LFB_EINVAL, "donor grid too dense for the table kernel's shared memory");
-            KREC(LFB_K_DONOR_TABLE);
-            CK(cudaFuncSetAttribute(donor_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-            donor_table_kernel<<<(unsigned)n, kDonorThreads, dsm, st>>>(A);
+        if (8 * G.n_donor_q > 65535) return fail(h, LFB_EINVAL, "donor grid too dense (16-bit break-point index)");
+        if (G.n_wd + G.n_disc > 32767 || G.n_bs > 32767)
+            return fail(h, LFB_EINVAL, "surface grid too dense: at most 32767 tiles per running sum (16-bit low limb)");
+    }
+    auto blocks = [&](long long units, int per_unit, bool whole_warps = false) {
+        const long long padded = whole_warps ? (per_unit + 31) & ~31 : per_unit;
+        return (unsigned)((units * padded + kElemThreads - 1) / kElemThreads);
+    };
+    if (record) CK(cudaEventRecord(ln.ev[ST_WALKER], st));
+    KREC(LFB_K_WALKER);
+    walker_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, what, flags, n, d_theta, ln.ws.as<WalkerScal>());
+    // fork 1: what needs the walker scalars only runs beside everything else on a second side stream -- the
+    // white-dwarf centre's lines of sight (Newton starts of its tiles), then the donor: its tiles and its phase table
+    CK(cudaEventRecord(ln.fork2_ev, st));
+    CK(cudaStreamWaitEvent(ln.side2, ln.fork2_ev, 0));
+    if (what != LFB_LN_PRIOR && !(flags & LFB_FLAG_SKIP_WD)) {
+        wdcentre_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ln.side2>>>(what, n, ln.ws.as<WalkerScal>());
+        h->launches++;
+    }
+    CK(cudaEventRecord(ln.wd_ev, ln.side2));
+    if (what != LFB_LN_PRIOR && !(flags & LFB_FLAG_SKIP_DONOR)) {
+        const size_t dsm = 224 * (size_t)G.n_donor_q + 4 * (kDonorBins + 1) + 64;
+        if (dsm > (size_t)h->max_smem - 2048) return fail(h, LFB_EINVAL, "donor grid too dense for the table kernel's shared memory");
+        if (trace) CK(cudaEventRecord(ln.dev[0], ln.side2));
+        elements_kernel<3><<<blocks(n, G.n_donor_q), kElemThreads, 0, ln.side2>>>(E);
+        if (trace) CK(cudaEventRecord(ln.dev[1], ln.side2));
+        // the donor's curve as a table over phase, once per walker (every eclipse of the walker reads it)
+        CK(cudaFuncSetAttribute(donor_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+        donor_table_kernel<<<(unsigned)n, kDonorThreads, dsm, ln.side2>>>(A);
+        if (trace) CK(cudaEventRecord(ln.dev[2], ln.side2));
+        h->launches += 2;
+    }
+    CK(cudaEventRecord(ln.don_ev, ln.side2));
+    if (record) CK(cudaEventRecord(ln.ev[ST_STREAM], st));
+    KREC(LFB_K_JOBCHECK);
+    jobcheck_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, st>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
+                                                                      ln.js.as<JobScal>());
+    // fork 2: the ballistic-stream ODE (one serial integration per job) runs beside the element solves
+    CK(cudaEventRecord(ln.fork_ev, st));
+    CK(cudaStreamWaitEvent(ln.side, ln.fork_ev, 0));
+    if (trace) CK(cudaEventRecord(ln.sev[0], ln.side));
+    if (njobs < h->stream_lanes_below)
+        stream_kernel<true><<<(unsigned)((njobs * 8 + 63) / 64), 64, 0, ln.side>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
+                                                                      ln.js.as<JobScal>());
+    else
+        stream_kernel<false><<<(unsigned)((njobs + 63) / 64), 64, 0, ln.side>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
+                                                                      ln.js.as<JobScal>());
+    if (trace) CK(cudaEventRecord(ln.sev[1], ln.side));
+    CK(cudaEventRecord(ln.join_ev, ln.side));
+    h->launches += 3;
+    if (record) CK(cudaEventRecord(ln.ev[ST_ELEMENTS], st));
+    if (what != LFB_LN_PRIOR) {
+        if (!(flags & LFB_FLAG_SKIP_DISC)) {
+            KREC(LFB_K_ELEM_DISC);
+            elements_kernel<1><<<blocks(njobs, G.n_disc_half, true), kElemThreads, 0, st>>>(E);
             h->launches++;
         }
+        if (!(flags & LFB_FLAG_SKIP_WD)) {
+            CK(cudaStreamWaitEvent(st, ln.wd_ev, 0));  // the white-dwarf centre's lines of sight (side stream)
+            KREC(LFB_K_ELEM_WD);
+            elements_kernel<0><<<blocks(n, G.n_wd_half), kElemThreads, 0, st>>>(E);
+            h->launches++;
+        }
+        if (record) CK(cudaEventRecord(ln.ev[ST_FLUX], st));
         // everything of the flux preparation that does not need the strip goes before the join with the
         // stream ODE, so that the main stream has work while the ODE finishes
         KREC(LFB_K_PREP);
@@ -607,9 +623,8 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         h->launches += 2;
         const FluxShape fs = flux_shape(h, mode);
         const size_t smem = (size_t)fs.NT * fs.RP * (mode ? 32 : 16);
-        if (G.n_wd + G.n_disc > 32767 || G.n_bs > 32767)
-            return fail(h, LFB_EINVAL, "surface grid too dense: at most 32767 tiles per running sum (16-bit low limb)");
         const dim3 fgrid((unsigned)njobs);
+        CK(cudaStreamWaitEvent(st, ln.don_ev, 0));  // the donor tables (second side stream)
         KREC(LFB_K_FLUX);
 #define LFB_LAUNCH_FLUX(MODE, NT, RP, CTAS)                                                                               \
     do {                                                                                                                  \
@@ -631,7 +646,7 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         CK(cudaStreamWaitEvent(st, ln.join_ev, 0));
         if (record) CK(cudaEventRecord(ln.ev[ST_FLUX], st));
     }
-    CK(cudaStreamWaitEvent(st, ln.wd_ev, 0));  // the second side stream always rejoins (stream capture needs it)
+    CK(cudaStreamWaitEvent(st, ln.don_ev, 0));  // the second side stream always rejoins (stream capture needs it)
     if (record) CK(cudaEventRecord(ln.ev[ST_FINISH], st));
     KREC(LFB_K_FINISH);
     if (d_out || d_chi) {
@@ -893,6 +908,12 @@ int lfb_last_trace_ms(lfb_handle* h, float out[LFB_K_COUNT + 1])
     if (cudaEventElapsedTime(&out[LFB_K_COUNT], ln.sev[0], ln.sev[1]) != cudaSuccess) {
         cudaGetLastError();
         out[LFB_K_COUNT] = -1.0f;
+    }
+    // the donor chain runs on the second side stream, beside the kernels above
+    if (cudaEventElapsedTime(&out[LFB_K_ELEM_DONOR], ln.dev[0], ln.dev[1]) != cudaSuccess ||
+        cudaEventElapsedTime(&out[LFB_K_DONOR_TABLE], ln.dev[1], ln.dev[2]) != cudaSuccess) {
+        cudaGetLastError();
+        out[LFB_K_ELEM_DONOR] = out[LFB_K_DONOR_TABLE] = -1.0f;
     }
     return LFB_OK;
 }

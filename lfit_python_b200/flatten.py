@@ -124,6 +124,15 @@ class VectorModel:
 
     __call__ = ln_prob
 
+    def ln_like_and_prob(self, theta):
+        """(ln_like, ln_prob) of every row from ONE pass -- what the reference hands ptemcee as (logl, logp)
+        (mcmcfit.py:264-270 passes ln_like and ln_prob).  Rows the priors reject get ln_like = 0 (they are not
+        evaluated, as in ptemcee's evaluator)."""
+        lnp, chi = self._eval(np.atleast_2d(theta), _cabi.LN_PROB, return_chisq=True)
+        skipped = np.isnan(chi).any(axis=1)
+        like = np.where(skipped, 0.0, -0.5 * np.where(np.isnan(chi), 0.0, chi).sum(axis=1))
+        return like, lnp
+
     def chisq(self, theta):
         """Per-eclipse chi-squared, shape (n, n_ecl) (SimpleEclipse.chisq for every leaf); for a GP
         tree, -2 ln L of every leaf."""

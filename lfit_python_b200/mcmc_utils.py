@@ -131,14 +131,27 @@ class EnsembleSampler:
         return self.naccepted / max(self.iterations, 1)
 
 
-def run_burnin(sampler, startPos, nSteps, storechain=False, progress=False):
-    """Advance nSteps without storing; returns (pos, prob, state) (mcmc_utils.py:114-132)."""
-    out = None
+def _sample_iter(sampler, startPos, nSteps, store, **kwargs):
+    """sampler.sample(...) with whichever keyword the sampler knows for storing the chain: emcee 3 and the
+    samplers here take store=, emcee 2 and ptemcee take storechain= (the reference tries one, then the other:
+    mcmc_utils.py:119-129,199-239)."""
+    if nSteps <= 0:
+        return
     try:
-        it = sampler.sample(startPos, iterations=nSteps, store=storechain)
+        it = sampler.sample(startPos, iterations=nSteps, store=store, **kwargs)
+        first = next(it)
     except TypeError:
-        it = sampler.sample(startPos, iterations=nSteps, storechain=storechain)
-    for out in it:
+        it = sampler.sample(startPos, iterations=nSteps, storechain=store, **kwargs)
+        first = next(it)
+    yield first
+    yield from it
+
+
+def run_burnin(sampler, startPos, nSteps, storechain=False, progress=False):
+    """Advance nSteps without storing; returns (pos, prob, state) (mcmc_utils.py:114-132).  A parallel-tempered
+    sampler returns (pos, logpost, logl) with a leading temperature axis."""
+    out = None
+    for out in _sample_iter(sampler, startPos, nSteps, storechain):
         pass
     return out[0], out[1], out[2]
 
@@ -177,7 +190,7 @@ def run_mcmc_save(sampler, startPos, nSteps, rState, file, col_names='', progres
             _cabi.chain_append(file, np.asarray(pending))
         pending.clear()
 
-    for pos, prob, state in sampler.sample(startPos, iterations=nSteps, store=True, **kwargs):
+    for pos, prob, state in _sample_iter(sampler, startPos, nSteps, True, **kwargs):
         pending.append(np.concatenate([pos, np.asarray(prob)[:, None]], axis=1))
         if len(pending) >= flush_every:
             flush()
@@ -203,6 +216,242 @@ def readchain(file, nskip=0, thin=1):
     npars = data.shape[1] - 1
     chain = data[:nprod * nwalkers, 1:].reshape((nprod, nwalkers, npars))
     return np.swapaxes(chain, 0, 1)[:, nskip::thin, :]
+
+
+def initialise_walkers_pt(p, scatter, nwalkers, ntemps, ln_prior, model, rng=None, max_rounds=200, verbose=True):
+    """A ball of walkers for every temperature, (ntemps, nwalkers, ndim); walkers violating the priors are
+    redrawn from the valid ones of the whole set (mcmc_utils.py:75-111).  ln_prior(matrix, model) is called
+    once per round on all ntemps x nwalkers rows."""
+    p = np.asarray(p, dtype=np.float64)
+    flat = initialise_walkers(p, scatter, nwalkers * ntemps, ln_prior, model, rng=rng, max_rounds=max_rounds,
+                              verbose=verbose)
+    return flat.reshape(ntemps, nwalkers, p.shape[0])
+
+
+def default_beta_ladder(ndim, ntemps, Tmax=None):
+    """Geometric ladder of inverse temperatures, beta_i = tstep ** -i.  ptemcee (not vendored in the reference
+    tree, call site mcmcfit.py:264-270) takes tstep from a table tuned for 25 % swap acceptance between
+    neighbouring temperatures of a Gaussian posterior and, beyond the table, from
+    1 + 2 sqrt(ln 4) / sqrt(ndim); that expression is used here for every ndim [the table itself is not
+    reproduced: pass `betas` for a pinned ladder].  With Tmax the ladder spans 1 .. Tmax in ntemps steps."""
+    if ntemps < 1:
+        raise ValueError("need at least one temperature")
+    if Tmax is not None and ntemps > 1:
+        tstep = float(Tmax) ** (1.0 / (ntemps - 1))
+    else:
+        tstep = 1.0 + 2.0 * np.sqrt(np.log(4.0)) / np.sqrt(ndim)
+    return tstep ** -np.arange(ntemps, dtype=np.float64)
+
+
+class PTSampler:
+    """Parallel-tempered affine-invariant ensemble sampler with ptemcee's call shape
+    (ptemcee.sampler.Sampler(nwalkers, dim, logl, logp, loglargs=, logpargs=, ntemps=), mcmcfit.py:264-270;
+    ptemcee is third-party and not vendored -- this is its published algorithm, Vousden, Farr & Mandel 2016,
+    restated): every temperature runs the stretch move on the tempered posterior beta * logl + logp (walkers
+    of even index proposed from those of odd index, then the reverse; z log-uniform on [1/a, a], acceptance
+    z^dim), then neighbouring temperatures try to swap walkers, hottest pair first.  Fixed ladder
+    (ptemcee's default when sample() is not asked to adapt).
+
+    vectorize=True: logl and logp take a (n, dim) matrix and return n values -- all ntemps x nwalkers / 2
+    proposals of a half-step are ONE call each (one CUDA pass); `joint`, if given, returns (logl, logp) of a
+    matrix in one call instead.  Walkers outside the prior (logp = -inf) are given logl = 0, as ptemcee does."""
+
+    def __init__(self, nwalkers, dim, logl, logp, ntemps=None, Tmax=None, betas=None, loglargs=(), logpargs=(),
+                 loglkwargs=None, logpkwargs=None, a=2.0, vectorize=False, joint=None, rng=None, pool=None):
+        if nwalkers % 2:
+            raise ValueError("The number of walkers must be even.")
+        if nwalkers < 2 * dim:
+            raise ValueError("The number of walkers must be greater than 2*dimension.")
+        self.nwalkers, self.dim, self.a = int(nwalkers), int(dim), float(a)
+        self.logl, self.logp, self.joint = logl, logp, joint
+        self.loglargs, self.logpargs = tuple(loglargs), tuple(logpargs)
+        self.loglkwargs, self.logpkwargs = dict(loglkwargs or {}), dict(logpkwargs or {})
+        self.vectorize, self.pool = vectorize, pool
+        if betas is None:
+            betas = default_beta_ladder(dim, ntemps if ntemps is not None else 1, Tmax)
+        self._betas = np.array(betas, dtype=np.float64)
+        self.ntemps = self._betas.shape[0]
+        self._random = np.random.default_rng() if rng is None else rng
+        self.reset()
+
+    def reset(self):
+        self._chain = []
+        self._logposterior, self._loglikelihood = [], []
+        self.nswap = np.zeros(self.ntemps)
+        self.nswap_accepted = np.zeros(self.ntemps)
+        self.nprop = np.zeros((self.ntemps, self.nwalkers))
+        self.nprop_accepted = np.zeros((self.ntemps, self.nwalkers))
+        self._p0 = self._logposterior0 = self._loglikelihood0 = None
+        self.time = 0
+
+    @property
+    def betas(self):
+        return self._betas
+
+    def _tempered_likelihood(self, logl, betas=None):
+        betas = self._betas if betas is None else betas
+        with np.errstate(invalid='ignore'):
+            out = logl * betas[:, None]
+        out[np.isnan(out)] = -np.inf
+        return out
+
+    def _evaluate(self, ps):
+        """(logl, logp) of positions ps (..., dim); walkers outside the prior are not asked for their likelihood."""
+        shape = ps.shape[:-1]
+        flat = np.ascontiguousarray(ps.reshape(-1, self.dim))
+        if self.joint is not None:
+            ll, lp = self.joint(flat)
+            ll, lp = np.array(ll, dtype=np.float64), np.array(lp, dtype=np.float64)
+        elif self.vectorize:
+            lp = np.array(self.logp(flat, *self.logpargs, **self.logpkwargs), dtype=np.float64)
+            ll = np.array(self.logl(flat, *self.loglargs, **self.loglkwargs), dtype=np.float64)
+        else:
+            mapper = self.pool.map if self.pool is not None else map
+            lp = np.array(list(mapper(lambda x: self.logp(x, *self.logpargs, **self.logpkwargs), flat)), dtype=np.float64)
+            ll = np.zeros_like(lp)
+            ok = lp > -np.inf
+            ll[ok] = list(mapper(lambda x: self.logl(x, *self.loglargs, **self.loglkwargs), flat[ok]))
+        ll = np.where(lp == -np.inf, 0.0, ll)
+        if np.isnan(lp).any():
+            raise ValueError('Prior function returned NaN.')
+        if np.isnan(ll).any():
+            raise ValueError('Log likelihood function returned NaN.')
+        return ll.reshape(shape), lp.reshape(shape)
+
+    def sample(self, p0=None, iterations=1, thin=1, storechain=True, adapt=False, **kwargs):
+        """Advance the chains; yields (p, logpost, logl) after every iteration, shapes (ntemps, nwalkers, dim),
+        (ntemps, nwalkers), (ntemps, nwalkers)."""
+        if 'store' in kwargs:
+            # the reference calls sample(..., store=True) first and falls back to storechain= on any exception
+            # (mcmc_utils.py:199,220): ptemcee raises here, so does this
+            raise TypeError("sample() got an unexpected keyword argument 'store'")
+        if adapt:
+            raise NotImplementedError("adaptive temperature ladders are not implemented (ptemcee's default is a fixed ladder)")
+        if p0 is None:
+            if self._p0 is None:
+                raise ValueError('Initial walker positions not specified.')
+            p, logpost, logl = self._p0, self._logposterior0, self._loglikelihood0
+        else:
+            p = np.array(p0, dtype=np.float64, copy=True)
+            if p.shape != (self.ntemps, self.nwalkers, self.dim):
+                raise ValueError("incompatible input dimensions: expected (ntemps, nwalkers, dim)")
+            logl, logp = self._evaluate(p)
+            logpost = self._tempered_likelihood(logl) + logp
+            if (logp == -np.inf).any():
+                raise ValueError('Attempting to start with samples outside posterior support.')
+        for i in range(iterations):
+            for j in (0, 1):
+                jupdate, jsample = j, (j + 1) % 2
+                pupdate, psample = p[:, jupdate::2, :], p[:, jsample::2, :]
+                half = self.nwalkers // 2
+                zs = np.exp(self._random.uniform(low=-np.log(self.a), high=np.log(self.a), size=(self.ntemps, half)))
+                qs = np.empty((self.ntemps, half, self.dim))
+                for k in range(self.ntemps):
+                    js = self._random.integers(0, half, size=half)
+                    qs[k] = psample[k, js, :] + zs[k, :, None] * (pupdate[k] - psample[k, js, :])
+                qslogl, qslogp = self._evaluate(qs)
+                qslogpost = self._tempered_likelihood(qslogl) + qslogp
+                with np.errstate(invalid='ignore'):
+                    logpaccept = self.dim * np.log(zs) + qslogpost - logpost[:, jupdate::2]
+                logr = np.log(self._random.uniform(low=0.0, high=1.0, size=(self.ntemps, half)))
+                accepts = logr < logpaccept
+                pupdate[accepts] = qs[accepts]          # (views: p is updated in place)
+                logpost[:, jupdate::2][accepts] = qslogpost[accepts]
+                logl[:, jupdate::2][accepts] = qslogl[accepts]
+                self.nprop[:, jupdate::2] += 1.0
+                self.nprop_accepted[:, jupdate::2] += accepts
+            self._temperature_swaps(p, logpost, logl)
+            self.time += 1
+            if storechain and (i + 1) % thin == 0:
+                self._chain.append(p.copy())
+                self._logposterior.append(logpost.copy())
+                self._loglikelihood.append(logl.copy())
+            self._p0, self._logposterior0, self._loglikelihood0 = p, logpost, logl
+            yield p, logpost, logl
+
+    def _temperature_swaps(self, p, logpost, logl):
+        """Neighbouring temperatures exchange walkers, hottest pair first: walker a of temperature i and walker b
+        of temperature i - 1 swap with probability min(1, exp((beta_{i-1} - beta_i) (logl_a - logl_b)))."""
+        for i in range(self.ntemps - 1, 0, -1):
+            dbeta = self._betas[i - 1] - self._betas[i]
+            iperm = self._random.permutation(self.nwalkers)
+            i1perm = self._random.permutation(self.nwalkers)
+            raccept = np.log(self._random.uniform(size=self.nwalkers))
+            with np.errstate(invalid='ignore'):
+                paccept = dbeta * (logl[i, iperm] - logl[i - 1, i1perm])
+            self.nswap[i] += self.nwalkers
+            self.nswap[i - 1] += self.nwalkers
+            asel = paccept > raccept
+            nacc = int(asel.sum())
+            self.nswap_accepted[i] += nacc
+            self.nswap_accepted[i - 1] += nacc
+            a, b = iperm[asel], i1perm[asel]
+            ptemp, ltemp, prtemp = p[i, a, :].copy(), logl[i, a].copy(), logpost[i, a].copy()
+            p[i, a, :] = p[i - 1, b, :]
+            logl[i, a] = logl[i - 1, b]
+            logpost[i, a] = logpost[i - 1, b] - dbeta * logl[i - 1, b]
+            p[i - 1, b, :] = ptemp
+            logl[i - 1, b] = ltemp
+            logpost[i - 1, b] = prtemp + dbeta * ltemp
+
+    def run_mcmc(self, p0=None, iterations=1, **kw):
+        out = None
+        for out in self.sample(p0, iterations=iterations, **kw):
+            pass
+        return out
+
+    @property
+    def chain(self):
+        """(ntemps, nwalkers, nsteps, dim)"""
+        if not self._chain:
+            return np.empty((self.ntemps, self.nwalkers, 0, self.dim))
+        return np.moveaxis(np.asarray(self._chain), 0, 2)
+
+    @property
+    def flatchain(self):
+        """(ntemps, nwalkers * nsteps, dim); the reference takes flatchain[0] (mcmcfit.py:328)."""
+        c = self.chain
+        return c.reshape(self.ntemps, -1, self.dim)
+
+    @property
+    def logprobability(self):
+        return np.moveaxis(np.asarray(self._logposterior), 0, 2) if self._logposterior else np.empty((self.ntemps, self.nwalkers, 0))
+
+    @property
+    def loglikelihood(self):
+        return np.moveaxis(np.asarray(self._loglikelihood), 0, 2) if self._loglikelihood else np.empty((self.ntemps, self.nwalkers, 0))
+
+    @property
+    def tswap_acceptance_fraction(self):
+        return self.nswap_accepted / np.maximum(self.nswap, 1)
+
+    @property
+    def acceptance_fraction(self):
+        return self.nprop_accepted / np.maximum(self.nprop, 1)
+
+
+def run_ptmcmc_save(sampler, startPos, nSteps, file, progress=False, col_names='', flush_every=16, **kwargs):
+    """Run a parallel-tempered chain and save the chain of the first temperature (beta = 1: the only one that
+    samples the posterior) in the reference's format (mcmc_utils.py:186-239), `flush_every` steps per write."""
+    from . import _cabi
+    if file:
+        with open(file, "w") as f:
+            f.write(col_names)
+            if col_names:
+                f.write("\n")
+    pending = []
+
+    def flush():
+        if file and pending:
+            _cabi.chain_append(file, np.asarray(pending))
+        pending.clear()
+
+    for pos, prob, like in _sample_iter(sampler, startPos, nSteps, True, **kwargs):
+        pending.append(np.concatenate([pos[0], np.asarray(prob[0])[:, None]], axis=1))
+        if len(pending) >= flush_every:
+            flush()
+    flush()
+    return sampler
 
 
 class DeviceSampler:

@@ -75,8 +75,8 @@ def main(argv=None):
     to_fit = int(cfg['fit'])
     double_burnin = bool(int(cfg['double_burnin']))
     comp_scat = bool(int(cfg['comp_scat']))
-    if bool(int(cfg.get('usePT', 0))):
-        raise NotImplementedError("parallel tempering (ptemcee) is outside this package's hot path; set usePT = 0")
+    use_pt = bool(int(cfg.get('usePT', 0)))
+    ntemps = int(cfg.get('ntemps', 1))
 
     eclipses = model.search_node_type('Eclipse')
     dof = int(np.sum([e.lc.n_data for e in eclipses]) - len(model.dynasty_par_names) - 1)
@@ -101,6 +101,25 @@ def main(argv=None):
         sys.exit(1)
     rng = np.random.default_rng(args.seed)
     s1 = scatter_vector(model, scatter_1, comp_scat)
+    col_names = "walker_no " + ' '.join(model.dynasty_par_names) + ' ln_prob'
+    if use_pt:
+        # parallel tempering (mcmcfit.py:251-270): ntemps x nwalkers rows per half-step are one CUDA pass.  As in
+        # the reference, ptemcee's "likelihood" is ln_like and its "prior" is ln_prob (sic).
+        print("MCMC using parallel tempering at {} levels, for {} total walkers.".format(ntemps, nwalkers * ntemps))
+        p0 = utils.initialise_walkers_pt(pars, s1, nwalkers, ntemps, ln_prior, model, rng=rng)
+        sampler = utils.PTSampler(nwalkers, npars, ln_like, ln_prob, loglargs=(model,), logpargs=(model,), ntemps=ntemps,
+                                  vectorize=True, joint=vec.ln_like_and_prob, rng=rng)
+        print("\n\nExecuting the burn-in phase...")
+        pos, prob, state = utils.run_burnin(sampler, p0, nburn)
+        if double_burnin:
+            print("Executing the second burn-in phase")
+            p0 = utils.initialise_walkers_pt(pos[0][np.argmax(prob[0])], s1 * (scatter_2 / scatter_1), nwalkers, ntemps,
+                                             ln_prior, model, rng=rng)
+            pos, prob, state = utils.run_burnin(sampler, p0, nburn)
+        sampler.reset()
+        print("Starting the main MCMC chain.")
+        utils.run_ptmcmc_save(sampler, pos, nprod, "chain_prod.txt", col_names=col_names)
+        return sampler
     p0 = utils.initialise_walkers(pars, s1, nwalkers, ln_prior, model, rng=rng)
     sampler = utils.EnsembleSampler(nwalkers, npars, ln_prob, args=(model,), vectorize=True, rng=rng)
     print("\n\nExecuting the burn-in phase...")
@@ -112,7 +131,6 @@ def main(argv=None):
         pos, prob, state = utils.run_burnin(sampler, p0, nburn)
     sampler.reset()
     print("Starting the main MCMC chain.")
-    col_names = "walker_no " + ' '.join(model.dynasty_par_names) + ' ln_prob'
     utils.run_mcmc_save(sampler, pos, nprod, state, "chain_prod.txt", col_names=col_names)
     return sampler
 

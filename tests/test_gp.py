@@ -244,6 +244,35 @@ def test_driver_runs_end_to_end(tmp_path, monkeypatch, capsys, use_gp):
     assert np.allclose(chain[:, -1, :ndim], sampler.chain[:, -1, :], rtol=1e-5, atol=1e-6)   # "%f"-style file precision
 
 
+@pytest.mark.gpu
+def test_driver_runs_parallel_tempering(tmp_path, monkeypatch, capsys):
+    """usePT = 1 (mcmcfit.py:251-270,319-328): ntemps x nwalkers rows per half-step in one CUDA pass; the chain
+    file holds the first temperature."""
+    from lfit_python_b200 import mcmcfit, mcmc_utils
+    path = write_input(tmp_path)
+    txt = open(path).read().replace("fit = 0", "fit = 1").replace("nburn = 10", "nburn = 3")
+    txt = txt.replace("nprod = 10", "nprod = 5").replace("nwalkers = 40", "nwalkers = 96")
+    txt = txt.replace("usePT = 0", "usePT = 1").replace("ntemps = 1", "ntemps = 3")
+    assert "usePT = 1" in txt and "ntemps = 3" in txt
+    open(path, "w").write(txt)
+    monkeypatch.chdir(tmp_path)
+    sampler = mcmcfit.main([path, "--seed", "3"])
+    out = capsys.readouterr().out
+    assert "MCMC using parallel tempering at 3 levels, for 288 total walkers." in out
+    ndim = sampler.chain.shape[-1]
+    assert sampler.chain.shape == (3, 96, 5, ndim) and sampler.ntemps == 3
+    assert np.all(np.isfinite(sampler.logprobability)) and np.all(sampler.tswap_acceptance_fraction >= 0)
+    # the stored posterior of the first temperature is ln_like + ln_prob of the stored positions (the reference's
+    # wiring: ptemcee's "prior" is ln_prob, mcmcfit.py:266-268)
+    model = mcmcfit.construct_model(path)
+    last = np.ascontiguousarray(sampler.chain[0, :, -1, :])
+    want = mcmcfit.ln_like(last, model) + mcmcfit.ln_prob(last, model)
+    assert np.allclose(sampler.logprobability[0, :, -1], want, rtol=1e-12)
+    chain = mcmc_utils.readchain(str(tmp_path / "chain_prod.txt"))
+    assert chain.shape == (96, 5, ndim + 1)
+    assert np.allclose(chain[:, -1, :ndim], sampler.chain[0, :, -1, :], rtol=1e-5, atol=1e-6)
+
+
 def _gp_golden():
     g = np.load(os.path.join(HERE, "golden", "gp.npz"))
     return g, [dict((k, g["%s_%d" % (k, i)]) for k in ("x", "ye", "resid", "hyper", "gaps", "lnl")) for i in range(int(g["n_cases"]))]

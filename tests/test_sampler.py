@@ -145,3 +145,54 @@ def test_native_chain_text_equals_the_reference_expression():
     assert utils.format_step(rows[0, :, :3], rows[0, :, 3]) == utils.format_step_python(rows[0, :, :3], rows[0, :, 3])
     with pytest.raises(ValueError):
         _cabi.chain_text(np.zeros((3, 4)))
+
+
+# ---- parallel tempering (ptemcee's algorithm; /root/reference/mcmcfit.py:251-270, mcmc_utils.py:75-111,186-239) ----
+def test_parallel_tempering_samples_the_tempered_gaussians(tmp_path):
+    rng = np.random.default_rng(5)
+    mu, sig = np.array([1.0, -2.0, 0.5]), np.array([0.5, 2.0, 1.0])
+    calls = []
+
+    def logl(t):
+        calls.append(np.shape(t))
+        return gauss_lnprob(t, mu, 1 / sig)
+
+    def logp(t):
+        return np.where(np.all(np.abs(np.atleast_2d(t)) < 50, axis=1), 0.0, -np.inf)
+
+    s = utils.PTSampler(20, 3, logl, logp, ntemps=4, vectorize=True, rng=rng)
+    assert s.betas[0] == 1.0 and np.all(np.diff(s.betas) < 0) and s.ntemps == 4
+    p0 = utils.initialise_walkers_pt(mu, np.full(3, 0.1), 20, 4, lambda t, m: logp(t), None, rng=rng, verbose=False)
+    assert p0.shape == (4, 20, 3)
+    pos, prob, like = utils.run_burnin(s, p0, 400)
+    assert s.chain.shape == (4, 20, 0, 3)
+    # one vectorised call per half-step for ALL temperatures: 4 x 10 rows
+    assert set(calls[1:]) == {(40, 3)} and len(calls) == 1 + 2 * 400
+    s.reset()
+    path = tmp_path / "chain_prod.txt"
+    utils.run_ptmcmc_save(s, pos, 2500, str(path), col_names="walker_no a b c ln_prob")
+    c = s.chain
+    assert c.shape == (4, 20, 2500, 3) and s.flatchain.shape == (4, 20 * 2500, 3)
+    for t in range(4):   # temperature t samples N(mu, sig^2 / beta_t)
+        f = c[t, :, ::5, :].reshape(-1, 3)
+        assert np.allclose(f.mean(axis=0), mu, atol=5 * sig / np.sqrt(s.betas[t]) / np.sqrt(250))
+        assert np.allclose(f.std(axis=0) * np.sqrt(s.betas[t]), sig, rtol=0.12)
+    assert np.all(s.tswap_acceptance_fraction > 0.2) and np.all(s.tswap_acceptance_fraction < 0.8)
+    assert np.all(s.acceptance_fraction.mean(axis=1) > 0.3)
+    # the file holds the first temperature only, in the reference's format, and reads back
+    chain = utils.readchain(str(path))
+    assert chain.shape == (20, 2500, 4) and np.array_equal(chain[:, :, :3], c[0])
+    assert np.allclose(chain[:, :, 3], s.logprobability[0], atol=1e-6)
+
+
+def test_parallel_tempering_argument_checks():
+    with pytest.raises(ValueError):
+        utils.PTSampler(7, 2, gauss_lnprob, gauss_lnprob, ntemps=2)
+    s = utils.PTSampler(8, 2, lambda t: -0.5 * np.sum(t * t, axis=1), lambda t: np.where(t[:, 0] > 0, 0.0, -np.inf), ntemps=2,
+                        vectorize=True, rng=np.random.default_rng(1))
+    with pytest.raises(ValueError, match="outside posterior support"):
+        s.run_mcmc(np.full((2, 8, 2), -1.0), 1)
+    out = s.run_mcmc(np.abs(np.random.default_rng(2).standard_normal((2, 8, 2))) + 0.1, 50)
+    assert (out[0][..., 0] > 0).all()                 # walkers never leave the prior support
+    one = utils.PTSampler(8, 2, lambda t: -0.5 * np.sum(t * t, axis=1), lambda t: np.zeros(len(t)), vectorize=True)
+    assert one.ntemps == 1 and one.betas[0] == 1.0
