@@ -110,6 +110,9 @@ struct JobScal {
     double xs, ys;             // stream impact point
     double smax, smaxp, shi;   // bright-spot strip: profile peak, peak^exp2, strip length (scale units)
     int status;                // 0 ok, 1 walker invalid, 2 stream misses disc, 3 bad parameter, 4 not needed
+    int veto;                  // what the stream ODE found (it runs beside other kernels and writes nothing they read):
+                               // 0 nothing, 2 the stream misses the disc, 5 azimuth outside its window.  Merged into
+                               // status / the walker's ln_prior after the join (prep_strip_kernel).
     int ev_lo, ev_hi;          // sample positions spanned by the eclipse events of the job's tiles
 };
 
@@ -200,6 +203,7 @@ __global__ void jobcheck_kernel(DevLayout L, int what, int flags, long long njob
     J.xs = J.ys = 0.0;
     J.smax = J.smaxp = J.shi = 1.0;
     J.status = 0;
+    J.veto = 0;
     J.ev_lo = kNoEventPos;
     J.ev_hi = -2;
     const WalkerScal& W = ws[w];
@@ -237,7 +241,7 @@ __global__ void jobcheck_kernel(DevLayout L, int what, int flags, long long njob
 // batches too small to hide the ODE behind the element solves; else one thread per job.
 template <bool LANES>
 __global__ void stream_kernel(DevLayout L, int what, int flags, long long njobs, const double* __restrict__ theta,
-                              WalkerScal* ws, JobScal* js)
+                              const WalkerScal* __restrict__ ws, JobScal* js)
 {
     // (a group of lanes enters and leaves together)
     long long job = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> (LANES ? 3 : 0);
@@ -253,8 +257,7 @@ __global__ void stream_kernel(DevLayout L, int what, int flags, long long njobs,
     const bool hit = LANES ? bspot_lanes(R, rdisc_a, imp) : bspot(R, rdisc_a, imp);
     if (LANES && (threadIdx.x & 7) != 0) return;  // one lane of the group writes
     if (!hit) {
-        js[job].status = 2;  // the stream misses the disc (roche.bspot raises, CVModel.py:309-316)
-        if (what != LFB_LN_LIKE) ws[w].lnprior = -INFINITY;
+        js[job].veto = 2;  // the stream misses the disc (roche.bspot raises, CVModel.py:309-316)
         return;
     }
     js[job].xs = imp[0];
@@ -266,8 +269,27 @@ __global__ void stream_kernel(DevLayout L, int what, int flags, long long njobs,
         if (alpha < 0.0) alpha = 90.0 - alpha;
         double tangent = alpha + 90.0;
         double minaz = fmax(0.0, tangent - 80.0), maxaz = fmin(178.0, tangent + 80.0);
-        if (!(az >= minaz) || !(az <= maxaz)) ws[w].lnprior = -INFINITY;
+        if (!(az >= minaz) || !(az <= maxaz)) js[job].veto = 5;
     }
+}
+
+// veto_kernel: thread per walker, right after the join with the stream ODE: what the ODE found for the walker's
+// eclipses becomes part of the walker's state -- a stream that misses the disc marks its job (no model:
+// CVModel.py:309-316), and either finding vetoes the walker's prior (SimpleEclipse.ln_prior, CVModel.py:282-316).
+// One writer per walker, and nothing else runs on these fields at this point.
+__global__ void veto_kernel(int what, int n_ecl, long long n, WalkerScal* __restrict__ ws, JobScal* __restrict__ js)
+{
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    bool any = false;
+    for (int e = 0; e < n_ecl; ++e) {
+        JobScal& J = js[w * n_ecl + e];
+        const int v = J.veto;
+        if (v == 0) continue;
+        any = true;
+        if (v == 2 && J.status == 0) J.status = 2;
+    }
+    if (any && what != LFB_LN_LIKE) ws[w].lnprior = -INFINITY;
 }
 
 // ---------------------------------------------------------------- elements_kernel
@@ -357,6 +379,7 @@ __global__ void __launch_bounds__(kElemThreads, kElemBlocks) elements_kernel(con
     } else {
         const JobScal& J = A.js[unit];
         if (J.status != 0) return;
+        if (COMP == 2 && J.veto != 0) return;  // (the strip is solved after the join with the stream ODE)
         if (COMP == 1) {
             // disc: ring m, sector j on the y > 0 side
             const double rwd_a = fetch(A.L, th, g[P_RWD]) * R.xl1, rdisc_a = fetch(A.L, th, g[P_RDISC]) * R.xl1;
@@ -806,7 +829,11 @@ __global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __g
     __shared__ int s_itot[NW];
     const long long w = blockIdx.x;
     const WalkerScal& W = A.ws[w];
-    if (W.status != 0 || (A.what != LFB_LN_LIKE && !(W.lnprior > -INFINITY))) return;
+    // (one thread decides for the CTA: every thread must take the same way through the barriers below)
+    __shared__ int s_live;
+    if (tid == 0) s_live = !(W.status != 0 || (A.what != LFB_LN_LIKE && !(W.lnprior > -INFINITY)));
+    __syncthreads();
+    if (!s_live) return;
     const double ud = G.donor_ulimb;
     for (int q = tid; q < kDonorBins + 1; q += kDonorThreads) cnt[q] = 0;
     // ---- 1. intervals of the four images of every quarter tile ----

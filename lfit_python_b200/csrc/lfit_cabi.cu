@@ -164,6 +164,7 @@ struct lfb_handle {
     cudaEvent_t enter_ev = nullptr, t0_ev = nullptr, t1_ev = nullptr;
     bool ev_valid = false;
     bool trace = false;  // lfb_set_trace
+    bool debug_sync = false;  // LFB_DEBUG_SYNC=1: synchronise after every kernel launch and name the one that faults
     // Gaussian-process likelihood (lfb_set_gp)
     bool gp_on = false;
     int gp_src[3] = {0, 0, 0};
@@ -470,6 +471,14 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
     const bool trace = record && h->trace;
     if (trace)
         for (int i = 0; i <= LFB_K_COUNT; ++i) ln.kev_set[i] = false;
+    // LFB_DEBUG_SYNC=1: synchronise the device after every launch and name the kernel that faulted
+#define KSYNC(name)                                                                                  \
+    do {                                                                                             \
+        if (h->debug_sync) {                                                                         \
+            cudaError_t e_ = cudaDeviceSynchronize();                                                \
+            if (e_ != cudaSuccess) return fail(h, LFB_ECUDA, std::string(name) + ": " + cudaGetErrorString(e_)); \
+        }                                                                                            \
+    } while (0)
 #define KREC(i)                                      \
     do {                                             \
         if (trace) {                                 \
@@ -550,12 +559,14 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
     if (record) CK(cudaEventRecord(ln.ev[ST_WALKER], st));
     KREC(LFB_K_WALKER);
     walker_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, what, flags, n, d_theta, ln.ws.as<WalkerScal>());
+    KSYNC("walker_kernel");
     // fork 1: what needs the walker scalars only runs beside everything else on a second side stream -- the
     // white-dwarf centre's lines of sight (Newton starts of its tiles), then the donor: its tiles and its phase table
     CK(cudaEventRecord(ln.fork2_ev, st));
     CK(cudaStreamWaitEvent(ln.side2, ln.fork2_ev, 0));
     if (what != LFB_LN_PRIOR && !(flags & LFB_FLAG_SKIP_WD)) {
         wdcentre_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ln.side2>>>(what, n, ln.ws.as<WalkerScal>());
+        KSYNC("wdcentre_kernel");
         h->launches++;
     }
     CK(cudaEventRecord(ln.wd_ev, ln.side2));
@@ -564,10 +575,12 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         if (dsm > (size_t)h->max_smem - 2048) return fail(h, LFB_EINVAL, "donor grid too dense for the table kernel's shared memory");
         if (trace) CK(cudaEventRecord(ln.dev[0], ln.side2));
         elements_kernel<3><<<blocks(n, G.n_donor_q), kElemThreads, 0, ln.side2>>>(E);
+        KSYNC("elements_kernel");
         if (trace) CK(cudaEventRecord(ln.dev[1], ln.side2));
         // the donor's curve as a table over phase, once per walker (every eclipse of the walker reads it)
         CK(cudaFuncSetAttribute(donor_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
         donor_table_kernel<<<(unsigned)n, kDonorThreads, dsm, ln.side2>>>(A);
+        KSYNC("donor_table_kernel");
         if (trace) CK(cudaEventRecord(ln.dev[2], ln.side2));
         h->launches += 2;
     }
@@ -576,6 +589,7 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
     KREC(LFB_K_JOBCHECK);
     jobcheck_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, st>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
                                                                       ln.js.as<JobScal>());
+    KSYNC("jobcheck_kernel");
     // fork 2: the ballistic-stream ODE (one serial integration per job) runs beside the element solves
     CK(cudaEventRecord(ln.fork_ev, st));
     CK(cudaStreamWaitEvent(ln.side, ln.fork_ev, 0));
@@ -586,6 +600,7 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
     else
         stream_kernel<false><<<(unsigned)((njobs + 63) / 64), 64, 0, ln.side>>>(L, what, flags, njobs, d_theta, ln.ws.as<WalkerScal>(),
                                                                       ln.js.as<JobScal>());
+        KSYNC("stream_kernel");
     if (trace) CK(cudaEventRecord(ln.sev[1], ln.side));
     CK(cudaEventRecord(ln.join_ev, ln.side));
     h->launches += 3;
@@ -594,12 +609,14 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         if (!(flags & LFB_FLAG_SKIP_DISC)) {
             KREC(LFB_K_ELEM_DISC);
             elements_kernel<1><<<blocks(njobs, G.n_disc_half, true), kElemThreads, 0, st>>>(E);
+            KSYNC("elements_kernel");
             h->launches++;
         }
         if (!(flags & LFB_FLAG_SKIP_WD)) {
             CK(cudaStreamWaitEvent(st, ln.wd_ev, 0));  // the white-dwarf centre's lines of sight (side stream)
             KREC(LFB_K_ELEM_WD);
             elements_kernel<0><<<blocks(n, G.n_wd_half), kElemThreads, 0, st>>>(E);
+            KSYNC("elements_kernel");
             h->launches++;
         }
         if (record) CK(cudaEventRecord(ln.ev[ST_FLUX], st));
@@ -607,19 +624,27 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         // stream ODE, so that the main stream has work while the ODE finishes
         KREC(LFB_K_PREP);
         prep_kernel<<<(unsigned)((njobs + 3) / 4), 128, 0, st>>>(A);
+        KSYNC("prep_kernel");
         const long long per_job0 = ((G.n_wd_half + G.n_disc_half) + 31) & ~31;
         const long long per_job1 = (G.n_bs + 31) & ~31;
         KREC(LFB_K_POSITIONS);
         positions_kernel<0><<<(unsigned)((njobs * per_job0 + 127) / 128), 128, 0, st>>>(A);
+        KSYNC("positions_kernel");
         CK(cudaStreamWaitEvent(st, ln.join_ev, 0));  // join: the strip needs the impact point
         KREC(LFB_K_ELEM_BS);  // includes any wait for the stream ODE on the side stream
+        veto_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(what, L.n_ecl, n, ln.ws.as<WalkerScal>(), ln.js.as<JobScal>());
+        KSYNC("veto_kernel");
+        h->launches++;
         if (!(flags & LFB_FLAG_SKIP_BS)) {
             elements_kernel<2><<<blocks(njobs, G.n_bs), kElemThreads, 0, st>>>(E);
+            KSYNC("elements_kernel");
             h->launches++;
         }
         KREC(LFB_K_PREP_BS);
         prep_strip_kernel<<<(unsigned)((njobs + 3) / 4), 128, 0, st>>>(A);
+        KSYNC("prep_strip_kernel");
         positions_kernel<1><<<(unsigned)((njobs * per_job1 + 127) / 128), 128, 0, st>>>(A);
+        KSYNC("positions_kernel");
         h->launches += 2;
         const FluxShape fs = flux_shape(h, mode);
         const size_t smem = (size_t)fs.NT * fs.RP * (mode ? 32 : 16);
@@ -636,14 +661,19 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         else if (fs.NT == 128) LFB_LAUNCH_FLUX(0, 128, 13, 8);
         else LFB_LAUNCH_FLUX(0, 256, 13, 4);
 #undef LFB_LAUNCH_FLUX
+        KSYNC("flux_kernel");
         h->launches += 3;
         if (gp) {
             KREC(LFB_K_GP);
             gp_kernel<<<dim3((unsigned)((n + kGpWalkers - 1) / kGpWalkers), (unsigned)L.n_ecl), kGpThreads, 0, st>>>(A);
+            KSYNC("gp_kernel");
             h->launches++;
         }
     } else {
         CK(cudaStreamWaitEvent(st, ln.join_ev, 0));
+        veto_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(what, L.n_ecl, n, ln.ws.as<WalkerScal>(), ln.js.as<JobScal>());
+        KSYNC("veto_kernel");
+        h->launches++;
         if (record) CK(cudaEventRecord(ln.ev[ST_FLUX], st));
     }
     CK(cudaStreamWaitEvent(st, ln.don_ev, 0));  // the second side stream always rejoins (stream capture needs it)
@@ -652,6 +682,7 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
     if (d_out || d_chi) {
         finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(what, L.n_ecl, n, ln.ws.as<WalkerScal>(),
                                                                   ln.chi_part.as<double>(), d_chi, d_out);
+        KSYNC("finish_kernel");
         h->launches++;
     }
     if (record) {
@@ -659,6 +690,7 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
     }
     KREC(LFB_K_COUNT);
 #undef KREC
+#undef KSYNC
     CK(cudaGetLastError());
     return LFB_OK;
 }
@@ -821,6 +853,10 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
     }
     if (const char* env = getenv("LFB_STREAM_LANES_BELOW")) h->stream_lanes_below = atoll(env);
     if (const char* env = getenv("LFB_GRAPHS")) h->graphs_on = atoi(env) != 0;
+    if (const char* env = getenv("LFB_DEBUG_SYNC")) {
+        h->debug_sync = atoi(env) != 0;
+        if (h->debug_sync) h->graphs_on = false;
+    }
     *out = h;
     return LFB_OK;
 }
