@@ -116,6 +116,12 @@ struct JobScal {
     int ev_lo, ev_hi;          // sample positions spanned by the eclipse events of the job's tiles
 };
 
+// walker of a job / unit (a batch holds far fewer than 2^31 jobs: 32-bit division, a fraction of the 64-bit one's cost)
+__device__ __forceinline__ long long walker_of(long long job, int n_ecl)
+{
+    return (long long)((unsigned)job / (unsigned)n_ecl);
+}
+
 __device__ __forceinline__ double fetch(const DevLayout& L, const double* th, int src)
 {
     return src >= 0 ? th[src] : L.consts[-src - 1];
@@ -197,7 +203,7 @@ __global__ void jobcheck_kernel(DevLayout L, int what, int flags, long long njob
 {
     long long job = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (job >= njobs) return;
-    long long w = job / L.n_ecl;
+    long long w = walker_of(job, L.n_ecl);
     int e = (int)(job - w * L.n_ecl);
     JobScal J;
     J.xs = J.ys = 0.0;
@@ -247,7 +253,7 @@ __global__ void stream_kernel(DevLayout L, int what, int flags, long long njobs,
     long long job = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> (LANES ? 3 : 0);
     if (job >= njobs || (flags & LFB_FLAG_SKIP_BS)) return;
     if (js[job].status != 0) return;
-    long long w = job / L.n_ecl;
+    long long w = walker_of(job, L.n_ecl);
     int e = (int)(job - w * L.n_ecl);
     const Roche R = ws[w].R;
     const double* th = theta + w * L.ndim;
@@ -326,11 +332,11 @@ __global__ void __launch_bounds__(kElemThreads, kElemBlocks) elements_kernel(con
     // components are dealt to threads back to back -- a warp may straddle two walkers, no idle lanes
     const int padded = COMP == 1 ? (per_unit + 31) & ~31 : per_unit;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long unit = gid / padded;
+    const long long unit = gid < 0xffffffffLL ? (long long)((unsigned)gid / (unsigned)padded) : gid / padded;
     const int t = (int)(gid - unit * padded);
     const long long nunits = (COMP == 0 || COMP == 3) ? A.n : A.njobs;
     if (unit >= nunits || t >= per_unit) return;
-    const long long w = (COMP == 0 || COMP == 3) ? unit : unit / A.L.n_ecl;
+    const long long w = (COMP == 0 || COMP == 3) ? unit : walker_of(unit, A.L.n_ecl);
     const int e = (COMP == 0 || COMP == 3) ? 0 : (int)(unit - w * A.L.n_ecl);
     const WalkerScal& W = A.ws[w];
     if (!walker_live(A, W)) return;
@@ -506,7 +512,7 @@ __global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ FluxA
     const int lane = threadIdx.x & 31;
     const long long job = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (job >= A.njobs) return;
-    const long long w = job / A.L.n_ecl;
+    const long long w = walker_of(job, A.L.n_ecl);
     const int e = (int)(job - w * A.L.n_ecl);
     const WalkerScal& W = A.ws[w];
     const JobScal& J = A.js[job];
@@ -706,7 +712,7 @@ __global__ void __launch_bounds__(128) prep_strip_kernel(const __grid_constant__
     const int lane = threadIdx.x & 31;
     const long long job = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (job >= A.njobs) return;
-    const long long w = job / A.L.n_ecl;
+    const long long w = walker_of(job, A.L.n_ecl);
     if (!job_live(A, A.ws[w], A.js[job])) return;
     const bool do_bs = !(A.flags & LFB_FLAG_SKIP_BS);
     long long* wq_bs = A.wq + job * (G.n_wd_rings + G.n_disc_r + G.n_bs) + G.n_wd_rings + G.n_disc_r;
@@ -728,10 +734,10 @@ __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ 
     const int per_job = PART == 0 ? G.n_wd_half + G.n_disc_half : G.n_bs;
     const int padded = (per_job + 31) & ~31;  // a warp never straddles two jobs
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long job = gid / padded;
+    const long long job = gid < 0xffffffffLL ? (long long)((unsigned)gid / (unsigned)padded) : gid / padded;
     const int t = (int)(gid - job * padded);
     if (job >= A.njobs) return;  // warp-uniform
-    const long long w = job / A.L.n_ecl;
+    const long long w = walker_of(job, A.L.n_ecl);
     const int egather = (int)(job - w * A.L.n_ecl);
     const int e = A.mode ? 0 : egather;
     const WalkerScal& W = A.ws[w];
@@ -1061,7 +1067,7 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
     __shared__ JobConst C;  // (in shared memory: a dozen doubles every thread reads but need not hold in registers)
 
     const long long job = blockIdx.x;
-    const long long w = job / A.L.n_ecl;
+    const long long w = walker_of(job, A.L.n_ecl);
     const int egather = (int)(job - w * A.L.n_ecl);
     const int e = MODE ? 0 : egather;
     const long long ch0 = A.smp.chunk_off[e];
