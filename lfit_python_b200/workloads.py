@@ -152,7 +152,7 @@ class Workload:
         self.lc_y = 0.2 + rng.normal(0.0, self.sigma, self.n_ecl * self.n_ph)
         return self.lc_y
 
-    def walkers(self, n, ln_prior_fn=None, scatter=0.10, seed=2024, max_rounds=50):
+    def walkers(self, n, ln_prior_fn=None, scatter=0.10, seed=2024, max_rounds=2000):
         """emcee.utils.sample_ball(p0, scatter*p0) then the resampling loop of
         mcmc_utils.initialise_walkers (mcmc_utils.py:46-72), with ln_prior_fn(theta[n, ndim]) -> (n,)."""
         rng = np.random.default_rng(seed)
