@@ -38,7 +38,8 @@ def build(force=False, verbose=False):
     """Compile csrc/lfit_kernels.cu for sm_100a; returns the library path."""
     if not force and not stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    extra = os.environ.get("LFB_NVCC_EXTRA", "").split()     # tuning experiments, e.g. -DLFB_ELEM_BLOCKS=8
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)

@@ -49,7 +49,7 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB
+    return os.environ.get("LFB_LIB") or _build.LIB     # (LFB_LIB: a differently tuned build, for experiments)
 
 
 def load():

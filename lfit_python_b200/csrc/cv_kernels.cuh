@@ -1504,7 +1504,17 @@ __global__ void ingress_egress_kernel(long long n, const double* __restrict__ q,
         double si, ci;
         sincos_(incl[i] * kDeg, &si, &ci);
         const Point T = {pts[5 * i], pts[5 * i + 1], pts[5 * i + 2], pts[5 * i + 3], pts[5 * i + 4]};
-        good = ingress_egress(R, si, ci, T, &pin, &pout);
+        // a tile of the white dwarf (offset on the sky only) is solved as the pipeline solves it: from the
+        // grazing lines of sight of the centre (wdcentre_kernel), when those exist
+        Roots hint;
+        hint.lam[0] = NAN;
+        bool have_hint = false;
+        if (T.x == 0.0 && T.y == 0.0 && T.z == 0.0 && (T.xi != 0.0 || T.eta != 0.0)) {
+            const Point T0 = {0.0, 0.0, 0.0, 0.0, 0.0};
+            double a, b;
+            have_hint = ingress_egress(R, si, ci, T0, &a, &b, nullptr, &hint) && hint.lam[0] == hint.lam[0];
+        }
+        good = ingress_egress(R, si, ci, T, &pin, &pout, have_hint ? &hint : nullptr);
     }
     out[2 * i] = good ? pin : NAN;
     out[2 * i + 1] = good ? pout : NAN;

@@ -527,14 +527,16 @@ LFB_HD bool graze_roots(const Roche& R, double si, double ci, const Point& T, do
             double dl = clampd((-D.St * F2 + D.Stl * F1) * idet, 0.2);
             // stay on this side of the deepest LOS: sin(th + dth - thm) must keep the sign of sg
             double cross = s * cm - c * sm;  // sin(th - thm)
+            bool newton_step = true;
             if (!(sg * (cross + dth * (c * cm + s * sm)) > 0.0)) {
                 dth = -0.5 * asin(cross > 1.0 ? 1.0 : (cross < -1.0 ? -1.0 : cross));
                 dl *= 0.5;
+                newton_step = false;  // (pushed back from the dividing LOS: a small step here is no convergence)
             }
             rotate_cs(c, s, dth);
             lam += dl;
-            // quadratic convergence: a step below 1e-9 leaves an error far below 1e-15
-            if (fabs(dth) < 1e-9 && fabs(dl) < 1e-7) { conv = true; break; }
+            // quadratic convergence: a Newton step below 1e-9 leaves an error far below 1e-15
+            if (newton_step && fabs(dth) < 1e-9 && fabs(dl) < 1e-7) { conv = true; break; }
         }
         // accept only a converged grazing LOS of the right kind (D is one tiny step old)
         double xx = T.x - T.xi * s - T.eta * ci * c + lam * si * c - 1.0;

@@ -387,11 +387,13 @@ static inline int lfo_ingress_egress_newton(const lfo_roche *R, double si, doubl
             double dl = (-D.St * F2 + D.Stl * F1) / det;
             lfo_newton_clamp(&dth, 0.2);
             lfo_newton_clamp(&dl, 0.2);
-            /* stay on this side of the deepest LOS */
-            if (sg * (th + dth - thm) <= 0.0) { dth = 0.5 * (thm - th); dl *= 0.5; }
+            /* stay on this side of the deepest LOS (a step pushed back from it is not a Newton step:
+             * however small, it does not signal convergence) */
+            int newton_step = 1;
+            if (sg * (th + dth - thm) <= 0.0) { dth = 0.5 * (thm - th); dl *= 0.5; newton_step = 0; }
             th += dth;
             lam += dl;
-            if (fabs(dth) < 1e-13 && fabs(dl) < 1e-10) { conv = 1; break; }
+            if (newton_step && fabs(dth) < 1e-13 && fabs(dl) < 1e-10) { conv = 1; break; }
         }
         /* accept only a converged grazing LOS of the right kind: a minimum along the LOS,
          * inside the bounding sphere, entering (side 0) or leaving (side 1) the lobe */
