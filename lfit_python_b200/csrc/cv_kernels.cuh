@@ -94,6 +94,8 @@ struct GridCfg {
     const int* rec_slot;             // [n_wd + n_disc + n_bs] where tile record i is stored: neighbouring tiles far apart
     const int* disc_order;      // [n_disc_half] disc elements ordered along the line of centres, so that the
                                 // threads of a warp solve elements of the same kind (deep / shallow / never eclipsed)
+    const double4* disc_geo;    // [n_disc_half] in disc_order: cos, sin of the sector azimuth, (ring + 0.5) / n_disc_r, tile
+    const double2* wd_geo;      // [n_wd_half] offset of a white-dwarf tile on the sky, in units of the star's radius
     double quad_off[kMaxQuad], quad_w[kMaxQuad];
 };
 
@@ -109,6 +111,7 @@ struct WalkerScal {
 struct JobScal {
     double xs, ys;             // stream impact point
     double smax, smaxp, shi;   // bright-spot strip: profile peak, peak^exp2, strip length (scale units)
+    double lsmax, caz, saz;    // ln(smax); direction of the strip (cos, sin of az)
     int status;                // 0 ok, 1 walker invalid, 2 stream misses disc, 3 bad parameter, 4 not needed
     int veto;                  // what the stream ODE found (it runs beside other kernels and writes nothing they read):
                                // 0 nothing, 2 the stream misses the disc, 5 azimuth outside its window.  Merged into
@@ -208,6 +211,9 @@ __global__ void jobcheck_kernel(DevLayout L, int what, int flags, long long njob
     JobScal J;
     J.xs = J.ys = 0.0;
     J.smax = J.smaxp = J.shi = 1.0;
+    J.lsmax = 0.0;
+    J.caz = 1.0;
+    J.saz = 0.0;
     J.status = 0;
     J.veto = 0;
     J.ev_lo = kNoEventPos;
@@ -235,6 +241,8 @@ __global__ void jobcheck_kernel(DevLayout L, int what, int flags, long long njob
             J.smax = pow(exp1 / exp2, 1.0 / exp2);
             J.smaxp = pow(J.smax, exp2);
             J.shi = fmin(20.0 + J.smax, pow(J.smaxp + 30.0, 1.0 / exp2));
+            J.lsmax = log(J.smax);
+            sincos_(fetch(L, th, g[P_AZ]) * kDeg, &J.saz, &J.caz);
         }
     }
     js[job] = J;
@@ -370,18 +378,9 @@ __global__ void __launch_bounds__(kElemThreads, kElemBlocks) elements_kernel(con
         // white dwarf: limb-darkened disc on the sky, ring k, tiles with cos(alpha) > 0
         const double rwd_a = fetch(A.L, th, g[P_RWD]) * R.xl1;
         if (!(rwd_a > 0.0) || !isfinite(rwd_a)) return;
-        int k = (int)sqrt(0.5 * (double)t);
-        while (2 * k * k > t) --k;
-        while (2 * (k + 1) * (k + 1) <= t) ++k;
-        int r = t - 2 * k * k, q1 = 2 * k + 1, nk = 4 * q1;
-        int j = r < q1 ? r : r + 2 * q1;
-        double inv = 1.0 / G.n_wd_rings;
-        double ra = k * inv, rb = (k + 1) * inv;
-        double rho = sqrt(0.5 * (ra * ra + rb * rb));
-        double sa, ca;
-        sincos_((j + 0.5) * kTwoPi / nk, &sa, &ca);
-        T.xi = rwd_a * rho * ca;
-        T.eta = rwd_a * rho * sa;
+        const double2 og = __ldg(G.wd_geo + t);
+        T.xi = rwd_a * og.x;
+        T.eta = rwd_a * og.y;
     } else {
         const JobScal& J = A.js[unit];
         if (J.status != 0) return;
@@ -389,25 +388,22 @@ __global__ void __launch_bounds__(kElemThreads, kElemBlocks) elements_kernel(con
         if (COMP == 1) {
             // disc: ring m, sector j on the y > 0 side
             const double rwd_a = fetch(A.L, th, g[P_RWD]) * R.xl1, rdisc_a = fetch(A.L, th, g[P_RDISC]) * R.xl1;
-            int hth = G.n_disc_th / 2;
-            tile = G.disc_order[t];
-            int m = tile / hth, j = tile - m * hth;
-            double r = rwd_a + (m + 0.5) * (rdisc_a - rwd_a) / G.n_disc_r;
-            double sa, ca;
-            sincos_((j + 0.5) * kTwoPi / G.n_disc_th, &sa, &ca);
-            T.x = r * ca;
-            T.y = r * sa;
+            const double2 cs = __ldg((const double2*)(G.disc_geo + t)), ft = __ldg((const double2*)(G.disc_geo + t) + 1);
+            tile = (int)ft.y;
+            const double r = rwd_a + ft.x * (rdisc_a - rwd_a);
+            T.x = r * cs.x;
+            T.y = r * cs.y;
         } else {
             // bright spot: strip through the stream impact point along azimuth az
             const double exp1 = A.L.npars > P_EXP1 ? fetch(A.L, th, g[P_EXP1]) : 2.0;
             const double exp2 = A.L.npars > P_EXP2 ? fetch(A.L, th, g[P_EXP2]) : 1.0;
-            double s = J.shi * t / (G.n_bs - 1);
-            wt = t == 0 ? 0.0 : pow(s / J.smax, exp1) * exp(J.smaxp - pow(s, exp2));
-            double len = (s - J.smax) * fetch(A.L, th, g[P_SCALE]) * R.xl1;
-            double tx, ty;
-            sincos_(fetch(A.L, th, g[P_AZ]) * kDeg, &ty, &tx);
-            T.x = J.xs + len * tx;
-            T.y = J.ys + len * ty;
+            const double s = J.shi * t / (G.n_bs - 1);
+            // brightness (s / smax)^exp1 exp(smax^exp2 - s^exp2), through one logarithm
+            const double ls = log(s);
+            wt = t == 0 ? 0.0 : exp(exp1 * (ls - J.lsmax) + (J.smaxp - exp(exp2 * ls)));
+            const double len = (s - J.smax) * fetch(A.L, th, g[P_SCALE]) * R.xl1;
+            T.x = J.xs + len * J.caz;
+            T.y = J.ys + len * J.saz;
         }
     }
     double pin, pout;

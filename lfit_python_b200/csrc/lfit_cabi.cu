@@ -194,7 +194,7 @@ struct lfb_handle {
     // layout
     bool have_layout = false, have_lc = false;
     int ndim = 0, n_ecl = 0, npars = 0, n_prior = 0, n_consts = 0;
-    DevBuf gather, consts, psrc, ptype, pisvar, pp1, pp2, pnorm, donor_off, disc_order, rec_widx, rec_slot;
+    DevBuf gather, consts, psrc, ptype, pisvar, pp1, pp2, pnorm, donor_off, disc_order, rec_widx, rec_slot, tile_geo;
     SampleSet lc, cf_lc;
     // calc_flux scratch
     DevBuf cf_gather, cf_pars, cf_tot, cf_comp;
@@ -783,6 +783,34 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
             cudaMemcpy(h->disc_order.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail("disc order table", cudaGetLastError());
         G.disc_order = h->disc_order.as<int>();
+        // what an element kernel thread needs to place its tile, looked up instead of worked out per thread:
+        // disc (in disc_order) cos and sin of the sector's azimuth, the ring's place between rwd and rdisc,
+        // the tile's number; white dwarf (half disc) the tile's offset on the sky in units of its radius
+        std::vector<double> geo((size_t)G.n_disc_half * 4 + (size_t)G.n_wd_half * 2);
+        for (int t = 0; t < G.n_disc_half; ++t) {
+            const int tile = order[t], m = tile / hth, j = tile % hth;
+            const double a = (j + 0.5) * kTwoPi / c.n_disc_th;
+            geo[4 * (size_t)t] = cos(a);
+            geo[4 * (size_t)t + 1] = sin(a);
+            geo[4 * (size_t)t + 2] = (m + 0.5) / c.n_disc_r;
+            geo[4 * (size_t)t + 3] = (double)tile;
+        }
+        double* wdg = geo.data() + (size_t)G.n_disc_half * 4;
+        for (int t = 0; t < G.n_wd_half; ++t) {
+            int k = (int)sqrt(0.5 * (double)t);
+            while (2 * k * k > t) --k;
+            while (2 * (k + 1) * (k + 1) <= t) ++k;
+            const int r = t - 2 * k * k, q1 = 2 * k + 1, nk = 4 * q1, j = r < q1 ? r : r + 2 * q1;
+            const double inv = 1.0 / c.n_wd_rings, ra = k * inv, rb = (k + 1) * inv;
+            const double rho = sqrt(0.5 * (ra * ra + rb * rb)), a = (j + 0.5) * kTwoPi / nk;
+            wdg[2 * (size_t)t] = rho * cos(a);
+            wdg[2 * (size_t)t + 1] = rho * sin(a);
+        }
+        if (h->tile_geo.reserve(geo.size() * sizeof(double)) != cudaSuccess ||
+            cudaMemcpy(h->tile_geo.p, geo.data(), geo.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail("tile geometry table", cudaGetLastError());
+        G.disc_geo = (const double4*)h->tile_geo.p;
+        G.wd_geo = (const double2*)(h->tile_geo.as<double>() + (size_t)G.n_disc_half * 4);
     }
     // where each tile record (mirrors included) finds its weight in a job's weight table
     // [white-dwarf rings | disc rings | strip elements]
@@ -868,7 +896,7 @@ void lfb_destroy(lfb_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_graphs(h);
     DevBuf* bufs[] = {&h->gather, &h->consts, &h->psrc, &h->ptype, &h->pisvar, &h->pp1, &h->pp2, &h->pnorm,
-                      &h->donor_off, &h->disc_order, &h->rec_widx, &h->rec_slot, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
+                      &h->donor_off, &h->disc_order, &h->rec_widx, &h->rec_slot, &h->tile_geo, &h->cf_gather, &h->cf_pars, &h->cf_tot, &h->cf_comp, &h->theta, &h->out,
                       &h->chisq, &h->h_in, &h->h_out, &h->h_chisq};
     for (DevBuf* b : bufs) b->release();
     for (DevBuf& b : h->scratch) b.release();

@@ -236,6 +236,26 @@ LFB_HD void ray_eval(const Roche& R, double si, double ci, const Point& T, doubl
     D.Stl = (a12 - 1.0) * e_t - b1 * x_e * x_t - b2 * d_e * d_t + (gx * ey - gy * ex);
 }
 
+// Potential and its derivative along the LOS only (the residuals of the grazing-LOS system): what a Newton
+// step with a frozen Jacobian needs -- about half of ray_eval.
+LFB_HD void ray_resid(const Roche& R, double si, double ci, const Point& T, double c, double s, double lam, double& S,
+                      double& Sl)
+{
+    LFB_CNT(11);
+    double ex = si * c, ey = -si * s;
+    double x = T.x + fma(lam, ex, -T.xi * s - T.eta * ci * c);
+    double y = T.y + fma(lam, ey, -T.xi * c + T.eta * ci * s);
+    double z = T.z + fma(lam, ci, T.eta * si);
+    double x2 = x - 1.0;
+    double yz = y * y + z * z;
+    double ir1 = fast_rsqrt(x * x + yz), ir2 = fast_rsqrt(x2 * x2 + yz);
+    double a1 = R.omu * ir1 * ir1 * ir1, a2 = R.mu * ir2 * ir2 * ir2;
+    double a12 = a1 + a2, xc = x - R.mu;
+    double gx = a1 * x + a2 * x2 - xc, gy = a12 * y - y, gz = a12 * z;
+    S = -R.omu * ir1 - R.mu * ir2 - 0.5 * (xc * xc + y * y);
+    Sl = gx * ex + gy * ey + gz * ci;
+}
+
 // (c, s) <- rotation by d radians, |d| <= 0.25: Taylor to d^13 (below 1e-17), no range reduction
 LFB_HD void rotate_cs(double& c, double& s, double d)
 {
@@ -256,6 +276,32 @@ LFB_HD void rotate_cs(double& c, double& s, double d)
     double cn = c * cd - s * sd;
     s = s * cd + c * sd;
     c = cn;
+}
+
+// Angle of the unit vector (c, s), in (-pi, pi] give or take a rounding: what atan2(s, c) returns, for a third
+// of its instructions.  An FP32 arctangent picks the nearest multiple of pi/64, whose cosine and sine come
+// from a table; the rest is the arcsine series of a sine below 0.025 (terms to x^11: 5e-20).
+#ifdef __CUDACC__
+struct AngleRow {
+    double c, s, a;
+};
+__device__ const AngleRow g_angle_rows[129] = {
+#include "angle_table.inc"
+};
+#endif
+LFB_HD double angle_of(double c, double s)
+{
+#ifdef __CUDA_ARCH__
+    const float af = atan2f((float)s, (float)c);
+    const int k = __float2int_rn(af * 20.371832715762602f);  // 64 / pi
+    const AngleRow row = g_angle_rows[k + 64];
+    const double x = s * row.c - c * row.s;  // sin(angle - row.a), |angle - row.a| < pi/128 + 1e-6
+    const double x2 = x * x;
+    const double p = fma(x2, fma(x2, fma(x2, fma(x2, 945.0 / 42240.0, 105.0 / 3456.0), 15.0 / 336.0), 3.0 / 40.0), 1.0 / 6.0);
+    return row.a + fma(x * x2, p, x);
+#else
+    return atan2(s, c);
+#endif
 }
 
 // min over the chord of the LOS inside the bounding sphere of Phi - Phi_c (robust path only)
@@ -384,6 +430,16 @@ LFB_HD float rsqrt_f(float x)
 #endif
 }
 
+// approximate FP32 reciprocal (one MUFU instruction; the warm-up only picks starting points)
+LFB_HD float rcp_f(float x)
+{
+#ifdef __CUDA_ARCH__
+    return __fdividef(1.0f, x);
+#else
+    return 1.0f / x;
+#endif
+}
+
 LFB_HD void ray_eval_f(float mu, float omu, float si, float ci, const PointF& T, float c, float s, float lam, DerivsF& D)
 {
     LFB_CNT(10);
@@ -430,9 +486,10 @@ LFB_HD bool warm_root(float mu, float omu, float phic, float si, float ci, const
 {
     DerivsF D;
     for (int it = 0; it < kWarmIters; ++it) {
+        LFB_CNT(13);
         ray_eval_f(mu, omu, si, ci, T, c, s, lam, D);
         float F1 = D.S - phic, F2 = D.Sl;
-        float idet = 1.0f / (D.St * D.Sll - D.Sl * D.Stl);
+        float idet = rcp_f(D.St * D.Sll - D.Sl * D.Stl);
         float dth = (-F1 * D.Sll + F2 * D.Sl) * idet, dl = (-D.St * F2 + D.Stl * F1) * idet;
         dth = dth > 0.2f ? 0.2f : (dth < -0.2f ? -0.2f : dth);
         dl = dl > 0.2f ? 0.2f : (dl < -0.2f ? -0.2f : dl);
@@ -444,7 +501,10 @@ LFB_HD bool warm_root(float mu, float omu, float phic, float si, float ci, const
         rotate_cs_f(c, s, dth);
         lam += dl;
         if (!(fabsf(dth) < 1.0f)) return false;  // NaN
-        if (fabsf(dth) < 2e-5f && fabsf(dl) < 2e-4f) return true;
+#ifndef LFB_WARM_TOL
+#define LFB_WARM_TOL 3e-4f
+#endif
+        if (fabsf(dth) < LFB_WARM_TOL && fabsf(dl) < 10.0f * LFB_WARM_TOL) return true;
     }
     return false;
 }
@@ -453,13 +513,13 @@ LFB_HD bool warm_root(float mu, float omu, float phic, float si, float ci, const
 // sight), from the conjunction LOS: Newton on lam alone first, then on both.  1: settled, g0 = depth below the
 // critical potential there (single precision); 0: it did not settle -- the caller searches in FP64 from scratch.
 LFB_HD int warm_min(float mu, float omu, float phic, float si, float ci, const PointF& T, float& c, float& s, float& lam,
-                    float& g0)
+                    float& g0, DerivsF& D)
 {
-    DerivsF D;
     for (int it = 0; it < 5; ++it) {
+        LFB_CNT(14);
         ray_eval_f(mu, omu, si, ci, T, c, s, lam, D);
         if (!(D.Sll > 0.0f)) return 0;
-        float dl = -D.Sl / D.Sll;
+        float dl = -D.Sl * rcp_f(D.Sll);
         dl = dl > 0.1f ? 0.1f : (dl < -0.1f ? -0.1f : dl);
         lam += dl;
         if (fabsf(dl) < 1e-3f) break;
@@ -468,7 +528,7 @@ LFB_HD int warm_min(float mu, float omu, float phic, float si, float ci, const P
         ray_eval_f(mu, omu, si, ci, T, c, s, lam, D);
         float det = D.Stt * D.Sll - D.Stl * D.Stl;
         if (!(D.Sll > 0.0f) || !(det > 0.0f)) return 0;
-        float idet = 1.0f / det;
+        float idet = rcp_f(det);
         float dth = -(D.St * D.Sll - D.Sl * D.Stl) * idet, dl = -(D.Sl * D.Stt - D.St * D.Stl) * idet;
         dth = dth > 0.1f ? 0.1f : (dth < -0.1f ? -0.1f : dth);
         dl = dl > 0.1f ? 0.1f : (dl < -0.1f ? -0.1f : dl);
@@ -486,6 +546,10 @@ LFB_HD int warm_min(float mu, float omu, float phic, float si, float ci, const P
 constexpr float kWarmRejectMargin = 3e-4f;  // depth above which the FP32 search alone says "never eclipsed"
 constexpr int kMinIters = 12;   // deepest-LOS Newton (shallow elements only), early exit
 constexpr int kRootIters = 16;  // grazing-LOS Newton, early exit
+#ifndef LFB_FROZEN_D0
+#define LFB_FROZEN_D0 2e-4
+#endif
+constexpr double kFrozenBelow = LFB_FROZEN_D0;  // Newton steps below this are followed by frozen-Jacobian steps
 
 // The two grazing lines of sight of an element: orbital angle as (cos, sin) and distance along the LOS
 struct Roots {
@@ -537,15 +601,37 @@ LFB_HD bool graze_roots(const Roche& R, double si, double ci, const Point& T, do
             lam += dl;
             // quadratic convergence: a Newton step below 1e-9 leaves an error far below 1e-15
             if (newton_step && fabs(dth) < 1e-9 && fabs(dl) < 1e-7) { conv = true; break; }
+#ifndef LFB_NO_FROZEN_STEP
+            // Close to the root (where the FP32 warm-up leaves the iteration) the next steps do not need a new
+            // Jacobian: with the one just used the error shrinks by ~ |Newton step| per step, and each such step
+            // costs the residuals only.  The contraction is measured (size of a step over the one before), and
+            // the iteration ends when contraction x step -- the error left behind -- is below 1e-15.
+            if (newton_step && fabs(dth) < kFrozenBelow && fabs(dl) < 10.0 * kFrozenBelow) {
+                double before = fabs(dth) + 0.1 * fabs(dl);
+                for (int k = 0; k < 2; ++k) {
+                    double S2, Sl2;
+                    ray_resid(R, si, ci, T, c, s, lam, S2, Sl2);
+                    const double G1 = S2 - R.phic;
+                    const double dth2 = (-G1 * D.Sll + Sl2 * D.Sl) * idet, dl2 = (-D.St * Sl2 + D.Stl * G1) * idet;
+                    const double now = fabs(dth2) + 0.1 * fabs(dl2);
+                    if (!(now < 0.01 * before)) break;  // not what a frozen step near the root does: full steps again
+                    rotate_cs(c, s, dth2);
+                    lam += dl2;
+                    if (now * now < 1e-15 * before) { conv = true; break; }
+                    before = now;
+                }
+                if (conv) break;
+            }
+#endif
         }
-        // accept only a converged grazing LOS of the right kind (D is one tiny step old)
+        // accept only a converged grazing LOS of the right kind (D is one or two tiny steps old)
         double xx = T.x - T.xi * s - T.eta * ci * c + lam * si * c - 1.0;
         double yy = T.y - T.xi * c + T.eta * ci * s - lam * si * s;
         double zz = T.z + T.eta * si + lam * ci;
         bool ok = conv && D.Sll > 0.0 && lam > 0.0 && xx * xx + yy * yy + zz * zz <= R.rs * R.rs &&
                   (side ? D.St > 0.0 : D.St < 0.0) && c * cpsi + s * spsi > 0.0;
         if (!ok) return false;
-        res[side] = atan2(s, c);
+        res[side] = angle_of(c, s);
         found.c[side] = c;
         found.s[side] = s;
         found.lam[side] = lam;
@@ -596,7 +682,11 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         }
     }
     double rxy = si * sqrt(wx * wx + wy * wy);
-    double tang = sqrt(w2 - R.rin * R.rin);
+#ifndef LFB_START_F
+#define LFB_START_F 1.15
+#endif
+    const double rstart = R.rin * LFB_START_F;
+    double tang = sqrt(w2 - rstart * rstart);
     double cosd = (tang - wz * ci) / rxy;
     Derivs D;
     double c0, s0, c1, s1, lam0, lam1, cm = cpsi, sm = spsi;
@@ -617,14 +707,15 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         lam0 = lam1 = tang;
     } else {
         LFB_CNT(4);
-        bool warmed = false;
+        bool warmed = false, starts = false;
 #ifndef LFB_NO_WARMUP
         {
             // the search for the deepest LOS runs in FP32 first: an element that clears the lobe by a wide margin
             // is done, the others hand the FP64 iteration a start ~1e-4 from the minimum
             const PointF Tf = {(float)T.x, (float)T.y, (float)T.z, (float)T.xi, (float)T.eta};
             float cf = (float)c, sf = (float)s, lf = (float)lam, g0f = 0.0f;
-            if (warm_min((float)R.mu, (float)R.omu, (float)R.phic, (float)si, (float)ci, Tf, cf, sf, lf, g0f)) {
+            DerivsF Df;
+            if (warm_min((float)R.mu, (float)R.omu, (float)R.phic, (float)si, (float)ci, Tf, cf, sf, lf, g0f, Df)) {
                 if (g0f > kWarmRejectMargin) {
                     LFB_CNT(6);
                     verdict = 0;
@@ -635,6 +726,31 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
                     s = sw * nrm;
                     lam = (double)lf;
                     warmed = true;
+#ifndef LFB_NO_WARM_STARTS
+                    // An element this far inside the shadow is eclipsed beyond doubt, and the starts of the
+                    // grazing-LOS iteration (osculating parabola at the deepest LOS) need no more than FP32.
+                    const float isll = rcp_f(Df.Sll), kap = Df.Stt - Df.Stl * Df.Stl * isll;
+                    const float del = sqrtf(-2.0f * g0f * rcp_f(kap)), slope = -Df.Stl * isll;
+                    if (g0f < -kWarmRejectMargin && Df.Sll > 0.0f && kap > 0.0f && del < 0.25f) {
+                        LFB_CNT(12);
+                        float sdl, cdl;
+#ifdef __CUDA_ARCH__
+                        __sincosf(del, &sdl, &cdl);
+#else
+                        sdl = sinf(del);
+                        cdl = cosf(del);
+#endif
+                        cm = c;
+                        sm = s;
+                        c0 = c * (double)cdl + s * (double)sdl;  // thm - del
+                        s0 = s * (double)cdl - c * (double)sdl;
+                        c1 = c * (double)cdl - s * (double)sdl;  // thm + del
+                        s1 = s * (double)cdl + c * (double)sdl;
+                        lam0 = lam - (double)(slope * del);
+                        lam1 = lam + (double)(slope * del);
+                        starts = true;
+                    }
+#endif
                 }
             }
         }
@@ -650,8 +766,8 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
             lam += dl;
             if (fabs(dl) < 1e-6) break;  // the 2-D Newton below finishes the job
         }
-        bool conv = false;
-        for (int it = 0; it < kMinIters && verdict < 0; ++it) {
+        bool conv = starts;
+        for (int it = 0; it < kMinIters && verdict < 0 && !starts; ++it) {
             ray_eval(R, si, ci, T, c, s, lam, D);
             double det = D.Stt * D.Sll - D.Stl * D.Stl;
             if (!(D.Sll > 0.0) || !(det > 0.0)) {
@@ -665,7 +781,7 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
             if (fabs(dth) < 1e-7 && fabs(dl) < 1e-7) { conv = true; break; }
         }
         if (verdict < 0 && !conv) verdict = 2;
-        if (verdict < 0) {
+        if (verdict < 0 && !starts) {
             ray_eval(R, si, ci, T, c, s, lam, D);
             double g0 = D.S - R.phic;
             double kappa = D.Stt - D.Stl * D.Stl / D.Sll;
