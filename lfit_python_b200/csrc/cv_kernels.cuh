@@ -457,8 +457,8 @@ struct DonorTable {
     unsigned short* first;  // [n][kDonorBins + 1] break points in the phase bins before bin g
     double* key;            // [n][nb_max]         sorted break points (an opening one is nudged up by one ulp:
                             //                     break point k applies to phase x iff key[k] <= x)
-    double* mom;            // [n][nb_max + 1][6]  moments (1, c, s, c^2, c s; one pad) after k break points, normalised
-                            //                     "at maximum light" (quadrature)
+    double* mom;            // [n][nb_max + 1][6]  row k: moments (1, c, s, c^2, c s) after k break points, normalised
+                            //                     "at maximum light" (quadrature), then key[k] (+inf for the last row)
     int nb_max;             // 8 n_donor_q
 };
 
@@ -974,7 +974,8 @@ __global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __g
     const double inv_norm = 1.0 / s_base[5];
     double* key_out = A.dt.key + w * A.dt.nb_max;
     double* mom_out = A.dt.mom + w * (A.dt.nb_max + 1) * 6;
-    if (tid < 6) mom_out[tid] = tid < 5 ? s_base[tid] * inv_norm : 0.0;
+    // (row k: the moments after k break points, and in its sixth slot the break point that ends it)
+    if (tid < 6) mom_out[tid] = tid < 5 ? s_base[tid] * inv_norm : (nb > 0 ? skey[0] : INFINITY);
     double carry[5];
 #pragma unroll
     for (int a = 0; a < 5; ++a) carry[a] = s_base[a];
@@ -1024,7 +1025,7 @@ __global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __g
                 double2* row = (double2*)(mom_out + (size_t)(x + 1) * 6);
                 row[0] = make_double2(run[0] * inv_norm, run[1] * inv_norm);
                 row[1] = make_double2(run[2] * inv_norm, run[3] * inv_norm);
-                row[2] = make_double2(run[4] * inv_norm, 0.0);
+                row[2] = make_double2(run[4] * inv_norm, x + 1 < nb ? skey[x + 1] : INFINITY);
             }
         }
         __syncthreads();
@@ -1094,7 +1095,6 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
     const bool do_don = C.f_rs != 0.0;
     // the walker's donor table
     const unsigned short* __restrict__ dfirst = A.dt.first + w * (kDonorBins + 1);
-    const double* __restrict__ dkey = A.dt.key + w * A.dt.nb_max;
     const double* __restrict__ dmom = A.dt.mom + w * (A.dt.nb_max + 1) * 6;
     const int nb = do_don ? (int)__ldg(dfirst + kDonorBins) : 0;
     double chi = 0.0;
@@ -1218,23 +1218,27 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
         }
         {
             // phase, cos, sin of the segment's samples, thread-major: sample (tid, r) at [r][tid]
-            const double* __restrict__ seg_tr = A.smp.seg_tr + (size_t)(ch0 + seg) * 3 * Ms + tid;
+            const double* __restrict__ sp = A.smp.seg_tr + (size_t)(ch0 + seg) * 3 * Ms + tid;
             // Donor table state: dm = moments of row kd (the break points at or before the last sample's phase),
-            // knext = the next break point; row kd + 1 and the break point after it (dn, knext2) are fetched ahead,
-            // so that crossing a break point costs no memory latency.
+            // kend = the break point that ends the row.  (Fetching the next row ahead was measured: the extra
+            // instructions cost more than the latency they hide -- other warps cover it.)
             int kd = -1;
-            double knext = -INFINITY, knext2 = INFINITY;
+            double kend = -INFINITY;
             double xprev = 2.0;
-            double dm[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, dn[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            double x0 = __ldg(seg_tr), c0 = __ldg(seg_tr + Ms), s0 = __ldg(seg_tr + 2 * Ms);
+            double dm[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            double x0 = __ldg(sp), c0 = __ldg(sp + Ms), s0 = __ldg(sp + 2 * Ms);
+            int* cell = cells + tid * RP * CW;
+            int p = tid * RP;
+            const int p_next = m0n - 1;
+            // per-job constants of the mix (registers for the loop; the rest stays in shared memory)
+            const double f01c = C.f_wd + C.f_d, f01k = C.F01 * kInvFix;
+            const double b0 = C.f_s * C.fis, b1 = C.f_s * (1.0 - C.fis);
 #pragma unroll 1
-            for (int r = 0; r < RP; ++r) {
-                const int p = tid * RP + r;
-                int* cell = cells + p * CW;
+            for (int r = 0; r < RP; ++r, ++p, cell += CW) {
                 // the next sample's phase, cos and sin travel while this one is evaluated
-                const int rn = r + 1 < RP ? r + 1 : r;
-                const double x0n = __ldg(seg_tr + rn * NT), c0n = __ldg(seg_tr + Ms + rn * NT);
-                const double s0n = __ldg(seg_tr + 2 * Ms + rn * NT);
+                const double* __restrict__ spn = r + 1 < RP ? sp + NT : sp;
+                const double x0n = __ldg(spn), c0n = __ldg(spn + Ms), s0n = __ldg(spn + 2 * Ms);
+                sp = spn;
                 if (tiles_matter) {
                     const int4 v = *(const int4*)cell;
                     run[0] += ((long long)v.x << kLimbBits) + v.y;
@@ -1243,7 +1247,7 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
                         const int2 u = *(const int2*)(cell + 4);
                         run[2] += ((long long)u.x << kLimbBits) + u.y;
                     }
-                    if (p == m0n - 1) {
+                    if (p == p_next) {
 #pragma unroll
                         for (int a = 0; a < NA; ++a) s_next[a] = run[a];
                     }
@@ -1257,50 +1261,38 @@ __global__ void __launch_bounds__(NT, CTAS) flux_kernel(const __grid_constant__ 
                         double x = x0 - C.phi0w;
                         x -= rint(x);
                         if (x >= 0.5) x -= 1.0;
-                        if (x >= knext || x < xprev) {
-                            bool fetch = true;
-                            if (kd >= 0 && x >= xprev && x < knext2) {
-                                // one break point crossed: the row fetched ahead
-                                ++kd;
-#pragma unroll
-                                for (int a = 0; a < 5; ++a) dm[a] = dn[a];
-                                knext = knext2;
-                            } else {
-                                // first sample / the phase wrapped / several break points at once: look the row up
-                                int k2 = kd + 1;
-                                if (kd < 0 || x < xprev || x - xprev > 2.0 / kDonorBins) k2 = (int)__ldg(dfirst + donor_bin(x));
-                                double kn = INFINITY;
-                                while (k2 < nb && (kn = __ldg(dkey + k2)) <= x) ++k2;
-                                knext = k2 < nb ? kn : INFINITY;
-                                const double2* row = (const double2*)(dmom + (size_t)k2 * 6);
-                                const double2 a01 = __ldg(row), a23 = __ldg(row + 1), a45 = __ldg(row + 2);
-                                dm[0] = a01.x; dm[1] = a01.y; dm[2] = a23.x; dm[3] = a23.y; dm[4] = a45.x;
-                                kd = k2;
-                                fetch = kd < nb;
-                                if (!fetch) knext2 = INFINITY;
+                        if (x >= kend || x < xprev) {
+                            // the row ended (or the phase wrapped, or this is the first sample): the next row,
+                            // or -- after a jump in phase -- a look-up through the bin table, then a short walk
+                            int k2 = kd + 1;
+                            if (kd < 0 || x < xprev || x - xprev > 2.0 / kDonorBins) k2 = (int)__ldg(dfirst + donor_bin(x));
+                            const double2* row = (const double2*)(dmom + (size_t)k2 * 6);
+                            double2 a01 = __ldg(row), a23 = __ldg(row + 1), a45 = __ldg(row + 2);
+                            while (a45.y <= x) {  // (the last row ends at +inf)
+                                ++k2;
+                                row += 3;
+                                a01 = __ldg(row);
+                                a23 = __ldg(row + 1);
+                                a45 = __ldg(row + 2);
                             }
-                            if (fetch && kd < nb) {
-                                // row kd + 1 and the break point after it, for the next crossing
-                                knext2 = kd + 1 < nb ? __ldg(dkey + kd + 1) : INFINITY;
-                                const double2* row = (const double2*)(dmom + (size_t)(kd + 1) * 6);
-                                const double2 a01 = __ldg(row), a23 = __ldg(row + 1), a45 = __ldg(row + 2);
-                                dn[0] = a01.x; dn[1] = a01.y; dn[2] = a23.x; dn[3] = a23.y; dn[4] = a45.x;
-                            }
+                            dm[0] = a01.x; dm[1] = a01.y; dm[2] = a23.x; dm[3] = a23.y; dm[4] = a45.x;
+                            kend = a45.y;
+                            kd = k2;
                         }
                         xprev = x;
                         f3 = C.f_rs * (dm[0] + dm[1] * cc + dm[2] * ss + dm[3] * (cc * cc) + dm[4] * (cc * ss));
                     }
                     const double bm = C.beam_a * cc + C.beam_b * ss + C.beam_d;
-                    const double beam = C.fis + (1.0 - C.fis) * (bm > 0.0 ? bm : 0.0);
+                    const double beam = b0 + b1 * (bm > 0.0 ? bm : 0.0);  // f_s (fis + (1 - fis) max(bm, 0))
                     if (MODE == 0) {
-                        const double f01 = (C.f_wd + C.f_d) - C.F01 * ((double)run[0] * kInvFix);
-                        const double f2 = C.f_s * beam * (1.0 - (double)run[1] * kInvFix);
+                        const double f01 = f01c - f01k * (double)run[0];
+                        const double f2 = beam - (beam * kInvFix) * (double)run[1];
                         *(double*)cell = f01 + f2 + f3;
                     } else {
                         double* out = (double*)cell;
                         out[0] = C.f_wd * (1.0 - (double)run[0] * kInvFix);
                         out[1] = C.f_d * (1.0 - (double)run[1] * kInvFix);
-                        out[2] = C.f_s * beam * (1.0 - (double)run[2] * kInvFix);
+                        out[2] = beam * (1.0 - (double)run[2] * kInvFix);
                         out[3] = f3;
                     }
                 }

@@ -190,7 +190,7 @@ struct lfb_handle {
     bool graphs_on = true, stages_valid = true;
     long long graph_max_jobs = 1024;
     long long stream_lanes_below = 1536;  // batches smaller than this spread each stream ODE over eight lanes
-    int n_lanes = kLanes;  // LFB_LANES=1 serialises the batches (clean per-stage timings for profiling)
+    int n_lanes = 2;       // LFB_LANES=1 serialises the batches (clean per-stage timings for profiling)
     // layout
     bool have_layout = false, have_lc = false;
     int ndim = 0, n_ecl = 0, npars = 0, n_prior = 0, n_consts = 0;
@@ -1159,7 +1159,7 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
     const long long njobs_all = n * h->n_ecl;
     long long nbatch = (njobs_all + h->max_jobs_per_batch - 1) / h->max_jobs_per_batch;
     if (nbatch < h->n_lanes && njobs_all >= 1024) nbatch = h->n_lanes;
-    if (h->n_lanes > 1 && nbatch > 1 && (nbatch & 1)) ++nbatch;
+    if (h->n_lanes > 1 && nbatch > 1) nbatch = (nbatch + h->n_lanes - 1) / h->n_lanes * h->n_lanes;  // the lanes get equal shares
     const long long per = (n + nbatch - 1) / nbatch;
     int used = 0;
     long long b = 0;
