@@ -237,11 +237,21 @@ def run_gpu(args, rank, local_rank, world):
     theta_d = torch.from_numpy(theta_h).cuda()
     lnp_d = torch.empty(n, dtype=torch.float64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 2x the 126 MB L2
+    peer = None
     if world > 1:
-        # ONE packed buffer per rank -- positions and ln_prob side by side -- gathered once per step
+        # ONE packed buffer per rank -- positions and ln_prob side by side -- gathered once per step: stored
+        # straight into every peer's HBM over NVLink by the engine's own kernel (csrc/peer.cuh); NCCL's
+        # all-gather where the peers' windows cannot be mapped
         packed = torch.empty(n, wl.ndim + 1, dtype=torch.float64, device="cuda")
         packed[:, : wl.ndim] = theta_d
         gathered = torch.empty(world * n, wl.ndim + 1, dtype=torch.float64, device="cuda")
+        if not os.environ.get("LFB_BENCH_NCCL"):
+            peer = parallel.PeerExchange(eng, n * (wl.ndim + 1) * 8)
+            if not peer.available:
+                if rank == 0:
+                    print("bench.py: peer exchange unavailable (%s): NCCL all-gather" % peer.why, file=sys.stderr)
+                peer = None
+    gathered_ptr = [0]
     # a dedicated non-default stream: the C ABI reads a NULL stream as "the handle's own stream",
     # and torch's default stream has handle 0
     tstream = torch.cuda.Stream()
@@ -251,7 +261,9 @@ def run_gpu(args, rank, local_rank, world):
 
     def step():
         eng.log_prob_device(theta_d.data_ptr(), n, lnp_d.data_ptr(), what=_cabi.LN_PROB, stream=stream)
-        if world > 1:
+        if peer is not None:
+            gathered_ptr[0] = peer.allgather(theta_d.data_ptr(), wl.ndim, lnp_d.data_ptr(), 1, n, stream)
+        elif world > 1:
             packed[:, wl.ndim].copy_(lnp_d)
             dist.all_gather_into_tensor(gathered, packed)
 
@@ -290,6 +302,9 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         # what was gathered is what was computed: this rank's slice holds its own positions and ln_probs, and
         # every rank holds the same gathered buffer
+        if peer is not None:
+            assert not peer.timed_out(), "a rank never arrived at an exchange"
+            gathered = peer.view(gathered_ptr[0], n, wl.ndim + 1).reshape(world * n, wl.ndim + 1).clone()
         mine = gathered[rank * n:(rank + 1) * n]
         gather_ok = bool(torch.equal(mine[:, wl.ndim], lnp_d) and torch.equal(mine[:, : wl.ndim], theta_d))
         chk = torch.nan_to_num(gathered[:, wl.ndim], neginf=-1e300).sum().reshape(1)
@@ -302,6 +317,10 @@ def run_gpu(args, rank, local_rank, world):
         gather_ok = bool(flag.item() == 1.0)
         assert gather_ok, "the all-gathered positions / log-probs differ from what the ranks computed"
 
+    peer_used = peer is not None
+    if peer is not None:
+        peer.close()     # (every rank is past its last exchange: the barrier above; the sharded sampler opens its own)
+        peer = None
     # end to end through the public host API: pinned H2D of theta + D2H of ln_prob every step
     e2e_steps = args.steps
     if world > 1:
@@ -372,10 +391,12 @@ def run_gpu(args, rank, local_rank, world):
         emcee["sharded_ranks_agree"] = bool(torch.equal(lo, hi))
         assert emcee["sharded_ranks_agree"], "the ranks of the sharded sampler hold different ensembles"
         emcee["device_acceptance_fraction"] = float((ss.naccepted / max(ss.iterations, 1)).mean())
+        ss_exchange = "peer stores over NVLink, csrc/peer.cuh" if ss.exchange == "peer" else "nccl all_gather_into_tensor"
         ss.close()
     emcee["sharded_ensemble_walkers"] = total_walkers
     emcee["sharded_note"] = ("device-resident stretch move (csrc/sampler.cuh), ONE ensemble of %d walkers over %d GPU(s), "
-                             "one packed all-gather of [rows, ndim + 2] per half-step" % (total_walkers, world))
+                             "one packed all-gather of [rows, ndim + 2] per half-step%s" % (
+                                 total_walkers, world, "" if world == 1 else " (exchange: %s)" % ss_exchange))
     emcee["sharded_lightcurve_evals_per_s"] = emcee["sharded_steps_per_s"] * total_walkers * wl.n_ecl
 
     # clean per-stage device times for the roofline: the same pass with the two batch lanes
@@ -483,8 +504,12 @@ def run_gpu(args, rank, local_rank, world):
                        "n_phase": wl.n_ph, "ndim": wl.ndim, "grid": eng.config,
                        "l2": "flushed between timed iterations (256 MB fill)",
                        "parallelism": "walkers sharded, %d rank(s)" % world,
-                       "collective": ("ONE nccl all_gather per step of a packed [walkers, ndim + 1] buffer "
-                                      "(positions + ln_prob); gathered == computed checked") if world > 1 else "none"},
+                       "collective": "none" if world == 1 else (
+                           ("ONE exchange per step of the packed [walkers, ndim + 1] rows (positions + ln_prob): the engine's "
+                            "own kernel stores them into every peer's HBM over NVLink and the ranks meet on device-side "
+                            "flags (csrc/peer.cuh); gathered == computed checked") if peer_used else
+                           ("ONE nccl all_gather per step of a packed [walkers, ndim + 1] buffer "
+                            "(positions + ln_prob); gathered == computed checked"))},
             "ensemble_passes_per_s": args.steps / (total_ms * 1e-3),
             "gather_verified": gather_ok,
             "gp_likelihood": gp,

@@ -225,6 +225,25 @@ enum {
 int lfb_set_trace(lfb_handle *h, int on);
 int lfb_last_trace_ms(lfb_handle *h, float out[LFB_K_COUNT + 1]);
 
+/* ---- Exchange of positions and log-probabilities between the GPUs of one box over NVLink peer memory ----
+ * Replaces the hand-back of the workers' results to the parent of the reference's multiprocessing.Pool
+ * (mcmcfit.py:273-288); north_star's all-gather per stretch-move half-step.  One process per GPU:
+ *   lfb_peer_create   allocates this rank's window (2 buffers of world slots of slot_bytes) and returns its CUDA
+ *                     IPC handle; the caller exchanges the 64-byte handles of all ranks (any transport),
+ *   lfb_peer_connect  maps the peers' windows, handles[world][64] in rank order,
+ *   lfb_peer_allgather packs rows [a row | b row] (a: rows x ca, b: rows x cb doubles on the device; cb may be 0),
+ *                     stores them into slot `rank` of every rank's window with one kernel, raises this rank's flag
+ *                     everywhere and waits -- on the device, on `stream` -- for every rank's flag.  *gathered =
+ *                     this step's buffer in the local window, [world][slot_bytes], valid to work queued on `stream`
+ *                     until the next-but-one exchange.  All ranks must call it the same number of times.
+ *   lfb_peer_status   synchronises and reports whether an exchange gave up waiting for a peer (~30 s). */
+int lfb_peer_create(lfb_handle *h, int rank, int world, long long slot_bytes, unsigned char handle_out[64]);
+int lfb_peer_connect(lfb_handle *h, const unsigned char *handles);
+int lfb_peer_allgather(lfb_handle *h, const double *a, int ca, const double *b, int cb, long long rows,
+                       const double **gathered, void *stream);
+int lfb_peer_status(lfb_handle *h, int *timed_out);
+void lfb_peer_destroy(lfb_handle *h);
+
 /* Measurement aid (no reference counterpart): sustained FP64 FMA rate of the device in
  * TFLOP/s (FMA = 2), the roofline denominator bench.py reports against. */
 int lfb_measure_fp64_peak(lfb_handle *h, int iters, double *tflops);

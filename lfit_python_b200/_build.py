@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "lfit_cabi.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "cv_kernels.cuh"), os.path.join(HERE, "csrc", "roche_device.cuh"),
         os.path.join(HERE, "csrc", "gp_device.cuh"), os.path.join(HERE, "csrc", "sampler.cuh"),
-        os.path.join(HERE, "csrc", "angle_table.inc"),
+        os.path.join(HERE, "csrc", "angle_table.inc"), os.path.join(HERE, "csrc", "peer.cuh"),
         os.path.join(HERE, "..", "include", "lfit_b200.h")]
 LIB = os.path.join(HERE, "liblfit_b200.so")
 

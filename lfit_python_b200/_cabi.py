@@ -27,6 +27,7 @@ EXPORTS = (
     "lfb_sampler_half_end", "lfb_sampler_packed", "lfb_sampler_positions", "lfb_sampler_log_prob",
     "lfb_sampler_get_state", "lfb_sampler_set_chain", "lfb_sampler_read_chain", "lfb_stretch_draws",
     "lfb_chain_format", "lfb_chain_append", "lfb_robust_calls",
+    "lfb_peer_create", "lfb_peer_connect", "lfb_peer_allgather", "lfb_peer_status", "lfb_peer_destroy",
 )
 TRACE_KERNELS = ("walker_kernel", "jobcheck_kernel", "elements_kernel<1> disc", "elements_kernel<0> white dwarf",
                  "elements_kernel<3> donor (side stream)", "donor_table_kernel (side stream)", "prep_kernel", "positions_kernel", "elements_kernel<2> strip",
@@ -108,6 +109,12 @@ def load():
     lib.lfb_chain_format.argtypes = [ll, ll, C.c_int, dp, C.c_char_p, ll]
     lib.lfb_chain_format.restype = ll
     lib.lfb_chain_append.argtypes = [C.c_char_p, ll, ll, C.c_int, dp]
+    lib.lfb_peer_create.argtypes = [vp, C.c_int, C.c_int, ll, C.c_char_p]
+    lib.lfb_peer_connect.argtypes = [vp, C.c_char_p]
+    lib.lfb_peer_allgather.argtypes = [vp, vp, C.c_int, vp, C.c_int, ll, C.POINTER(vp), vp]
+    lib.lfb_peer_status.argtypes = [vp, ip]
+    lib.lfb_peer_destroy.argtypes = [vp]
+    lib.lfb_peer_destroy.restype = None
     _lib = lib
     return lib
 

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "cv_kernels.cuh"
+#include "peer.cuh"
 
 using namespace lfb;
 
@@ -205,6 +206,16 @@ struct lfb_handle {
     bool h2d_pending = false;  // the last call staged theta through h_in and returned without synchronising
     // bumped when a buffer a captured graph may point into moves (the lanes' buffers, theta / out / chisq staging)
     unsigned long long alloc_generation = 0;
+    // exchange over NVLink peer memory (lfb_peer_*): this rank's window and the peers' windows as mapped here
+    struct Peer {
+        int rank = -1, world = 0;
+        long long slot_bytes = 0;
+        size_t bytes = 0;
+        unsigned char* win[kMaxPeers] = {};
+        unsigned int* ticket = nullptr;
+        unsigned long long step = 0;
+        bool connected = false;
+    } peer;
     lfb_handle()
     {
         h_in.pinned_host = h_out.pinned_host = h_chisq.pinned_host = true;
@@ -889,6 +900,116 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
     return LFB_OK;
 }
 
+// ---- exchange over NVLink peer memory (peer.cuh) ----
+void lfb_peer_destroy(lfb_handle* h)
+{
+    if (!h || h->peer.world == 0) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < h->peer.world; ++p)
+        if (p != h->peer.rank && h->peer.win[p]) cudaIpcCloseMemHandle(h->peer.win[p]);
+    if (h->peer.rank >= 0 && h->peer.win[h->peer.rank]) cudaFree(h->peer.win[h->peer.rank]);
+    if (h->peer.ticket) cudaFree(h->peer.ticket);
+    h->peer = lfb_handle::Peer();
+}
+
+int lfb_peer_create(lfb_handle* h, int rank, int world, long long slot_bytes, unsigned char handle_out[64])
+{
+    if (!h || !handle_out || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || slot_bytes <= 0 || (slot_bytes & 7))
+        return h ? fail(h, LFB_EINVAL, "peer_create: need 1 <= world <= 16, 0 <= rank < world, slot_bytes a positive multiple of 8") : LFB_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the IPC handle is what the header promises");
+    CK(cudaSetDevice(h->device));
+    lfb_peer_destroy(h);
+    lfb_handle::Peer& P = h->peer;
+    P.bytes = (size_t)kPeerHeader + 2 * (size_t)world * (size_t)slot_bytes;
+    void* w = nullptr;
+    CK(cudaMalloc(&w, P.bytes));
+    cudaError_t e = cudaMemset(w, 0, P.bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&P.ticket, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(P.ticket, 0, sizeof(unsigned int));
+    cudaIpcMemHandle_t ipc;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&ipc, w);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(w);
+        if (P.ticket) cudaFree(P.ticket);
+        P = lfb_handle::Peer();
+        return fail(h, LFB_ECUDA, std::string("peer_create: ") + cudaGetErrorString(e));
+    }
+    P.rank = rank;
+    P.world = world;
+    P.slot_bytes = slot_bytes;
+    P.win[rank] = (unsigned char*)w;
+    memcpy(handle_out, &ipc, 64);
+    return LFB_OK;
+}
+
+int lfb_peer_connect(lfb_handle* h, const unsigned char* handles)
+{
+    if (!h || !handles || h->peer.world == 0) return h ? fail(h, LFB_ESTATE, "peer_connect: call peer_create first") : LFB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    lfb_handle::Peer& P = h->peer;
+    for (int p = 0; p < P.world; ++p) {
+        if (p == P.rank || P.win[p]) continue;
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, handles + 64 * (size_t)p, 64);
+        void* w = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&w, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, LFB_ECUDA, std::string("peer_connect: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        }
+        P.win[p] = (unsigned char*)w;
+    }
+    P.connected = true;
+    return LFB_OK;
+}
+
+int lfb_peer_allgather(lfb_handle* h, const double* a, int ca, const double* b, int cb, long long rows,
+                       const double** gathered, void* stream_v)
+{
+    if (!h) return LFB_EINVAL;
+    lfb_handle::Peer& P = h->peer;
+    if (!P.connected) return fail(h, LFB_ESTATE, "peer_allgather: call peer_create and peer_connect first");
+    if (!a || ca < 1 || cb < 0 || (cb && !b) || rows < 0 || rows * (long long)(ca + cb) * 8 > P.slot_bytes)
+        return fail(h, LFB_EINVAL, "peer_allgather: rows do not fit the slot");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    PeerArgs A;
+    A.a = a;
+    A.b = b;
+    A.ca = ca;
+    A.cb = cb;
+    A.rows = rows;
+    for (int p = 0; p < kMaxPeers; ++p) A.win[p] = P.win[p];
+    A.rank = P.rank;
+    A.world = P.world;
+    A.step = ++P.step;
+    A.buf = (int)(A.step & 1);
+    A.slot_bytes = P.slot_bytes;
+    A.ticket = P.ticket;
+    A.spin_limit = 60000000000LL;  // ~30 s of SM clocks: a rank that died must not hang its peers for ever
+    const long long total = rows * (ca + cb);
+    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count);
+    if (blocks < 1) blocks = 1;
+    peer_allgather_kernel<<<blocks, 256, 0, st>>>(A);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (gathered) *gathered = (const double*)(P.win[P.rank] + kPeerHeader + (size_t)A.buf * P.world * P.slot_bytes);
+    return LFB_OK;
+}
+
+int lfb_peer_status(lfb_handle* h, int* timed_out)
+{
+    if (!h || !timed_out || h->peer.world == 0) return h ? fail(h, LFB_ESTATE, "peer_status: no window") : LFB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    unsigned int v = 0;
+    CK(cudaMemcpy(&v, h->peer.win[h->peer.rank] + kMaxPeers * 8, sizeof(v), cudaMemcpyDeviceToHost));
+    *timed_out = (int)v;
+    return LFB_OK;
+}
+
 void lfb_destroy(lfb_handle* h)
 {
     if (!h) return;
@@ -903,6 +1024,7 @@ void lfb_destroy(lfb_handle* h)
     h->gp_dist.release();
     h->lc.release();
     h->cf_lc.release();
+    lfb_peer_destroy(h);
     for (int i = 0; i < kLanes; ++i) {
         if (h->lanes[i].st) cudaStreamSynchronize(h->lanes[i].st);
         h->lanes[i].destroy();

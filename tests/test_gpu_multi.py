@@ -51,7 +51,37 @@ def _worker(rank, world, port, out_dir):
     np.save(os.path.join(out_dir, "pos_%d.npy" % rank), pos)
     np.save(os.path.join(out_dir, "slnp_%d.npy" % rank), lnp)
     np.save(os.path.join(out_dir, "acc_%d.npy" % rank), smp.naccepted)
+    with open(os.path.join(out_dir, "exchange_%d.txt" % rank), "w") as f:
+        f.write(smp.exchange)
     smp.close()
+    # the same chain with the library collective: the exchange cannot change a bit
+    smp = ShardedDeviceSampler(eng, 256, seed=11, exchange="nccl")
+    smp.set_state(theta0)
+    smp.run(6)
+    pos2, lnp2 = smp.get_state()
+    assert smp.exchange == "nccl" and np.array_equal(pos, pos2) and np.array_equal(lnp, lnp2)
+    smp.close()
+    # the exchange itself: rows [a | b] of every rank, many rounds back to back (the two buffers of a window
+    # alternate; a rank may run one exchange ahead of its peers), against NCCL's all-gather of the same rows
+    from lfit_python_b200.parallel import PeerExchange
+    rows, ca, cb = 37, 5, 2
+    px = PeerExchange(eng, rows * (ca + cb) * 8)
+    if px.available:
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            for it in range(40):
+                a = torch.full((rows, ca), float(rank * 1000 + it), dtype=torch.float64, device="cuda") + torch.arange(ca, device="cuda")
+                b = -torch.arange(rows * cb, dtype=torch.float64, device="cuda").reshape(rows, cb) - it
+                ptr = px.allgather(a.data_ptr(), ca, b.data_ptr(), cb, rows, st.cuda_stream)
+                got = px.view(ptr, rows, ca + cb).clone()
+                want = torch.empty(world, rows, ca + cb, dtype=torch.float64, device="cuda")
+                dist.all_gather_into_tensor(want, torch.cat([a, b], dim=1).contiguous())
+                assert torch.equal(got, want), "peer exchange differs from NCCL at round %d" % it
+                if rank == 0 and it % 7 == 0:
+                    torch.cuda._sleep(20_000_000)     # a slow rank: its peers run ahead as far as the protocol lets them
+        st.synchronize()
+        assert not px.timed_out()
+        px.close()
     dist.barrier()
     dist.destroy_process_group()
     eng.close()
@@ -85,3 +115,5 @@ def test_two_rank_nccl_equals_one_gpu(tmp_path):
         assert np.array_equal(np.load(tmp_path / ("acc_%d.npy" % r)), smp.naccepted)
     smp.close()
     eng.close()
+    # (informative) which exchange the sharded sampler used on this box
+    print("exchange:", [open(tmp_path / ("exchange_%d.txt" % r)).read() for r in range(2)])
