@@ -74,6 +74,7 @@ struct DevSamples {
     const double *y, *iye;       // [total] in phase order: flux, 1 / error
     const double *S, *cosS, *sinS;  // [K * total] sorted per eclipse
     const int* bins;             // [K * total + n_ecl] per eclipse M + 1 entries (see SampleAxis)
+    const double4* axis;         // [n_ecl] first and last sample phase, bins per unit phase (see SampleAxis)
     const int* pos;              // [total * K] sorted position of each (point, node); points in phase order
     const int* pt_index;         // [total] original index of each phase-ordered point
     const double *gp_x, *gp_var; // [total] GP likelihood: raw phases ascending per eclipse, noise variances
@@ -599,9 +600,10 @@ __device__ __forceinline__ SampleAxis sample_axis(const DevSamples& smp, int e, 
     X.M = (int)(smp.lc_off[e + 1] - lc0) * K;
     X.S = smp.S + lc0 * K;
     X.bins = smp.bins + lc0 * K + e;
-    X.s_first = X.M > 0 ? __ldg(X.S) : 0.0;
-    X.s_last = X.M > 0 ? __ldg(X.S + X.M - 1) : 0.0;
-    X.inv_binw = X.s_last > X.s_first ? (double)X.M / (X.s_last - X.s_first) : 0.0;
+    const double2 fl = __ldg((const double2*)(smp.axis + e));
+    X.s_first = fl.x;
+    X.s_last = fl.y;
+    X.inv_binw = __ldg((const double*)(smp.axis + e) + 2);
     return X;
 }
 
@@ -669,9 +671,13 @@ __device__ __forceinline__ EventRec no_events()
 // and exposures are shorter than an orbit, so the axis spans less than two cycles and b - a < 1:
 // at most three shifts contribute.  Each piece is (first sample inside, first sample at or past
 // the end); kAtStart = open before the first sample, kNoEvent = nothing.
-__device__ __forceinline__ EventRec interval_pieces(const SampleAxis& X, double a, double b)
+__device__ __forceinline__ EventRec interval_pieces(const SampleAxis& X, double a, double b, int& lo, int& hi)
 {
+    // lo / hi: the span of the record's events on the axis as rec_first / rec_last_close would read them back
+    // (kNoEvent / -2 for an empty record; hi = kNoEvent when the last piece stays open to the end)
     int ev[6] = {kNoEvent, kNoEvent, kNoEvent, kNoEvent, kNoEvent, kNoEvent};
+    lo = kNoEvent;
+    hi = -2;
     if ((a < b) && (a > -1e29) && (b < 1e29) && X.M > 0) {
         int n_lo = (int)ceil(X.s_first - b), n_hi = (int)floor(X.s_last - a);
         int np = 0;
@@ -682,22 +688,15 @@ __device__ __forceinline__ EventRec interval_pieces(const SampleAxis& X, double 
             if (pc <= po) continue;  // no sample inside
             if (po == 0) po = kAtStart;
             if (pc >= X.M) pc = kNoEvent;
-            if (np == 0) { ev[0] = po; ev[1] = pc; }
+            if (np == 0) { ev[0] = po; ev[1] = pc; lo = po; }
             else if (np == 1) { ev[2] = po; ev[3] = pc; }
             else { ev[4] = po; ev[5] = pc; }
+            hi = pc;
             ++np;
         }
     }
     return make_ulonglong2(enc_pos(ev[0]) | (enc_pos(ev[1]) << 21) | (enc_pos(ev[2]) << 42),
                            enc_pos(ev[3]) | (enc_pos(ev[4]) << 21) | (enc_pos(ev[5]) << 42));
-}
-
-// position of the last closing event of a record (kNoEvent if it stays open to the end; -2 if empty)
-__device__ __forceinline__ int rec_last_close(const EventRec& rec)
-{
-    if (dec_pos(rec.x, 0) == kNoEvent) return -2;
-    const int o1 = dec_pos(rec.x, 2), o2 = dec_pos(rec.y, 1);
-    return o2 != kNoEvent ? dec_pos(rec.y, 2) : (o1 != kNoEvent ? dec_pos(rec.y, 0) : dec_pos(rec.x, 1));
 }
 
 // prep_strip_kernel: warp per job, after the strip solve (which waits for the stream ODE): fixed-point
@@ -762,16 +761,15 @@ __global__ void __launch_bounds__(128) positions_kernel(const __grid_constant__ 
             i0 = G.n_wd + 2 * h;
         }
         const bool ecl = io.y > io.x;
-        const EventRec r0 = ecl ? interval_pieces(X, io.x + phi0w, io.y + phi0w) : none;
+        const EventRec r0 = ecl ? interval_pieces(X, io.x + phi0w, io.y + phi0w, lo, hi) : none;
         ivp[__ldg(G.rec_slot + i0)] = r0;
-        lo = dec_pos(r0.x, 0);
-        hi = rec_last_close(r0);
         // the y -> -y image is eclipsed from -egress to -ingress
         if (mirror) {
-            const EventRec r1 = ecl ? interval_pieces(X, -io.y + phi0w, -io.x + phi0w) : none;
+            int lo1 = kNoEvent, hi1 = -2;
+            const EventRec r1 = ecl ? interval_pieces(X, -io.y + phi0w, -io.x + phi0w, lo1, hi1) : none;
             ivp[__ldg(G.rec_slot + i0 + 1)] = r1;
-            lo = min(lo, dec_pos(r1.x, 0));
-            hi = max(hi, rec_last_close(r1));
+            lo = min(lo, lo1);
+            hi = max(hi, hi1);
         }
     }
     // span of the job's eclipse events (lets segments far from the eclipse skip the tile records)

@@ -53,7 +53,7 @@ struct DevBuf {
 
 // Sorted exposure samples of a set of light curves (device copies)
 struct SampleSet {
-    DevBuf lc_off, y, ye, S, cosS, sinS, bins, pos, pt_index, chunk_off, chunks, seg_tr;
+    DevBuf lc_off, y, ye, S, cosS, sinS, bins, pos, pt_index, chunk_off, chunks, seg_tr, axis;
     DevBuf gp_x, gp_var, gp_slot, gp_span;  // GP likelihood: points in ascending raw phase
     int max_chunks = 1;
     int max_nph = 0;
@@ -61,7 +61,7 @@ struct SampleSet {
     long long total = 0;
     void release()
     {
-        DevBuf* b[] = {&lc_off, &y, &ye, &S, &cosS, &sinS, &bins, &pos, &pt_index, &chunk_off, &chunks, &seg_tr,
+        DevBuf* b[] = {&lc_off, &y, &ye, &S, &cosS, &sinS, &bins, &pos, &pt_index, &chunk_off, &chunks, &seg_tr, &axis,
                        &gp_x, &gp_var, &gp_slot, &gp_span};
         for (DevBuf* x : b) x->release();
     }
@@ -75,6 +75,7 @@ struct SampleSet {
         v.cosS = cosS.as<double>();
         v.sinS = sinS.as<double>();
         v.bins = bins.as<int>();
+        v.axis = axis.as<double4>();
         v.pos = pos.as<int>();
         v.pt_index = pt_index.as<int>();
         v.gp_x = gp_x.as<double>();
@@ -191,6 +192,7 @@ struct lfb_handle {
     bool graphs_on = true, stages_valid = true;
     long long graph_max_jobs = 1024;
     long long stream_lanes_below = 1536;  // batches smaller than this spread each stream ODE over eight lanes
+    size_t flux_smem_pad = 0, donor_smem_pad = 0;  // tuning: extra dynamic shared memory = fewer resident CTAs per SM
     int n_lanes = 2;       // LFB_LANES=1 serialises the batches (clean per-stage timings for profiling)
     // layout
     bool have_layout = false, have_lc = false;
@@ -302,6 +304,7 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int NT, int RP, int n_ecl
     std::vector<double> gp_x((size_t)total), gp_var((size_t)total);
     std::vector<int> gp_slot((size_t)total), gp_rank;
     std::vector<double2> gp_span((size_t)std::max(n_ecl, 1));
+    std::vector<double4> axis((size_t)std::max(n_ecl, 1), make_double4(0.0, 0.0, 0.0, 0.0));
     std::vector<long long> chunk_off(n_ecl + 1, 0);
     std::vector<int4> chunks;
     int max_nph = 0, max_chunks = 1, max_gaps = 0;
@@ -350,6 +353,7 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int NT, int RP, int n_ecl
             int* bt = bins.data() + o * K + e;
             const double s0 = S[o * K], s1 = S[o * K + M - 1];
             const double inv_binw = s1 > s0 ? (double)M / (s1 - s0) : 0.0;
+            axis[e] = make_double4(s0, s1, inv_binw, 0.0);
             int r = 0;
             for (int b = 0; b <= M; ++b) {
                 while (r < M) {
@@ -448,6 +452,7 @@ static int build_samples(lfb_handle* h, SampleSet& ss, int NT, int RP, int n_ecl
     if ((rc = upload(h, ss.cosS, cS.data(), sizeof(double) * cS.size()))) return rc;
     if ((rc = upload(h, ss.sinS, sS.data(), sizeof(double) * sS.size()))) return rc;
     if ((rc = upload(h, ss.bins, bins.data(), sizeof(int) * bins.size()))) return rc;
+    if ((rc = upload(h, ss.axis, axis.data(), sizeof(double4) * axis.size()))) return rc;
     if ((rc = upload(h, ss.pos, pos.data(), sizeof(int) * pos.size()))) return rc;
     if ((rc = upload(h, ss.pt_index, pt_index.data(), sizeof(int) * pt_index.size()))) return rc;
     if ((rc = upload(h, ss.gp_x, gp_x.data(), sizeof(double) * gp_x.size()))) return rc;
@@ -582,7 +587,7 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
     }
     CK(cudaEventRecord(ln.wd_ev, ln.side2));
     if (what != LFB_LN_PRIOR && !(flags & LFB_FLAG_SKIP_DONOR)) {
-        const size_t dsm = 224 * (size_t)G.n_donor_q + 4 * (kDonorBins + 1) + 64;
+        const size_t dsm = 224 * (size_t)G.n_donor_q + 4 * (kDonorBins + 1) + 64 + h->donor_smem_pad;
         if (dsm > (size_t)h->max_smem - 2048) return fail(h, LFB_EINVAL, "donor grid too dense for the table kernel's shared memory");
         if (trace) CK(cudaEventRecord(ln.dev[0], ln.side2));
         elements_kernel<3><<<blocks(n, G.n_donor_q), kElemThreads, 0, ln.side2>>>(E);
@@ -658,7 +663,7 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         KSYNC("positions_kernel");
         h->launches += 2;
         const FluxShape fs = flux_shape(h, mode);
-        const size_t smem = (size_t)fs.NT * fs.RP * (mode ? 32 : 16);
+        const size_t smem = (size_t)fs.NT * fs.RP * (mode ? 32 : 16) + h->flux_smem_pad;
         const dim3 fgrid((unsigned)njobs);
         CK(cudaStreamWaitEvent(st, ln.don_ev, 0));  // the donor tables (second side stream)
         KREC(LFB_K_FLUX);
@@ -886,6 +891,8 @@ int lfb_create(int device, const lfb_config* cfg_in, lfb_handle** out)
         int v = atoi(env);
         if (v >= 0 && v <= 2) h->flux_variant = v;
     }
+    if (const char* env = getenv("LFB_FLUX_SMEM_PAD")) h->flux_smem_pad = (size_t)std::max(0, atoi(env));
+    if (const char* env = getenv("LFB_DONOR_SMEM_PAD")) h->donor_smem_pad = (size_t)std::max(0, atoi(env));
     if (const char* env = getenv("LFB_LANES")) {
         int v = atoi(env);
         if (v >= 1 && v <= kLanes) h->n_lanes = v;

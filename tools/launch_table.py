@@ -16,7 +16,7 @@ import sys
 from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CSRC = ("cv_kernels.cuh", "roche_device.cuh", "gp_device.cuh", "lfit_cabi.cu", "sampler.cuh")
+CSRC = ("cv_kernels.cuh", "roche_device.cuh", "gp_device.cuh", "lfit_cabi.cu", "sampler.cuh", "peer.cuh", "angle_table.inc")
 
 
 def csrc_sha():
@@ -51,9 +51,10 @@ def main(path, n_lc=None, json_out=None):
             if k != "name":
                 a[k] = a.get(k, 0.0) + v
     tot_t = sum(a.get('gpu__time_duration.sum', 0) / a["n"] for a in agg.values())
-    print("%-34s %4s %10s %6s %12s %9s %7s %10s" % ("kernel", "n", "time_us", "share", "fp64_flop", "TFLOP/s", "lanes",
-                                                     "dram_MB"))
+    print("%-34s %4s %10s %6s %12s %9s %7s %10s %11s %7s" % ("kernel", "n", "time_us", "share", "fp64_flop", "TFLOP/s", "lanes",
+                                                             "dram_MB", "warp_inst", "issue%"))
     tot_f = 0.0
+    tot_i = 0.0
     kern = OrderedDict()
     for name, a in agg.items():
         n = a["n"]
@@ -65,14 +66,16 @@ def main(path, n_lc=None, json_out=None):
         lanes = a.get('smsp__thread_inst_executed_per_inst_executed.ratio', 0) / n
         dram = (a.get('dram__bytes_read.sum', 0) + a.get('dram__bytes_write.sum', 0)) / n
         smem_wf = a.get('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 0) / n
+        winst = a.get('smsp__inst_executed.sum', 0) / n
+        issue = a.get('smsp__issue_active.avg.pct_of_peak_sustained_active', 0) / n
+        tot_i += winst
         kern[name] = {"launches": n, "time_us": t, "fp64_flop": fl, "dram_bytes": dram, "smem_wavefronts": smem_wf,
-                      "lanes": lanes}
-        print("%-34s %4d %10.1f %5.1f%% %12.4g %9.2f %7.1f %10.2f" % (name[:34], n, t, 100 * t * 1e3 / tot_t, fl,
-                                                                      fl / (t * 1e-6) * 1e-12 if t else 0, lanes,
-                                                                      dram * 1e-6))
-    print("sum of kernel times %.1f us, FP64 flop per pass %.4g" % (tot_t * 1e-3, tot_f))
+                      "lanes": lanes, "warp_inst": winst, "issue_active_pct": issue}
+        print("%-34s %4d %10.1f %5.1f%% %12.4g %9.2f %7.1f %10.2f %11.4g %7.1f" % (
+            name[:34], n, t, 100 * t * 1e3 / tot_t, fl, fl / (t * 1e-6) * 1e-12 if t else 0, lanes, dram * 1e-6, winst, issue))
+    print("sum of kernel times %.1f us, FP64 flop per pass %.4g, warp instructions per pass %.4g" % (tot_t * 1e-3, tot_f, tot_i))
     if n_lc:
-        print("FP64 flop per light curve: %.4g" % (tot_f / n_lc))
+        print("FP64 flop per light curve: %.4g; warp instructions per light curve: %.4g" % (tot_f / n_lc, tot_i / n_lc))
     if json_out and n_lc:
         def grp(pred, key):
             return sum(k[key] for nm, k in kern.items() if pred(nm)) / n_lc
@@ -83,6 +86,9 @@ def main(path, n_lc=None, json_out=None):
                 "elements_flop": grp(lambda nm: nm.startswith("elements_kernel") or nm.startswith("stage1_kernel"), "fp64_flop"),
                 "flux_flop": grp(lambda nm: nm.startswith("flux_kernel"), "fp64_flop"),
                 "all_flop": tot_f / n_lc,
+                "all_warp_inst": tot_i / n_lc,
+                "elements_warp_inst": grp(lambda nm: nm.startswith("elements_kernel"), "warp_inst"),
+                "flux_warp_inst": grp(lambda nm: nm.startswith("flux_kernel"), "warp_inst"),
                 "elements_dram_bytes": grp(lambda nm: nm.startswith("elements_kernel") or nm.startswith("stage1_kernel"), "dram_bytes"),
                 "flux_dram_bytes": grp(lambda nm: nm.startswith("flux_kernel"), "dram_bytes"),
                 "flux_smem_wavefronts": grp(lambda nm: nm.startswith("flux_kernel"), "smem_wavefronts"),
