@@ -474,6 +474,20 @@ def run_gpu(args, rank, local_rank, world):
                                 "note": "FP64 operations the kernels EXECUTE (ncu, FMA = 2; the FP32 warm-up of the Newton "
                                         "iterations is not counted)"}
             roof["whole_pass"] = {"achieved": tf(pl["all_flop"], k_ms), "frac": tf(pl["all_flop"], k_ms) / fp64_peak}
+            if "all_warp_inst" in pl:
+                # what actually bounds these kernels: instruction issue (one warp instruction per clock per SM sub-partition)
+                n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                issue_peak = n_sm * 4 * sm_mhz * 1e6 * 1e-9
+                gi = lambda winst, ms: winst * per_rank / (ms * 1e-3) * 1e-9
+                roof["issue"] = {
+                    "unit": "G warp-instructions/s", "peak": issue_peak,
+                    "peak_source": "%d SMs x 4 schedulers x %d MHz (the SM clock sampled during the timed region)" % (n_sm, sm_mhz),
+                    "elements": {"achieved": gi(pl["elements_warp_inst"], el_ms), "frac": gi(pl["elements_warp_inst"], el_ms) / issue_peak},
+                    "flux_kernel": {"achieved": gi(pl["flux_warp_inst"], fx_ms), "frac": gi(pl["flux_warp_inst"], fx_ms) / issue_peak},
+                    "whole_pass": {"achieved": gi(pl["all_warp_inst"], k_ms), "frac": gi(pl["all_warp_inst"], k_ms) / issue_peak},
+                    "warp_inst_per_lightcurve": {"elements": pl["elements_warp_inst"], "flux": pl["flux_warp_inst"], "all": pl["all_warp_inst"]},
+                    "note": "warp instructions the kernels execute (ncu smsp__inst_executed.sum) / CUDA-event time; an FP64 "
+                            "instruction holds its issue port for two clocks, so the FP64-heavy kernels saturate below 1.0"}
             roof["kernels"] = {
                 "flux_kernel": {
                     "ms": fx_ms, "share_of_step": fx_ms / serial["total"],
