@@ -279,20 +279,30 @@ def run_gpu(args, rank, local_rank, world):
         dist.barrier()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms, stage_ms = [], []
+    # the K timed steps are queued back to back -- [L2 flush][event][step][event] -- with no host synchronisation in
+    # between, so that the ranks stay in step on the device (a host-side pause on one rank would be waited for
+    # inside the timed region of all the others)
     for i in range(args.steps):
         flush.fill_(float(i))  # evict L2 between timed iterations (outside the event pair)
         ev[i][0].record()
         step()
         ev[i][1].record()
-        ev[i][1].synchronize()
-        kernel_ms.append(eng.last_kernel_ms())
-        stage_ms.append(eng.last_stage_ms())
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     clocks = sampler.stop()
     launches = eng.launch_count - launches0
+    # per-stage device times of the overlapped pipeline: a few more steps, read back one by one
+    kernel_ms, stage_ms = [], []
+    for i in range(min(args.steps, 10)):
+        flush.fill_(float(i))
+        step()
+        torch.cuda.synchronize()
+        kernel_ms.append(eng.last_kernel_ms())
+        stage_ms.append(eng.last_stage_ms())
+    if world > 1:
+        dist.barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
     if world > 1:
