@@ -408,7 +408,8 @@ __global__ void __launch_bounds__(kElemThreads, kElemBlocks) elements_kernel(con
         }
     }
     double pin, pout;
-    if (!ingress_egress(R, si, ci, T, &pin, &pout, (COMP == 0 && W.wd_ok) ? &W.wd : nullptr)) { pin = kBig; pout = -kBig; }
+    // (disc and strip elements lie in the orbital plane: the solver's PLANAR form)
+    if (!ingress_egress<COMP == 1 || COMP == 2>(R, si, ci, T, &pin, &pout, (COMP == 0 && W.wd_ok) ? &W.wd : nullptr)) { pin = kBig; pout = -kBig; }
     if (COMP == 0) A.wd_io[unit * G.n_wd_half + t] = make_double2(pin, pout);
     else if (COMP == 1) A.disc_io[unit * G.n_disc_half + tile] = make_double2(pin, pout);
     else {

@@ -209,14 +209,18 @@ LFB_HD double fast_rcp(double x)
 
 // Potential and its derivatives over the (th, lam) family of LOS of one element, at the
 // orbital angle whose cosine and sine are (c, s).
+// PLANAR: the element lies in the orbital plane with no offset on the sky (disc, bright-spot strip: z = xi = eta
+// = 0) -- the terms that vanish are left out (the compiler may not drop a multiplication by a 0.0 it cannot
+// prove finite-safe).
+template <bool PLANAR = false>
 LFB_HD void ray_eval(const Roche& R, double si, double ci, const Point& T, double c, double s, double lam, Derivs& D)
 {
     LFB_CNT(9);
     double ex = si * c, ey = -si * s;
-    double dx = fma(lam, ex, -T.xi * s - T.eta * ci * c);
-    double dy = fma(lam, ey, -T.xi * c + T.eta * ci * s);
-    double dz = fma(lam, ci, T.eta * si);
-    double x = T.x + dx, y = T.y + dy, z = T.z + dz;
+    double dx = PLANAR ? lam * ex : fma(lam, ex, -T.xi * s - T.eta * ci * c);
+    double dy = PLANAR ? lam * ey : fma(lam, ey, -T.xi * c + T.eta * ci * s);
+    double dz = PLANAR ? lam * ci : fma(lam, ci, T.eta * si);
+    double x = T.x + dx, y = T.y + dy, z = PLANAR ? dz : T.z + dz;
     double tx = dy, ty = -dx;  // d/dth of the part that turns with the observer
     double x2 = x - 1.0;
     double yz = y * y + z * z;
@@ -238,14 +242,15 @@ LFB_HD void ray_eval(const Roche& R, double si, double ci, const Point& T, doubl
 
 // Potential and its derivative along the LOS only (the residuals of the grazing-LOS system): what a Newton
 // step with a frozen Jacobian needs -- about half of ray_eval.
+template <bool PLANAR = false>
 LFB_HD void ray_resid(const Roche& R, double si, double ci, const Point& T, double c, double s, double lam, double& S,
                       double& Sl)
 {
     LFB_CNT(11);
     double ex = si * c, ey = -si * s;
-    double x = T.x + fma(lam, ex, -T.xi * s - T.eta * ci * c);
-    double y = T.y + fma(lam, ey, -T.xi * c + T.eta * ci * s);
-    double z = T.z + fma(lam, ci, T.eta * si);
+    double x = PLANAR ? fma(lam, ex, T.x) : T.x + fma(lam, ex, -T.xi * s - T.eta * ci * c);
+    double y = PLANAR ? fma(lam, ey, T.y) : T.y + fma(lam, ey, -T.xi * c + T.eta * ci * s);
+    double z = PLANAR ? lam * ci : T.z + fma(lam, ci, T.eta * si);
     double x2 = x - 1.0;
     double yz = y * y + z * z;
     double ir1 = fast_rsqrt(x * x + yz), ir2 = fast_rsqrt(x2 * x2 + yz);
@@ -440,14 +445,15 @@ LFB_HD float rcp_f(float x)
 #endif
 }
 
+template <bool PLANAR = false>
 LFB_HD void ray_eval_f(float mu, float omu, float si, float ci, const PointF& T, float c, float s, float lam, DerivsF& D)
 {
     LFB_CNT(10);
     float ex = si * c, ey = -si * s;
-    float dx = fmaf(lam, ex, -T.xi * s - T.eta * ci * c);
-    float dy = fmaf(lam, ey, -T.xi * c + T.eta * ci * s);
-    float dz = fmaf(lam, ci, T.eta * si);
-    float x = T.x + dx, y = T.y + dy, z = T.z + dz;
+    float dx = PLANAR ? lam * ex : fmaf(lam, ex, -T.xi * s - T.eta * ci * c);
+    float dy = PLANAR ? lam * ey : fmaf(lam, ey, -T.xi * c + T.eta * ci * s);
+    float dz = PLANAR ? lam * ci : fmaf(lam, ci, T.eta * si);
+    float x = T.x + dx, y = T.y + dy, z = PLANAR ? dz : T.z + dz;
     float tx = dy, ty = -dx;
     float x2 = x - 1.0f;
     float yz = y * y + z * z;
@@ -481,13 +487,14 @@ LFB_HD void rotate_cs_f(float& c, float& s, float d)
 constexpr int kWarmIters = 10;
 
 // FP32 Newton towards the grazing LOS on side sg of the deepest LOS (cm, sm); true if it settled.
+template <bool PLANAR = false>
 LFB_HD bool warm_root(float mu, float omu, float phic, float si, float ci, const PointF& T, float cm, float sm, float sg,
                       float& c, float& s, float& lam)
 {
     DerivsF D;
     for (int it = 0; it < kWarmIters; ++it) {
         LFB_CNT(13);
-        ray_eval_f(mu, omu, si, ci, T, c, s, lam, D);
+        ray_eval_f<PLANAR>(mu, omu, si, ci, T, c, s, lam, D);
         float F1 = D.S - phic, F2 = D.Sl;
         float idet = rcp_f(D.St * D.Sll - D.Sl * D.Stl);
         float dth = (-F1 * D.Sll + F2 * D.Sl) * idet, dl = (-D.St * F2 + D.Stl * F1) * idet;
@@ -512,12 +519,13 @@ LFB_HD bool warm_root(float mu, float omu, float phic, float si, float ci, const
 // FP32 search for the deepest LOS of an element (the minimum over (th, lam) of the potential along its lines of
 // sight), from the conjunction LOS: Newton on lam alone first, then on both.  1: settled, g0 = depth below the
 // critical potential there (single precision); 0: it did not settle -- the caller searches in FP64 from scratch.
+template <bool PLANAR = false>
 LFB_HD int warm_min(float mu, float omu, float phic, float si, float ci, const PointF& T, float& c, float& s, float& lam,
                     float& g0, DerivsF& D)
 {
     for (int it = 0; it < 5; ++it) {
         LFB_CNT(14);
-        ray_eval_f(mu, omu, si, ci, T, c, s, lam, D);
+        ray_eval_f<PLANAR>(mu, omu, si, ci, T, c, s, lam, D);
         if (!(D.Sll > 0.0f)) return 0;
         float dl = -D.Sl * rcp_f(D.Sll);
         dl = dl > 0.1f ? 0.1f : (dl < -0.1f ? -0.1f : dl);
@@ -525,7 +533,7 @@ LFB_HD int warm_min(float mu, float omu, float phic, float si, float ci, const P
         if (fabsf(dl) < 1e-3f) break;
     }
     for (int it = 0; it < 12; ++it) {
-        ray_eval_f(mu, omu, si, ci, T, c, s, lam, D);
+        ray_eval_f<PLANAR>(mu, omu, si, ci, T, c, s, lam, D);
         float det = D.Stt * D.Sll - D.Stl * D.Stl;
         if (!(D.Sll > 0.0f) || !(det > 0.0f)) return 0;
         float idet = rcp_f(det);
@@ -559,6 +567,7 @@ struct Roots {
 // 2-D Newton on (th, lam) for the grazing LOS (Phi = Phi_c, dPhi/dlam = 0) on either side of the
 // deepest LOS (cm, sm), from the given starts (FP32 warm-up, then FP64).  True if both converged to
 // grazing LOS of the right kind; res = their orbital angles (radians), ingress then egress.
+template <bool PLANAR = false>
 LFB_HD bool graze_roots(const Roche& R, double si, double ci, const Point& T, double cpsi, double spsi, double cm,
                         double sm, const Roots& start, double res[2], Roots* roots)
 {
@@ -573,7 +582,7 @@ LFB_HD bool graze_roots(const Roche& R, double si, double ci, const Point& T, do
 #ifndef LFB_NO_WARMUP
         {
             float cf = (float)c, sf = (float)s, lf = (float)lam;
-            if (warm_root(muf, omuf, phicf, sif, cif, Tf, (float)cm, (float)sm, (float)sg, cf, sf, lf)) {
+            if (warm_root<PLANAR>(muf, omuf, phicf, sif, cif, Tf, (float)cm, (float)sm, (float)sg, cf, sf, lf)) {
                 const double cw = (double)cf, sw = (double)sf;
                 const double nrm = fast_rsqrt(cw * cw + sw * sw);
                 c = cw * nrm;
@@ -584,7 +593,7 @@ LFB_HD bool graze_roots(const Roche& R, double si, double ci, const Point& T, do
 #endif
         bool conv = false;
         for (int it = 0; it < kRootIters; ++it) {
-            ray_eval(R, si, ci, T, c, s, lam, D);
+            ray_eval<PLANAR>(R, si, ci, T, c, s, lam, D);
             double F1 = D.S - R.phic, F2 = D.Sl;
             double idet = fast_rcp(D.St * D.Sll - D.Sl * D.Stl);
             double dth = clampd((-F1 * D.Sll + F2 * D.Sl) * idet, 0.2);
@@ -610,7 +619,7 @@ LFB_HD bool graze_roots(const Roche& R, double si, double ci, const Point& T, do
                 double before = fabs(dth) + 0.1 * fabs(dl);
                 for (int k = 0; k < 2; ++k) {
                     double S2, Sl2;
-                    ray_resid(R, si, ci, T, c, s, lam, S2, Sl2);
+                    ray_resid<PLANAR>(R, si, ci, T, c, s, lam, S2, Sl2);
                     const double G1 = S2 - R.phic;
                     const double dth2 = (-G1 * D.Sll + Sl2 * D.Sl) * idet, dl2 = (-D.St * Sl2 + D.Stl * G1) * idet;
                     const double now = fabs(dth2) + 0.1 * fabs(dl2);
@@ -651,6 +660,7 @@ LFB_HD bool graze_roots(const Roche& R, double si, double ci, const Point& T, do
 // hint: grazing LOS of the element at the origin (the white-dwarf centre, for white-dwarf tiles): tried
 // first as the Newton starts when its eclipse is much wider than this element's offset; roots: where
 // the element's own end up (fast path only).
+template <bool PLANAR = false>
 LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, double* ph_in, double* ph_out,
                           const Roots* hint = nullptr, Roots* roots = nullptr)
 {
@@ -674,7 +684,7 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         // the hinted eclipse is several offsets wide none of this can be confused: solve from the hint.
         const double off = sqrt(T.xi * T.xi + T.eta * T.eta + T.x * T.x + T.y * T.y + T.z * T.z);
         if (-hint->s[0] > 4.0 * off && hint->s[1] > 4.0 * off && hint->c[0] > 0.0 && hint->c[1] > 0.0 &&
-            graze_roots(R, si, ci, T, cpsi, spsi, cpsi, spsi, *hint, res, roots)) {
+            graze_roots<PLANAR>(R, si, ci, T, cpsi, spsi, cpsi, spsi, *hint, res, roots)) {
             LFB_CNT(2);
             *ph_in = res[0] * (1.0 / kTwoPi);
             *ph_out = res[1] * (1.0 / kTwoPi);
@@ -715,7 +725,7 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
             const PointF Tf = {(float)T.x, (float)T.y, (float)T.z, (float)T.xi, (float)T.eta};
             float cf = (float)c, sf = (float)s, lf = (float)lam, g0f = 0.0f;
             DerivsF Df;
-            if (warm_min((float)R.mu, (float)R.omu, (float)R.phic, (float)si, (float)ci, Tf, cf, sf, lf, g0f, Df)) {
+            if (warm_min<PLANAR>((float)R.mu, (float)R.omu, (float)R.phic, (float)si, (float)ci, Tf, cf, sf, lf, g0f, Df)) {
                 if (g0f > kWarmRejectMargin) {
                     LFB_CNT(6);
                     verdict = 0;
@@ -756,7 +766,7 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         }
 #endif
         for (int it = 0; it < 5 && !warmed && verdict < 0; ++it) {
-            ray_eval(R, si, ci, T, c, s, lam, D);
+            ray_eval<PLANAR>(R, si, ci, T, c, s, lam, D);
             if (!(D.Sll > 0.0)) {  // no potential minimum along the closest LOS: out of reach
                 LFB_CNT(5);
                 verdict = 0;
@@ -768,7 +778,7 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         }
         bool conv = starts;
         for (int it = 0; it < kMinIters && verdict < 0 && !starts; ++it) {
-            ray_eval(R, si, ci, T, c, s, lam, D);
+            ray_eval<PLANAR>(R, si, ci, T, c, s, lam, D);
             double det = D.Stt * D.Sll - D.Stl * D.Stl;
             if (!(D.Sll > 0.0) || !(det > 0.0)) {
                 verdict = D.S >= R.phic ? 0 : 2;
@@ -782,7 +792,7 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
         }
         if (verdict < 0 && !conv) verdict = 2;
         if (verdict < 0 && !starts) {
-            ray_eval(R, si, ci, T, c, s, lam, D);
+            ray_eval<PLANAR>(R, si, ci, T, c, s, lam, D);
             double g0 = D.S - R.phic;
             double kappa = D.Stt - D.Stl * D.Stl / D.Sll;
             if (!(g0 < 0.0)) {  // the deepest LOS clears the lobe
@@ -810,7 +820,7 @@ LFB_HD int ingress_egress(const Roche& R, double si, double ci, const Point& T, 
     }
     if (verdict < 0) {
         const Roots start = {{c0, c1}, {s0, s1}, {lam0, lam1}};
-        if (graze_roots(R, si, ci, T, cpsi, spsi, cm, sm, start, res, roots)) verdict = 1;
+        if (graze_roots<PLANAR>(R, si, ci, T, cpsi, spsi, cm, sm, start, res, roots)) verdict = 1;
         else verdict = 2;
     }
     if (verdict == 1) {
