@@ -54,7 +54,8 @@ enum { LFB_PRIOR_GAUSS = 0, LFB_PRIOR_GAUSSPOS, LFB_PRIOR_UNIFORM, LFB_PRIOR_LOG
 enum { LFB_LN_PRIOR = 0, LFB_LN_LIKE = 1, LFB_LN_PROB = 2 };
 
 /* lfb_roche `which` = trm.roche calls on the path (CVModel.py:222,288,460,561) */
-enum { LFB_ROCHE_XL1 = 0, LFB_ROCHE_FINDPHI = 1, LFB_ROCHE_FINDI = 2, LFB_ROCHE_BSPOT = 3 };
+enum { LFB_ROCHE_XL1 = 0, LFB_ROCHE_FINDPHI = 1, LFB_ROCHE_FINDI = 2, LFB_ROCHE_BSPOT = 3,
+       LFB_ROCHE_ANGLE = 4 /* test aid, no reference counterpart: out = the solver's arctangent of the unit vector (a, b) */ };
 
 /* Surface-grid density (the element counts the lfit component constructors take,
  * testCV.py:31,43).  Zero / NULL selects the defaults in brackets. */

@@ -15,7 +15,7 @@ from . import _build
 NPAR = 18
 LN_PRIOR, LN_LIKE, LN_PROB = 0, 1, 2
 FLAG_INCL, FLAG_SKIP_WD, FLAG_SKIP_DISC, FLAG_SKIP_BS, FLAG_SKIP_DONOR = 1, 2, 4, 8, 16
-ROCHE_XL1, ROCHE_FINDPHI, ROCHE_FINDI, ROCHE_BSPOT = 0, 1, 2, 3
+ROCHE_XL1, ROCHE_FINDPHI, ROCHE_FINDI, ROCHE_BSPOT, ROCHE_ANGLE = 0, 1, 2, 3, 4
 PRIOR_CODES = {"gauss": 0, "gaussPos": 1, "uniform": 2, "log_uniform": 3, "mod_jeff": 4}
 
 EXPORTS = (

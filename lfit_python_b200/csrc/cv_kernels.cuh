@@ -1545,7 +1545,11 @@ __global__ void roche_kernel(int which, long long n, const double* __restrict__ 
     double o[4] = {0.0, 0.0, 0.0, 0.0};
     int good = 0;
     Roche R;
-    if (roche_init(a[i], R)) {
+    if (which == LFB_ROCHE_ANGLE) {
+        // diagnostic: the solver's arctangent of a unit vector, o[0] = angle_of(a, b) for a = cos, b = sin
+        o[0] = angle_of(a[i], b[i]);
+        good = 1;
+    } else if (roche_init(a[i], R)) {
         if (which == LFB_ROCHE_XL1) {
             o[0] = R.xl1;
             good = 1;

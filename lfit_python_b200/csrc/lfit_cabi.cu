@@ -1588,7 +1588,7 @@ int lfb_ingress_egress(lfb_handle* h, long long n, const double* q, const double
 int lfb_roche(lfb_handle* h, int which, long long n, const double* a, const double* b, double* out, int* ok)
 {
     if (!h) return LFB_EINVAL;
-    if (which < LFB_ROCHE_XL1 || which > LFB_ROCHE_BSPOT || n < 0 || (n && (!a || !out || !ok)) ||
+    if (which < LFB_ROCHE_XL1 || which > LFB_ROCHE_ANGLE || n < 0 || (n && (!a || !out || !ok)) ||
         (n && which != LFB_ROCHE_XL1 && !b))
         return fail(h, LFB_EINVAL, "roche: bad arguments");
     if (n == 0) return LFB_OK;

@@ -19,6 +19,22 @@ def rel_flux_err(a, b):
     return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
 
 
+def test_angle_of_a_unit_vector(engine):
+    """The solver's replacement for atan2 (FP32 arctangent -> one of 129 tabulated angles -> arcsine series of
+    the remainder, roche_device.cuh: angle_of): every part of the circle, the seams between table rows, and
+    vectors that are unit only to rounding, as the Newton iteration leaves them."""
+    rng = np.random.default_rng(3)
+    seams = (np.arange(-64, 64) + 0.5) * np.pi / 64
+    ang = np.concatenate([rng.uniform(-np.pi, np.pi, 200000), seams, seams + 1e-9, seams - 1e-9,
+                          np.arange(-64, 65) * np.pi / 64 * (1 - 1e-16), [0.0, 1e-300, -1e-12, 3.0, -3.1]])
+    ang = ang[np.abs(ang) < np.pi - 1e-6]           # (at +-pi either sign of the answer is right: not compared)
+    norm = 1.0 + rng.uniform(-4e-16, 4e-16, ang.shape)
+    out, ok = engine.roche(_cabi.ROCHE_ANGLE, np.cos(ang) * norm, np.sin(ang) * norm)
+    assert ok.all()
+    ref = np.arctan2(np.sin(ang), np.cos(ang))
+    assert np.max(np.abs(out[:, 0] - ref)) < 1e-15
+
+
 def test_roche_scalars(engine):
     q = np.array([0.05, 0.1, 0.1037, 0.2, 0.5, 1.0, 2.5])
     out, ok = engine.roche(_cabi.ROCHE_XL1, q)
