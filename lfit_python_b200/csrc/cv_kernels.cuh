@@ -457,10 +457,10 @@ struct JobConst {
 // holds the sorted break points and the moments between them.
 struct DonorTable {
     unsigned short* first;  // [n][kDonorBins + 1] break points in the phase bins before bin g
-    double* key;            // [n][nb_max]         sorted break points (an opening one is nudged up by one ulp:
-                            //                     break point k applies to phase x iff key[k] <= x)
     double* mom;            // [n][nb_max + 1][6]  row k: moments (1, c, s, c^2, c s) after k break points, normalised
-                            //                     "at maximum light" (quadrature), then key[k] (+inf for the last row)
+                            //                     "at maximum light" (quadrature), then key[k], the sorted break point
+                            //                     that ends the row (+inf for the last row).  An opening break point
+                            //                     is nudged up by one ulp: break point k applies to phase x iff key[k] <= x
     int nb_max;             // 8 n_donor_q
 };
 
@@ -952,26 +952,28 @@ __global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __g
         }
     }
     __syncthreads();
-    // afterwards cnt[g + 1] = end of bin g; its start is the end of bin g - 1 (0 for bin 0): sort every bin
-    for (int g = tid; g < kDonorBins; g += kDonorThreads) {
+    // afterwards cnt[g + 1] = end of bin g; its start is the end of bin g - 1 (0 for bin 0).  Order inside a bin
+    // (a handful of break points at most): every break point counts those of its bin that come before it (ties
+    // by image, so the order is unique) and takes that place -- one thread per break point, back into the
+    // arrays the unsorted ones came from.
+    for (int i = tid; i < nb; i += kDonorThreads) {
+        const double k = skey[i];
+        const unsigned short id = sid[i];
+        const int g = donor_bin(k);
         const int b0 = g == 0 ? 0 : cnt[g], b1 = cnt[g + 1];
-        for (int i = b0 + 1; i < b1; ++i) {
-            const double k = skey[i];
-            const unsigned short id = sid[i];
-            int j = i - 1;
-            while (j >= b0 && (skey[j] > k || (skey[j] == k && sid[j] > id))) {
-                skey[j + 1] = skey[j];
-                sid[j + 1] = sid[j];
-                --j;
-            }
-            skey[j + 1] = k;
-            sid[j + 1] = id;
+        int before = 0;
+        for (int j = b0; j < b1; ++j) {
+            const double kj = skey[j];
+            before += (kj < k || (kj == k && sid[j] < id)) ? 1 : 0;
         }
+        ukey[b0 + before] = k;
+        uid[b0 + before] = id;
     }
     __syncthreads();
+    skey = ukey;  // (sorted now)
+    sid = uid;
     // ---- 3. moments after every break point: block scan in sorted order ----
     const double inv_norm = 1.0 / s_base[5];
-    double* key_out = A.dt.key + w * A.dt.nb_max;
     double* mom_out = A.dt.mom + w * (A.dt.nb_max + 1) * 6;
     // (row k: the moments after k break points, and in its sixth slot the break point that ends it)
     if (tid < 6) mom_out[tid] = tid < 5 ? s_base[tid] * inv_norm : (nb > 0 ? skey[0] : INFINITY);
@@ -1020,7 +1022,6 @@ __global__ void __launch_bounds__(kDonorThreads, 8) donor_table_kernel(const __g
             if (x < nb) {
                 const int id = sid[x];
                 donor_image_moments(qm + (id >> 3), NDQ, (id >> 1) & 3, (id & 1) ? -1.0 : 1.0, run);
-                key_out[x] = skey[x];
                 double2* row = (double2*)(mom_out + (size_t)(x + 1) * 6);
                 row[0] = make_double2(run[0] * inv_norm, run[1] * inv_norm);
                 row[1] = make_double2(run[2] * inv_norm, run[3] * inv_norm);

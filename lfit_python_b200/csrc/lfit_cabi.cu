@@ -544,13 +544,11 @@ static int run_batch(lfb_handle* h, Lane& ln, const DevLayout& L, SampleSet& ss,
         CK(ln.ivp.reserve(sizeof(EventRec) * (size_t)njobs * A.ni_total));
         CK(ln.chi_part.reserve(sizeof(double) * (size_t)njobs));
         CK(ln.dt_first.reserve(sizeof(unsigned short) * (size_t)n * (kDonorBins + 1)));
-        CK(ln.dt_key.reserve(sizeof(double) * (size_t)n * nb_max));
         CK(ln.dt_mom.reserve(sizeof(double) * (size_t)n * (nb_max + 1) * 6));
         A.jc = ln.jc.as<JobConst>();
         A.wq = ln.wq.as<long long>();
         A.ivp = ln.ivp.as<EventRec>();
         A.dt.first = ln.dt_first.as<unsigned short>();
-        A.dt.key = ln.dt_key.as<double>();
         A.dt.mom = ln.dt_mom.as<double>();
         A.dt.nb_max = (int)nb_max;
         A.chisq_job = ln.chi_part.as<double>();
