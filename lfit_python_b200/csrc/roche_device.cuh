@@ -903,7 +903,9 @@ LFB_HD bool bspot(const Roche& R, double rad, double out[4])
             for (int it = 0; it < 8; ++it) {
                 gbs_step(R, y, h, yn);
                 rn = sqrt(yn[0] * yn[0] + yn[1] * yn[1]);
-                h -= (rn - rad) * rn / (yn[0] * yn[2] + yn[1] * yn[3]);
+                const double dh = (rn - rad) * rn / (yn[0] * yn[2] + yn[1] * yn[3]);
+                h -= dh;
+                if (fabs(dh) <= 1e-8 * fabs(h)) break;  // quadratic convergence: the step after one this small is below rounding
             }
             gbs_step(R, y, h, yn);
             for (int j = 0; j < 4; ++j) out[j] = yn[j];
@@ -981,7 +983,9 @@ __device__ __forceinline__ bool bspot_lanes(const Roche& R, double rad, double o
             for (int it = 0; it < 8; ++it) {
                 gbs_step_lanes(R, y, h, yn);
                 rn = sqrt(yn[0] * yn[0] + yn[1] * yn[1]);
-                h -= (rn - rad) * rn / (yn[0] * yn[2] + yn[1] * yn[3]);
+                const double dh = (rn - rad) * rn / (yn[0] * yn[2] + yn[1] * yn[3]);
+                h -= dh;
+                if (fabs(dh) <= 1e-8 * fabs(h)) break;  // (the same test on the same numbers in every lane of the group)
             }
             gbs_step_lanes(R, y, h, yn);
             for (int j = 0; j < 4; ++j) out[j] = yn[j];
