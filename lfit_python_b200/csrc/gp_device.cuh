@@ -58,6 +58,7 @@ struct GpFilter {
     double m0, m1, m2, m3;                                    // state mean (f1, f1', f2, f2')
     double p00, p01, p11, p02, p03, p12, p13, p22, p23, p33;  // state covariance, upper triangle
     double xp, ll, sprod;
+    double t_dt, t_a, t_b, t_c, t_d, t_q00, t_q01, t_q11;  // the transition over the last spacing (see advance)
     double g_lo, g_hi;  // the first gap that does not end before the current point (times ascend)
     int gi, cur_gap, last_gap, k, nprod, dir;  // last_gap: gap of the last point stepped over (-1: none)
     bool bad;
@@ -87,6 +88,9 @@ struct GpFilter {
         sprod = 1.0;
         nprod = 0;
         gi = -1;
+        t_dt = -1.0;
+        t_a = t_d = 1.0;
+        t_b = t_c = t_q00 = t_q01 = t_q11 = 0.0;
         g_lo = g_hi = -INFINITY;
         next_gap(G);
     }
@@ -122,13 +126,25 @@ struct GpFilter {
                 bad = true;
                 return;
             }
-            const double ed = exp(-c * dt);
-            const double a = ed * (1.0 + c * dt), b = ed * dt, cc = -ed * c2 * dt, d = ed * (1.0 - c * dt);
+            // transition over dt: kept from the step before when the spacing repeats (regular sampling, up to the
+            // rounding of the phases: 1e-11 relative, far below anything the likelihood can see)
+            if (!(fabs(dt - t_dt) <= 1e-11 * dt)) {
+                const double ed = exp(-c * dt);
+                t_dt = dt;
+                t_a = ed * (1.0 + c * dt);
+                t_b = ed * dt;
+                t_c = -ed * c2 * dt;
+                t_d = ed * (1.0 - c * dt);
+                t_q00 = 1.0 - (t_a * t_a + t_b * t_b * c2);
+                t_q01 = -(t_a * t_c + t_b * t_d * c2);
+                t_q11 = c2 - (t_c * t_c + t_d * t_d * c2);
+            }
+            const double a = t_a, b = t_b, cc = t_c, d = t_d;
             // mean
             const double n0 = a * m0 + b * m1, n1 = cc * m0 + d * m1, n2 = a * m2 + b * m3, n3 = cc * m2 + d * m3;
             m0 = n0; m1 = n1; m2 = n2; m3 = n3;
             // process noise of a unit-variance Matern-3/2 state: Pinf - A Pinf A^T, Pinf = diag(1, c^2)
-            const double q00 = 1.0 - (a * a + b * b * c2), q01 = -(a * cc + b * d * c2), q11 = c2 - (cc * cc + d * d * c2);
+            const double q00 = t_q00, q01 = t_q01, q11 = t_q11;
             // covariance blocks: X <- A X A^T (+ Q)
             {
                 const double t00 = a * p00 + b * p01, t01 = a * p01 + b * p11, t10 = cc * p00 + d * p01, t11 = cc * p01 + d * p11;
