@@ -102,10 +102,10 @@ struct Lane {
     cudaEvent_t ev[ST_COUNT + 1] = {};
     cudaEvent_t kev[LFB_K_COUNT + 1] = {}, sev[2] = {};  // per-kernel trace (lfb_set_trace), side-stream pair
     bool kev_set[LFB_K_COUNT + 1] = {};
-    DevBuf ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, ivp, chi_part, gp_resid, dt_first, dt_key, dt_mom;
+    DevBuf ws, js, wd_io, don, disc_io, bs_io, bs_b, jc, wq, ivp, chi_part, gp_resid, dt_first, dt_mom;
     void track(unsigned long long* gen)
     {
-        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &ivp, &chi_part, &gp_resid, &dt_first, &dt_key, &dt_mom};
+        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &ivp, &chi_part, &gp_resid, &dt_first, &dt_mom};
         for (DevBuf* x : b) x->gen = gen;
     }
     cudaError_t create()
@@ -132,7 +132,7 @@ struct Lane {
     }
     void destroy()
     {
-        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &ivp, &chi_part, &gp_resid, &dt_first, &dt_key, &dt_mom};
+        DevBuf* b[] = {&ws, &js, &wd_io, &don, &disc_io, &bs_io, &bs_b, &jc, &wq, &ivp, &chi_part, &gp_resid, &dt_first, &dt_mom};
         for (DevBuf* x : b) x->release();
         for (int i = 0; i <= ST_COUNT; ++i)
             if (ev[i]) cudaEventDestroy(ev[i]);
