@@ -284,13 +284,18 @@ class Engine:
                                                   _dp(phase), _dp(width), _dp(y), _dp(ye)), "lfb_set_lightcurves")
 
     # -- hot path -----------------------------------------------------------------------
-    def log_prob(self, theta, what=LN_PROB, return_chisq=False):
-        """theta: (n, ndim) host array -> ln-values (n,) [and chisq (n, n_ecl)]."""
+    def log_prob(self, theta, what=LN_PROB, return_chisq=False, out=None):
+        """theta: (n, ndim) host array -> ln-values (n,) [and chisq (n, n_ecl)].  Page-locked arrays (e.g. the
+        .numpy() view of a pinned torch tensor) for theta and `out` are copied from / to as they stand; pageable
+        ones are staged through the engine's own pinned buffers."""
         theta = _f64(theta)
         if theta.ndim != 2 or theta.shape[1] != self.ndim:
             raise ValueError("Wrong vector length - Expected {}, got {}".format(self.ndim, theta.shape[-1]))
         n = theta.shape[0]
-        out = np.empty(n)
+        if out is None:
+            out = np.empty(n)
+        elif out.dtype != np.float64 or out.shape != (n,) or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 array of shape (n,)")
         chis = np.empty((n, self.n_ecl)) if return_chisq else None
         self._check(self._lib.lfb_log_prob(self._h, int(what), n, theta.ctypes.data, out.ctypes.data,
                                            chis.ctypes.data if return_chisq else None, None), "lfb_log_prob")

@@ -274,6 +274,18 @@ static bool is_device_ptr(const void* p)
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor): copies to and from it are
+// asynchronous as they stand, so it is not staged through the handle's own pinned buffers
+static bool is_pinned_host_ptr(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 static int upload(lfb_handle* h, DevBuf& b, const void* src, size_t bytes)
 {
     CK(b.reserve(bytes ? bytes : 8));
@@ -1254,6 +1266,7 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
     const size_t th_bytes = sizeof(double) * (size_t)n * (size_t)(h->ndim > 0 ? h->ndim : 1);
     const bool th_dev = is_device_ptr(theta), out_dev = is_device_ptr(out);
     const bool chi_dev = chisq_out && is_device_ptr(chisq_out);
+    const bool th_pinned = !th_dev && is_pinned_host_ptr(theta), out_pinned = !out_dev && is_pinned_host_ptr(out);
     const double* d_theta = theta;
     if (!th_dev) {
         // the previous call may have returned with its copy out of h_in still in flight (host theta, device
@@ -1261,7 +1274,7 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
         if (h->h2d_pending) CK(cudaEventSynchronize(h->t1_ev));
         h->h2d_pending = false;
         CK(h->theta.reserve(th_bytes));
-        CK(h->h_in.reserve(th_bytes));
+        if (!th_pinned) CK(h->h_in.reserve(th_bytes));
         d_theta = h->theta.as<double>();  // staged batch by batch below, so that a copy overlaps the batch before
     }
     double* d_out = out;
@@ -1320,8 +1333,12 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
             Lane& ln = h->lanes[0];
             CK(cudaStreamWaitEvent(ln.st, h->enter_ev, 0));
             if (!th_dev) {
-                memcpy(h->h_in.p, theta, sizeof(double) * (size_t)n * h->ndim);
-                CK(cudaMemcpyAsync(h->theta.p, h->h_in.p, sizeof(double) * (size_t)n * h->ndim, cudaMemcpyHostToDevice, ln.st));
+                const void* src = theta;
+                if (!th_pinned) {
+                    memcpy(h->h_in.p, theta, sizeof(double) * (size_t)n * h->ndim);
+                    src = h->h_in.p;
+                }
+                CK(cudaMemcpyAsync(h->theta.p, src, sizeof(double) * (size_t)n * h->ndim, cudaMemcpyHostToDevice, ln.st));
             }
             bool ok = ge->exec != nullptr;
             if (!ok) {
@@ -1370,8 +1387,12 @@ int lfb_log_prob(lfb_handle* h, int what, long long n, const double* theta, doub
         const long long nb = std::min(per, n - w0);
         if (!th_dev) {
             const size_t off = (size_t)w0 * h->ndim, cnt = sizeof(double) * (size_t)nb * h->ndim;
-            memcpy((double*)h->h_in.p + off, theta + off, cnt);
-            CK(cudaMemcpyAsync(h->theta.as<double>() + off, (double*)h->h_in.p + off, cnt, cudaMemcpyHostToDevice, ln.st));
+            const double* src = theta + off;  // page-locked memory of the caller's: copied from as it stands
+            if (!th_pinned) {
+                memcpy((double*)h->h_in.p + off, theta + off, cnt);
+                src = (const double*)h->h_in.p + off;
+            }
+            CK(cudaMemcpyAsync(h->theta.as<double>() + off, src, cnt, cudaMemcpyHostToDevice, ln.st));
         }
         const bool last_on_lane0 = (b % h->n_lanes) == 0 && w0 + (long long)h->n_lanes * per >= n;
         int rc = run_batch(h, ln, L, h->lc, what, 0, 0, nb, d_theta + w0 * h->ndim, d_out + w0, d_chi + w0 * h->n_ecl,
@@ -1391,17 +1412,20 @@ finished:
     CK(cudaEventRecord(h->t1_ev, st));
     h->ev_valid = true;
     if (!out_dev || (chisq_out && !chi_dev)) {
-        CK(h->h_out.reserve(sizeof(double) * (size_t)n));
-        if (!out_dev) CK(cudaMemcpyAsync(h->h_out.p, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (!out_pinned) CK(h->h_out.reserve(sizeof(double) * (size_t)n));
+        if (!out_dev) CK(cudaMemcpyAsync(out_pinned ? (void*)out : h->h_out.p, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
         if (chisq_out && !chi_dev) {
             CK(h->h_chisq.reserve(sizeof(double) * (size_t)njobs));
             CK(cudaMemcpyAsync(h->h_chisq.p, d_chi, sizeof(double) * (size_t)njobs, cudaMemcpyDeviceToHost, st));
         }
         CK(cudaStreamSynchronize(st));
-        if (!out_dev) memcpy(out, h->h_out.p, sizeof(double) * (size_t)n);
+        if (!out_dev && !out_pinned) memcpy(out, h->h_out.p, sizeof(double) * (size_t)n);
         if (chisq_out && !chi_dev) memcpy(chisq_out, h->h_chisq.p, sizeof(double) * (size_t)njobs);
     } else if (!th_dev) {
-        h->h2d_pending = true;
+        // host theta, device outputs: the call returns with work in flight.  A copy out of the caller's own
+        // page-locked buffer must be over before the caller may write there again: wait for it here
+        if (th_pinned) CK(cudaEventSynchronize(h->t1_ev));
+        else h->h2d_pending = true;
     }
     return LFB_OK;
 }

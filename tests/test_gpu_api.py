@@ -330,3 +330,31 @@ def test_small_repeated_calls_replay_a_cuda_graph_safely():
         assert np.array_equal(call(17), a[:17])
     finally:
         eng.close()
+
+
+def test_page_locked_host_buffers_are_used_as_they_stand():
+    """theta and the output in pinned host memory (copied from / to directly) give what pageable arrays give
+    (staged through the engine's own pinned buffers), bit for bit; so do device outputs with pinned theta."""
+    import torch
+    eng = _cabi.Engine(0)
+    wl = workloads.config(1, n_ph=150)
+    wl.make_data(lambda p, x, w: eng.calc_flux(p, x, w))
+    wl.apply(eng)
+    theta = wl.walkers(1500, scatter=0.05, seed=8)          # two lanes; some walkers outside the priors
+    ref, rchi = eng.log_prob(theta, return_chisq=True)
+    tp = torch.from_numpy(theta).pin_memory()
+    op = torch.empty(theta.shape[0], dtype=torch.float64).pin_memory()
+    for _ in range(3):                                      # (the third identical call may replay a graph)
+        op.fill_(7.0)
+        got = eng.log_prob(tp.numpy(), out=op.numpy())
+        assert got is not None and np.array_equal(op.numpy(), ref, equal_nan=True)
+    small = theta[:300]                                     # one batch: the CUDA-graph path
+    sp = torch.from_numpy(small).pin_memory()
+    for _ in range(4):
+        assert np.array_equal(eng.log_prob(sp.numpy()), ref[:300], equal_nan=True)
+    d_out = torch.empty(theta.shape[0], dtype=torch.float64, device="cuda")
+    eng.log_prob_device(tp.data_ptr(), theta.shape[0], d_out.data_ptr())
+    tp.fill_(0.0)                                           # the call has finished reading the pinned buffer
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), ref, equal_nan=True)
+    eng.close()
