@@ -136,6 +136,74 @@ def test_disc_curve_against_brute_force_visibility():
     assert 0.0 < got.min() < 0.9 and abs(got.max() - 1.0) < 1e-14
 
 
+def test_white_dwarf_curve_against_brute_force_visibility():
+    """PyWhiteDwarf-like curve from the oracle vs. a numpy restatement of DESIGN.md section 2 that never computes
+    ingress / egress: 4 n^2 equal-area tiles of the limb-darkened disc, fixed on the SKY (their position in the
+    rotating frame turns with the observer), weight (1 - u) + u <mu>_ring, dense potential sampling for visibility."""
+    q, inc, rwd, ulimb, n = 0.2, 80.5, 0.03, 0.45, 4
+    cfg = O.config(n_wd_rings=n, solver=O.SOLVER_ROBUST)
+    phases = np.array([-0.06, -0.037, -0.0355, -0.034, -0.0325, 0.0, 0.033, 0.0345, 0.036, 0.0375, 0.06])
+    pars = [1.0, 0, 0, 0, q, inc, 0.3, ulimb, rwd, 0.03, 120, 0.2, 0.5, 0.0]
+    st, got = O.calc_flux(pars, phases, None, cfg=cfg, flags=O.FLAG_INCL | O.SKIP_DISC | O.SKIP_BS | O.SKIP_DONOR)
+    assert st == 0
+    xl = O.xl1(q)
+    si, ci = np.sin(np.radians(inc)), np.cos(np.radians(inc))
+    sky, w = [], []
+    for k in range(n):
+        ra, rb = k / n, (k + 1) / n
+        ua, ub = 1 - ra * ra, 1 - rb * rb
+        mubar = (2.0 / 3.0) * (ua ** 1.5 - ub ** 1.5) / (rb * rb - ra * ra)
+        rho, nk = np.sqrt(0.5 * (ra * ra + rb * rb)), 4 * (2 * k + 1)
+        for j in range(nk):
+            a = (j + 0.5) * 2 * np.pi / nk
+            sky.append((rwd * xl * rho * np.cos(a), rwd * xl * rho * np.sin(a)))
+            w.append((1 - ulimb) + ulimb * mubar)
+    sky, w = np.array(sky), np.array(w)
+    ref = []
+    for ph in phases:
+        th = 2 * np.pi * ph
+        s, c = np.sin(th), np.cos(th)
+        # sky axes in the rotating frame: xi along (-sin th, -cos th, 0), eta along (-ci cos th, ci sin th, si)
+        pts = sky[:, :1] * np.array([[-s, -c, 0.0]]) + sky[:, 1:] * np.array([[-ci * c, ci * s, si]])
+        ref.append(w[~_blink(q, si, ci, pts, th, nlam=4000)].sum() / w.sum())
+    ref = np.array(ref)
+    assert np.allclose(got, ref, atol=1e-12)
+    assert abs(got[0] - 1.0) < 1e-14 and got[5] == 0.0 and np.sum((got > 0.05) & (got < 0.95)) >= 4  # ingress and egress are resolved
+
+
+def test_bright_spot_curve_against_brute_force_visibility():
+    """PySpot-like curve (complex bright spot) from the oracle vs. a numpy restatement: strip through the stream's
+    impact point along az, profile (s/smax)^exp1 exp(smax^exp2 - s^exp2), isotropic + beamed emission normalised to
+    its best alignment, dense potential sampling for visibility."""
+    q, inc, rdisc, scale, az, fis, exp1, exp2, tilt, yaw, nbs = 0.15, 82.0, 0.4, 0.03, 115.0, 0.3, 1.6, 1.3, 70.0, 12.0, 24
+    cfg = O.config(n_bs=nbs, solver=O.SOLVER_ROBUST)
+    phases = np.array([-0.2, -0.05, -0.03, -0.015, 0.0, 0.03, 0.06, 0.075, 0.09, 0.11, 0.3])
+    pars = [0, 0, 1.0, 0, q, inc, rdisc, 0.3, 0.02, scale, az, fis, 0.5, 0.0, exp1, exp2, tilt, yaw]
+    st, got = O.calc_flux(pars, phases, None, cfg=cfg, flags=O.FLAG_INCL | O.SKIP_WD | O.SKIP_DISC | O.SKIP_DONOR)
+    assert st == 0
+    xl = O.xl1(q)
+    si, ci = np.sin(np.radians(inc)), np.cos(np.radians(inc))
+    x0, y0 = O.bspot(q, rdisc * xl)[:2]
+    smax = (exp1 / exp2) ** (1 / exp2)
+    shi = min(20 + smax, (smax ** exp2 + 30) ** (1 / exp2))
+    sv = shi * np.arange(nbs) / (nbs - 1)
+    b = np.where(sv > 0, (sv / smax) ** exp1 * np.exp(smax ** exp2 - sv ** exp2), 0.0)
+    ln = (sv - smax) * scale * xl
+    pts = np.stack([x0 + ln * np.cos(np.radians(az)), y0 + ln * np.sin(np.radians(az)), np.zeros(nbs)], axis=1)
+    ta, pa = np.radians(tilt), np.radians(az - 90 + yaw)
+    bhat = np.array([np.sin(ta) * np.cos(pa), np.sin(ta) * np.sin(pa), np.cos(ta)])
+    norm = fis + (1 - fis) * max(0.0, np.cos(np.radians(inc - tilt)))
+    ref = []
+    for ph in phases:
+        th = 2 * np.pi * ph
+        earth = np.array([si * np.cos(th), -si * np.sin(th), ci])
+        beam = fis + (1 - fis) * max(0.0, float(bhat @ earth))
+        ref.append(beam / norm * b[~_blink(q, si, ci, pts, th, nlam=4000)].sum() / b.sum())
+    ref = np.array(ref)
+    assert np.allclose(got, ref, atol=1e-12)
+    assert got.min() < 0.2 and got.max() > 0.5   # the spot is eclipsed and seen
+
+
 def test_components_are_unit_normalised_and_add_up():
     """Out of eclipse each component is at its 'maximum light' scale and
     flux = wdFlux*ywd + dFlux*yd + sFlux*ys + rsFlux*yrs (testCV.py:59-65)."""
