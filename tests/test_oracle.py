@@ -204,6 +204,49 @@ def test_bright_spot_curve_against_brute_force_visibility():
     assert got.min() < 0.2 and got.max() > 0.5   # the spot is eclipsed and seen
 
 
+def test_donor_curve_against_numpy_restatement():
+    """PyDonor-like curve from the oracle vs. numpy with nothing shared: lobe radii by scipy's brentq, the outward
+    normal and |grad Phi| by central differences (so the oracle's analytic gradient is checked too), gravity
+    darkening |grad Phi|^0.32, linear limb darkening 0.8, normalised at quadrature."""
+    from scipy.optimize import brentq
+    q, inc, nth = 0.3, 78.0, 6
+    cfg = O.config(n_donor_th=nth)
+    phases = np.linspace(-0.5, 0.5, 41)
+    pars = [0, 0, 0, 1.0, q, inc, 0.3, 0.3, 0.02, 0.03, 120, 0.2, 0.5, 0.0]
+    st, got = O.calc_flux(pars, phases, None, cfg=cfg, flags=O.FLAG_INCL | O.SKIP_WD | O.SKIP_DISC | O.SKIP_BS)
+    assert st == 0
+    mu, xl = q / (1 + q), O.xl1(q)
+    pot = lambda x, y, z: (-(1 - mu) / np.sqrt(x * x + y * y + z * z) - mu / np.sqrt((x - 1) ** 2 + y * y + z * z)
+                           - 0.5 * ((x - mu) ** 2 + y * y))
+    phic, rs = pot(xl, 0.0, 0.0), 1 - xl
+    si, ci = np.sin(np.radians(inc)), np.cos(np.radians(inc))
+    nrm, wts = [], []
+    for k in range(nth):
+        th = (k + 0.5) * np.pi / nth
+        nph = 4 * int(max(1.0, np.floor(0.5 * nth * np.sin(th) + 0.5)))
+        for j in range(nph):
+            ph = (j + 0.5) * 2 * np.pi / nph
+            d = np.array([-np.cos(th), np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph)])
+            r = brentq(lambda rr: pot(1 + rr * d[0], rr * d[1], rr * d[2]) - phic, 0.02 * rs, rs, xtol=1e-15, rtol=1e-15)
+            p0, h = np.array([1.0, 0.0, 0.0]) + r * d, 1e-6
+            g = np.array([(pot(*(p0 + h * e)) - pot(*(p0 - h * e))) / (2 * h) for e in np.eye(3)])
+            gm = np.linalg.norm(g)
+            area = r * r * np.sin(th) * (np.pi / nth) * (2 * np.pi / nph) / float(g @ d / gm)
+            nrm.append(g / gm)
+            wts.append(area * gm ** 0.32)
+    nrm, wts = np.array(nrm), np.array(wts)
+
+    def curve(phase):
+        th = 2 * np.pi * phase
+        m = nrm @ np.array([si * np.cos(th), -si * np.sin(th), ci])
+        m = np.where(m > 0, m, 0.0)
+        return float(np.sum(wts * m * (1 - 0.8 + 0.8 * m)))
+
+    ref = np.array([curve(p) for p in phases]) / curve(0.25)
+    assert np.allclose(got, ref, rtol=2e-8)                  # (finite-difference gradients)
+    assert got.max() > 1.0 - 1e-9 and got.min() < 0.9        # ellipsoidal modulation, no eclipse of the donor
+
+
 def test_components_are_unit_normalised_and_add_up():
     """Out of eclipse each component is at its 'maximum light' scale and
     flux = wdFlux*ywd + dFlux*yd + sFlux*ys + rsFlux*yrs (testCV.py:59-65)."""
