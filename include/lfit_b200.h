@@ -158,7 +158,7 @@ int lfb_sampler_create(lfb_handle *h, long long nwalkers, double a, unsigned lon
 void lfb_sampler_destroy(lfb_sampler *s);
 /* Start positions pos[n][ndim] (host or device) and optionally their log-probabilities (NULL: evaluated). */
 int lfb_sampler_set_state(lfb_sampler *s, const double *pos, const double *lnp, void *stream);
-/* nsteps full steps on this GPU (nothing crosses PCIe; small ensembles replay one CUDA graph per step).
+/* nsteps full steps on this GPU (nothing crosses PCIe; ensembles whose half fits one batch replay one CUDA graph per step).
  * Asynchronous: lfb_sampler_get_state synchronises. */
 int lfb_sampler_run(lfb_sampler *s, long long nsteps, void *stream);
 /* Sharded ensemble (one process per GPU, the ensemble replicated): this rank proposes, evaluates and
@@ -198,7 +198,7 @@ long long lfb_robust_calls(lfb_handle *h);
 /* Device time (ms) of the stages of the last lfb_log_prob (its last batch), from CUDA events
  * recorded on the stream the kernels ran on; valid once that stream is synchronised.
  * out = {walker, stream, elements (4 launches), flux, finish, total}; the stages are -1 when the
- * call replayed a CUDA graph (small ensembles, from the third identical call on). */
+ * call replayed a CUDA graph (a call that fits one batch does, from its third identical occurrence on). */
 int lfb_last_stage_ms(lfb_handle *h, float out[6]);
 /* elements + flux of the same call, <0 if none */
 float lfb_last_kernel_ms(lfb_handle *h);
