@@ -44,7 +44,8 @@ int main(int argc, char** argv)
         lfo_roche Ro;
         lfb::roche_init(q, R);
         lfo_roche_init(&Ro, q);
-        double inc = 60 + urand() * 30, si = sin(inc * lfb::kDeg), ci = cos(inc * lfb::kDeg);
+        // (a quarter of the elements at low inclinations, where lines of sight pass over the lobe's pole)
+        double inc = (t % 4 == 0) ? 20 + urand() * 40 : 60 + urand() * 30, si = sin(inc * lfb::kDeg), ci = cos(inc * lfb::kDeg);
         lfb::Point T = {0, 0, 0, 0, 0};
         lfo_point To = {{0, 0, 0}, 0, 0};
         int kind = rand() % 3;
