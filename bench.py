@@ -8,7 +8,8 @@ A "step" is one pass of the hot path over one batch: ln_prob (priors + model + c
 mcmcfit.py:37-41) for every walker of the ensemble.  The default workload is BASELINE.json configs[1]
 (C2): one complex-BS eclipse, 2000 phase points, 4096 walkers, exposure-width smearing; --config 0..4
 selects the others.  Under torchrun the ranks shard the walkers and, per step, all-gather ONE packed
-buffer of positions + log-probs over NCCL, as a stretch-move half-step does:
+buffer of positions + log-probs (the engine's own exchange over NVLink peer memory; NCCL as the fallback),
+as a stretch-move half-step does:
 C1-C3 weak scaling (the config's walkers per GPU), C4 / C5 strong scaling (BASELINE names their total).
 
 Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM; `e2e` goes through the
@@ -370,7 +371,7 @@ def run_gpu(args, rank, local_rank, world):
     emcee["host_sampler_note"] = "numpy stretch move + one CUDA ln_prob call per half-step, host buffers, %d walkers per GPU" % n
     emcee["acceptance_fraction"] = float(hs.acceptance_fraction.mean())
     # (b) the ensemble resident in HBM: native stretch-move kernels, nothing crosses PCIe.  One GPU: the
-    # config's ensemble on this GPU; N GPUs: ONE ensemble sharded over the ranks, one packed NCCL all-gather per
+    # config's ensemble on this GPU; N GPUs: ONE ensemble sharded over the ranks, one exchange of packed rows per
     # half-step (weak configs: N x walkers in total; strong configs: the config's total)
     total_walkers = n * world
     if world == 1:

@@ -164,7 +164,7 @@ int lfb_sampler_run(lfb_sampler *s, long long nsteps, void *stream);
 /* Sharded ensemble (one process per GPU, the ensemble replicated): this rank proposes, evaluates and
  * accepts rows [lo, hi) of half `half` (0 or 1) into packed[hi - lo][ndim + 2] = (position, ln_prob,
  * accepted) on the device (NULL: the sampler's own buffer, lfb_sampler_packed); the caller all-gathers
- * the packed rows of all ranks (NCCL), then lfb_sampler_half_end writes gathered[world][slot][ndim + 2]
+ * the packed rows of all ranks (lfb_peer_allgather below, or NCCL), then lfb_sampler_half_end writes gathered[world][slot][ndim + 2]
  * (rank r's rows at gathered[r][0..]; balanced contiguous shards, lower ranks one row longer) into the
  * ensemble.  The second half's half_end ends the step. */
 int lfb_sampler_half_begin(lfb_sampler *s, int half, long long lo, long long hi, double *packed, void *stream);

@@ -2,8 +2,9 @@
 
 The reference spreads walkers over a multiprocessing.Pool (mcmcfit.py:273-288).  Here every
 rank holds the whole ensemble and the same random stream, evaluates a contiguous slice of each
-half-step's proposals on its own GPU, and an all-gather (NCCL over NVLink on device tensors;
-gloo on host tensors in the CPU tests) hands every rank all log-probabilities.  Walkers are
+half-step's proposals on its own GPU, and an all-gather hands every rank all log-probabilities: the
+engine's own exchange through NVLink peer memory (PeerExchange; device resident), NCCL on device
+tensors where the peers' windows cannot be mapped, gloo on host tensors in the CPU tests.  Walkers are
 independent, so an N-GPU run returns bit-for-bit what one GPU returns.
 """
 import numpy as np
@@ -128,7 +129,8 @@ class ShardedDeviceSampler:
     Every rank holds the whole ensemble in its HBM.  Per half-step a rank proposes, evaluates and
     accepts its contiguous slice of the half (lfb_sampler_half_begin) into a packed
     [rows, ndim + 2] buffer (new position, ln_prob, accepted); ONE all-gather of the packed rows
-    (NCCL over NVLink on the device buffers; gloo on host tensors in the CPU tests) hands every rank
+    (PeerExchange: the engine's own kernel over NVLink peer memory; NCCL on the device buffers as the
+    fallback; gloo on host tensors in the CPU tests) hands every rank
     the whole half, and lfb_sampler_half_end writes it into the replicated ensemble.  Nothing touches
     the host.  The draws are counter based (Philox keyed by seed, counted by step / half / walker), so
     N ranks follow the 1-GPU chain bit for bit.
